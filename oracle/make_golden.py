@@ -1,0 +1,317 @@
+"""Mint golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+TEST INFRASTRUCTURE.  The reference has no tests or fixtures of its own
+(SURVEY.md section 4), so parity is pinned against the reference itself: this
+script imports it (oracle/ref_shim.py), records every RNG draw it makes by
+wrapping `np.random.randint` / `np.random.random` (the envs look them up through
+the `np.random` namespace at call time, Game2048_env.py:19-20) and
+`random.random` / `random.randint` (tabular agent, main.py:35-36), and stores
+inputs + outputs as small .npz files.  The committed files are what
+tests/test_oracle_golden.py (CPU) and tests/test_gpu_parity.py (GPU) replay.
+
+Files
+  env_penalty.npz    QLearningBase/environment/Game2048_env.py        (penalty flavour)
+  env_nopenalty.npz  Deep_QLearning/environment/Game2048_nopenalty_env.py under the
+                     caller protocol of mainDQL_CNN_step2.py:163-237 (caller commits the board)
+  qlearn_ref.npz     QLearningBase/Agent/main.py QLearningAgent driven by the loop main.py:80-109
+"""
+from __future__ import annotations
+
+import os
+import random as pyrandom
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_shim  # noqa: E402
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+N_ENVS = 96
+N_STEPS = 384
+PEN_SAT = 25
+
+
+def pack_board(tiles) -> int:
+    b = 0
+    for j, v in enumerate(np.asarray(tiles).reshape(16)):
+        v = int(v)
+        lvl = v.bit_length() - 1 if v else 0
+        assert v == 0 or (1 << lvl) == v and 1 <= lvl <= 15, v
+        b |= lvl << (4 * j)
+    return b
+
+
+class DrawRecorder:
+    """Wraps np.random.randint / np.random.random; every call is logged."""
+
+    def __init__(self):
+        self.log = []
+        self._ri, self._rr = np.random.randint, np.random.random
+
+    def __enter__(self):
+        def randint(low, high=None, *a, **k):
+            v = self._ri(low, high, *a, **k)
+            self.log.append(("i", int(v), int(high)))
+            return v
+
+        def rnd(*a, **k):
+            v = self._rr(*a, **k)
+            self.log.append(("f", float(v)))
+            return v
+
+        np.random.randint, np.random.random = randint, rnd
+        return self
+
+    def __exit__(self, *exc):
+        np.random.randint, np.random.random = self._ri, self._rr
+
+    def take(self):
+        out, self.log = self.log, []
+        return out
+
+
+def spawn_pairs(log):
+    """[(k, is4), ...] from a draw log that must be (randint, random) pairs."""
+    assert len(log) % 2 == 0, log
+    pairs = []
+    for i in range(0, len(log), 2):
+        assert log[i][0] == "i" and log[i + 1][0] == "f", log
+        pairs.append((log[i][1], 0 if log[i + 1][1] < 0.9 else 1))
+    return pairs
+
+
+def teleport_board(rs: np.random.RandomState, lmax: int) -> np.ndarray:
+    """A random mid/late-game board (raw tile values) with max level <= lmax."""
+    p_zero = rs.choice([0.0, 0.0, 0.1, 0.3])
+    lv = rs.randint(1, min(lmax, 14) + 1, size=16)  # at most one level-15 tile: 65536 is unrepresentable
+    lv[rs.randint(0, 16)] = lmax
+    lv = np.where(rs.random_sample(16) < p_zero, 0, lv)
+    if rs.random_sample() < 0.35:  # checkerboard-ish dead board
+        cap = min(lmax, 14)
+        a, b = rs.randint(1, cap + 1), rs.randint(1, cap + 1)
+        if a == b:
+            b = a % cap + 1 if cap > 1 else a
+        if a != b:
+            lv = np.array([[a, b, a, b], [b, a, b, a], [a, b, a, b], [b, a, b, a]]).reshape(16)
+            for _ in range(rs.randint(0, 4)):
+                lv[rs.randint(0, 16)] = rs.randint(1, cap + 1)
+    board = np.where(lv > 0, 2 ** lv.astype(np.int64), 0).reshape(4, 4)
+    if not board.any():
+        board[0, 0] = 2
+    return board.astype(np.int64)
+
+
+def policy_action(kind: str, rs: np.random.RandomState, last: int | None) -> int:
+    if kind == "uniform" or last is None:
+        return int(rs.randint(0, 4))
+    if kind == "sticky":  # long same-action runs: stall penalty and >100 termination
+        return last if rs.random_sample() < 0.985 else int(rs.randint(0, 4))
+    if kind == "corner":  # mostly left/up, reaches higher tiles
+        return int(rs.choice([0, 1, 0, 1, 0, 1, 2, 3]))
+    raise ValueError(kind)
+
+
+def env_kind(i: int) -> tuple[str, bool]:
+    """(policy, teleport) of golden env i."""
+    if i < 40:
+        return "uniform", False
+    if i < 56:
+        return "sticky", False
+    if i < 64:
+        return "corner", False
+    if i < 88:
+        return "uniform", True
+    return "sticky", True
+
+
+def record_env(flavour: str):
+    mod = ref_shim.load_penalty_env() if flavour == "penalty" else ref_shim.load_nopenalty_env()
+    E, T = N_ENVS, N_STEPS
+    g = {
+        "board_in": np.zeros((E, T), np.uint64), "reload": np.zeros((E, T), np.uint8),
+        "action": np.zeros((E, T), np.uint8), "draws": np.full((E, T, 4), 255, np.uint8),
+        "board_out": np.zeros((E, T), np.uint64), "reward": np.zeros((E, T), np.float64),
+        "flags": np.zeros((E, T), np.uint8), "maxlvl": np.zeros((E, T), np.uint8),
+        "move_score": np.zeros((E, T), np.int32), "env_score": np.zeros((E, T), np.int32),
+        "aux_out": np.zeros((E, T), np.uint64), "last_pen": np.zeros((E, T), np.float64),
+    }
+    reset_draws, reset_boards = [], []
+    pen_table = [-1.0]
+    for _ in range(64):
+        pen_table.append(max(pen_table[-1] * 1.1, -10))
+
+    # capture (moved, score) of every Game2048.move and the result of is_game_over
+    calls = {}
+    orig_move, orig_over = mod.Game2048.move, mod.Game2048.is_game_over
+
+    def move_wrap(self, *a, **k):
+        res = orig_move(self, *a, **k)
+        calls.setdefault("move", []).append((a, k, (bool(res[0]), int(res[1]))))
+        return res
+
+    def over_wrap(self):
+        calls["in_over"] = True
+        n0 = len(calls.get("move", []))
+        res = orig_over(self)
+        calls["over"] = bool(res)
+        calls["over_moves"] = calls.get("move", [])[n0:]
+        del calls["move"][n0:]
+        calls["in_over"] = False
+        return res
+
+    mod.Game2048.move, mod.Game2048.is_game_over = move_wrap, over_wrap
+    try:
+        with DrawRecorder() as rec:
+            for i in range(E):
+                kind, tele = env_kind(i)
+                np.random.seed(1000 + i)
+                rs = np.random.RandomState(2000 + i)
+                env = mod.Game2048_env()
+                rec.take()
+                episode = 0
+                fresh = True
+                last = None
+                for t in range(T):
+                    if fresh and tele:
+                        lmax = int(min(15, 2 + episode // 2 + rs.randint(0, 3)))
+                        env.game.board = teleport_board(rs, lmax)
+                    b_in = pack_board(env.game.board)
+                    g["board_in"][i, t] = b_in
+                    g["reload"][i, t] = 1 if fresh else 0
+                    fresh = False
+                    full_before = not (np.asarray(env.game.board) == 0).any()
+                    a = policy_action(kind, rs, last)
+                    last = a
+                    calls.clear()
+                    board, reward, done, max_number = env.step(a)
+                    log = rec.take()
+                    (margs, mkw, (valid, mscore)) = calls["move"][0]
+                    assert margs[0] == a
+                    game_over = calls["over"]
+                    pairs = spawn_pairs(log)
+                    d = [255, 255, 255, 255]
+                    if flavour == "penalty":
+                        # [spawn of the move if valid] + [phantom spawn if the new board is full and alive]
+                        if valid:
+                            d[0], d[1] = pairs[0]
+                        assert len(pairs) == int(valid) + int(len(calls["over_moves"]) > 0 and not game_over)
+                    else:
+                        # [spawn of the move if valid] + [quirk spawn if S was full and alive]
+                        if valid:
+                            d[0], d[1] = pairs[0]
+                        if full_before and not game_over:
+                            d[2], d[3] = pairs[-1]
+                        assert len(pairs) == int(valid) + int(full_before and not game_over)
+                        env.game.board = board  # caller commit, mainDQL_CNN_step2.py:237
+                    g["action"][i, t] = a
+                    g["draws"][i, t] = d
+                    g["board_out"][i, t] = pack_board(board)
+                    g["reward"][i, t] = float(reward)
+                    g["flags"][i, t] = int(valid) | (int(game_over) << 1) | (int(bool(done)) << 2)
+                    g["maxlvl"][i, t] = int(max_number).bit_length() - 1
+                    g["move_score"][i, t] = mscore
+                    g["env_score"][i, t] = int(env.score)
+                    if flavour == "penalty":
+                        ca = 255 if env.consecutive_action is None else int(env.consecutive_action)
+                        lp = float(env.last_consecutive_penalty)
+                        pen_idx = min(pen_table.index(lp), PEN_SAT)
+                        prev_level = int(env.previous_max).bit_length() - 1
+                        g["aux_out"][i, t] = prev_level | (ca << 8) | (pen_idx << 16) | (int(env.consecutive_count) << 32)
+                        g["last_pen"][i, t] = lp
+                    if done:
+                        env.reset()
+                        rp = spawn_pairs(rec.take())
+                        assert len(rp) == 2
+                        reset_draws.append([rp[0][0], rp[0][1], rp[1][0], rp[1][1]])
+                        reset_boards.append(pack_board(env.game.board))
+                        episode += 1
+                        fresh = True
+    finally:
+        mod.Game2048.move, mod.Game2048.is_game_over = orig_move, orig_over
+    g["reset_draws"] = np.array(reset_draws, np.uint8).reshape(-1, 4)
+    g["reset_board"] = np.array(reset_boards, np.uint64)
+    return g
+
+
+def record_qlearn(episodes: int = 150):
+    """The loop of main.py:80-109 on the reference agent + penalty env."""
+    penv = ref_shim.load_penalty_env()
+    agent_mod = ref_shim.load_tabular_agent()
+    np.random.seed(0)
+    pyrandom.seed(0)
+    env = penv.Game2048_env()
+    agent = agent_mod.QLearningAgent(episodes, action_space=env.action_space.n, learning_rate=0.1,
+                                     discount_factor=0.99, exploration_rate=0.95)
+    agent_draws = []
+    orig_r, orig_i = pyrandom.random, pyrandom.randint
+
+    def r_wrap():
+        v = orig_r()
+        agent_draws.append(("f", v))
+        return v
+
+    def i_wrap(a, b):
+        v = orig_i(a, b)
+        agent_draws.append(("i", v))
+        return v
+
+    pyrandom.random, pyrandom.randint = r_wrap, i_wrap
+    S, A, R, S2, D, EXP, RA, EP = [], [], [], [], [], [], [], []
+    eps_hist = []
+    try:
+        for episode in range(episodes):
+            eps_hist.append(agent.epsilon)
+            state = tuple(map(tuple, env.reset()))
+            done = False
+            while not done:
+                del agent_draws[:]
+                action = agent.choose_action(state)
+                explore = agent_draws[0][1] < agent.epsilon
+                ra = agent_draws[1][1] if explore else 255
+                next_state, reward, done, info = env.step(action)
+                next_state = tuple(map(tuple, next_state))
+                _ = agent.q_table[state]  # main.py:96 (insert side effect)
+                agent.update_q_value(state, action, reward, next_state, done)
+                S.append(pack_board(state)); A.append(int(action)); R.append(float(reward))
+                S2.append(pack_board(next_state)); D.append(int(bool(done)))
+                EXP.append(int(explore)); RA.append(int(ra)); EP.append(episode)
+                state = next_state
+            agent.decay_exploration(episode)
+    finally:
+        pyrandom.random, pyrandom.randint = orig_r, orig_i
+    eps_hist.append(agent.epsilon)
+    keys = np.array([pack_board(k) for k in agent.q_table.keys()], np.uint64)
+    rows = np.array([np.asarray(v, np.float64) for v in agent.q_table.values()], np.float64).reshape(-1, 4)
+    order = np.argsort(keys)
+    return {
+        "s": np.array(S, np.uint64), "a": np.array(A, np.uint8), "r": np.array(R, np.float64),
+        "s2": np.array(S2, np.uint64), "done": np.array(D, np.uint8), "explore": np.array(EXP, np.uint8),
+        "rand_action": np.array(RA, np.uint8), "episode": np.array(EP, np.int32),
+        "eps": np.array(eps_hist, np.float64), "q_keys": keys[order], "q_rows": rows[order],
+        "params": np.array([episodes, 0.1, 0.99, 0.95, 0.01], np.float64),
+    }
+
+
+def main():
+    if not ref_shim.available():
+        raise SystemExit(f"reference not found under {ref_shim.REF_ROOT}")
+    os.makedirs(OUT_DIR, exist_ok=True)
+    for flavour in ("penalty", "nopenalty"):
+        g = record_env(flavour)
+        path = os.path.join(OUT_DIR, f"env_{flavour}.npz")
+        np.savez_compressed(path, **g)
+        fl = g["flags"]
+        print(f"{path}: {fl.size} steps, valid {np.mean(fl & 1):.3f}, game_over {int(np.sum((fl >> 1) & 1))}, "
+              f"done {int(np.sum((fl >> 2) & 1))}, resets {len(g['reset_board'])}, max level {int(g['maxlvl'].max())}, "
+              f"{os.path.getsize(path) / 1e3:.0f} kB")
+    q = record_qlearn()
+    path = os.path.join(OUT_DIR, "qlearn_ref.npz")
+    np.savez_compressed(path, **q)
+    print(f"{path}: {len(q['s'])} transitions, {len(q['q_keys'])} states, {os.path.getsize(path) / 1e3:.0f} kB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""The CPU oracle (oracle/g2048_oracle.c) against golden vectors recorded from the reference itself.
+
+The goldens were produced by oracle/make_golden.py importing the unmodified reference
+(QLearningBase/environment/Game2048_env.py, Deep_QLearning/environment/Game2048_nopenalty_env.py,
+QLearningBase/Agent/main.py).  Everything here is bit-exact: boards, flags, scores, aux state and the
+float64 shaped reward (same libm expressions in the same order).
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def replay_env(g, flavour, step_fn):
+    """Carried replay: the implementation keeps its own boards/aux/score across steps; boards are
+    reloaded only where the golden says a new episode (reset/teleport) starts."""
+    E, T = g["action"].shape
+    boards = g["board_in"][:, 0].copy()
+    aux = np.full(E, oracle.AUX_INIT, np.uint64)
+    score = np.zeros(E, np.int32)
+    for t in range(T):
+        reload = g["reload"][:, t].astype(bool)
+        boards[reload] = g["board_in"][reload, t]
+        if t:
+            prev_done = (g["flags"][:, t - 1] >> 2) & 1
+            score[prev_done.astype(bool)] = 0  # env.reset() zeroes env.score (Game2048_env.py:190)
+        assert np.array_equal(boards, g["board_in"][:, t]), f"carried board differs at step {t}"
+        reward, flags, maxlvl, ms = step_fn(boards, aux, score, np.ascontiguousarray(g["action"][:, t]),
+                                            np.ascontiguousarray(g["draws"][:, t]), flavour)
+        assert np.array_equal(boards, g["board_out"][:, t]), f"board_out step {t}"
+        assert np.array_equal(flags & 7, g["flags"][:, t]), f"flags step {t}"
+        assert np.array_equal(maxlvl, g["maxlvl"][:, t]), f"maxlvl step {t}"
+        assert np.array_equal(ms, g["move_score"][:, t]), f"move_score step {t}"
+        assert np.array_equal(score, g["env_score"][:, t]), f"env.score step {t}"
+        assert np.array_equal(reward.view(np.uint64), g["reward"][:, t].view(np.uint64)), f"reward bits step {t}"
+        if flavour == oracle.FLAVOUR_PENALTY:
+            assert np.array_equal(aux, g["aux_out"][:, t]), f"aux step {t}"
+
+
+def oracle_step(boards, aux, score, actions, draws, flavour):
+    return oracle.env_step(boards, aux, score, actions, draws, flavour)
+
+
+@pytest.mark.parametrize("name,flavour", [("env_penalty", oracle.FLAVOUR_PENALTY),
+                                          ("env_nopenalty", oracle.FLAVOUR_NOPENALTY)])
+def test_env_step_matches_reference(golden, name, flavour):
+    g = golden(name)
+    replay_env(g, flavour, oracle_step)
+
+
+def test_golden_covers_the_branches(golden):
+    g = golden("env_penalty")
+    fl, lv = g["flags"], g["maxlvl"]
+    assert ((fl >> 2) & 1).sum() > 100 and ((fl >> 1) & 1).sum() > 100
+    assert lv.max() == 15 and (lv >= 9).sum() > 1000                     # the >=512 reward terms
+    assert ((g["aux_out"] >> np.uint64(32)) > 100).any()                  # stall termination
+    assert (((g["aux_out"] >> np.uint64(16)) & np.uint64(0xFF)) == 25).any()  # saturated stall penalty
+    assert (g["reward"] < -10).any() and (g["reward"] == 10).any()
+    over_hi = (((fl >> 1) & 1) == 1) & ((fl & 1) == 0) & (lv >= 9) & (lv <= 11)
+    assert over_hi.any()                                                  # game over on 512/1024/2048
+    n = golden("env_nopenalty")
+    quirk = n["draws"][:, :, 2] != 255
+    assert quirk.sum() > 100                                              # full-board quirk (App. A.3)
+    assert ((n["flags"] & 1) == 0)[quirk].any()                           # ... also on an invalid agent move
+
+
+@pytest.mark.parametrize("name", ["env_penalty", "env_nopenalty"])
+def test_reset_matches_reference(golden, name):
+    g = golden(name)
+    boards = np.zeros(len(g["reset_board"]), np.uint64)
+    score = np.ones(len(boards), np.int32)
+    oracle.env_reset(boards, score, None, np.ascontiguousarray(g["reset_draws"]))
+    assert np.array_equal(boards, g["reset_board"])
+    assert not score.any()
+
+
+def test_stall_penalty_table():
+    lib = oracle.load()
+    p, ref = -1, []
+    for _ in range(40):  # Game2048_env.py:124-125
+        p = max(p * 1.1, -10)
+        ref.append(float(p))
+    got = [lib.orc_stall_penalty(k) for k in range(1, 41)]
+    assert got == ref
+    assert got[oracle.PEN_SAT - 2] > -10 and got[oracle.PEN_SAT - 1] == -10
+
+
+def test_tabular_agent_matches_reference(golden):
+    g = golden("qlearn_ref")
+    episodes, lr, gamma, eps0, eps_min = g["params"]
+    tab = oracle.QTable(1 << 17, f32=False)
+    actions = tab.replay_agent_f64(g["s"], g["explore"], g["rand_action"], g["r"], g["s2"], g["done"], lr, gamma)
+    assert np.array_equal(actions, g["a"])           # greedy choices (first-max argmax) follow the reference
+    keys, rows = tab.export()
+    assert np.array_equal(keys, g["q_keys"])         # same set of states (defaultdict inserts on read)
+    assert np.array_equal(rows.view(np.uint64), g["q_rows"].view(np.uint64))  # float64 bit-exact
+
+    tab2 = oracle.QTable(1 << 17, f32=False)
+    tab2.update_seq_f64(g["s"], g["a"], g["r"], g["s2"], g["done"], lr, gamma)
+    assert np.array_equal(tab2.export()[1].view(np.uint64), g["q_rows"].view(np.uint64))
+
+
+def test_epsilon_schedule_matches_reference(golden):
+    g = golden("qlearn_ref")
+    episodes, lr, gamma, eps0, eps_min = g["params"]
+    sched = oracle.decay_exploration_schedule(int(episodes), eps0, eps_min)
+    assert np.array_equal(sched.view(np.uint64), g["eps"].view(np.uint64))
+
+
+def test_batch_update_n1_is_sequential_update(golden):
+    """Batched synchronous float32 update with N = 1 per call == update_q_value in float32."""
+    g = golden("qlearn_ref")
+    n = 4000
+    lr, gamma = np.float32(0.1), np.float32(0.99)
+    tab = oracle.QTable(1 << 15, f32=True)
+    ref = {}
+    r32 = g["r"].astype(np.float32)
+    for i in range(n):
+        s, a, s2, d = int(g["s"][i]), int(g["a"][i]), int(g["s2"][i]), int(g["done"][i])
+        tab.update_batch_f32(g["s"][i:i + 1], g["a"][i:i + 1], r32[i:i + 1], g["s2"][i:i + 1], g["done"][i:i + 1],
+                             float(lr), float(gamma))
+        q2 = ref.setdefault(s2, np.zeros(4, np.float32))
+        q = ref.setdefault(s, np.zeros(4, np.float32))
+        target = r32[i] + (np.float32(0) if d else gamma * q2.max())
+        q[a] = q[a] + lr * (target - q[a])
+    keys, rows = tab.export()
+    assert len(keys) == len(ref)
+    for k, row in zip(keys, rows):
+        assert np.array_equal(row.astype(np.float32), ref[int(k)])
+    # and float32 stays within the stated tolerance of the reference's float64 table
+    tab64 = oracle.QTable(1 << 15, f32=False)
+    tab64.update_seq_f64(g["s"][:n], g["a"][:n], g["r"][:n], g["s2"][:n], g["done"][:n], 0.1, 0.99)
+    k64, r64 = tab64.export()
+    assert np.array_equal(k64, keys)
+    np.testing.assert_allclose(rows, r64, rtol=1e-5, atol=1e-5)
