@@ -1,0 +1,132 @@
+"""ctypes binding of libg2048.so (include/g2048.h).  No CPU fallback: if the library is missing and
+cannot be built, or a compute call is made without a CUDA device, the call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "libg2048.so")
+SOURCES = [os.path.join(_HERE, "csrc", "g2048.cu")]
+DEPENDS = SOURCES + [os.path.join(_HERE, "csrc", "g2048_device.cuh"), os.path.join(ROOT, "include", "g2048.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "-diag-suppress", "550,177"]
+
+
+class G2048Error(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise G2048Error("nvcc not found: libg2048.so cannot be built (there is no CPU fallback)")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (cross-compiles without a GPU)."""
+    stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(SO_PATH) for d in DEPENDS)
+    if force or stale:
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + SOURCES
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise G2048Error("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    return SO_PATH
+
+
+def declared_symbols() -> list[str]:
+    """Every entry point include/g2048.h declares."""
+    text = open(os.path.join(ROOT, "include", "g2048.h")).read()
+    return sorted(set(re.findall(r"G2048_API\s+[\w\s\*]+?\b(g2048_\w+)\s*\(", text)))
+
+
+_lib = None
+vp, i64, u64, i32, f32, f64, sz = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_float, C.c_double, C.c_size_t
+_SIG = {
+    "g2048_version": (i32, []),
+    "g2048_last_error": (C.c_char_p, []),
+    "g2048_init": (i32, [i32]),
+    "g2048_device_count": (i32, []),
+    "g2048_host_alloc": (vp, [sz]),
+    "g2048_host_free": (None, [vp]),
+    "g2048_env_reset": (i32, [vp, vp, vp, vp, i64, u64, u64, u64, vp]),
+    "g2048_env_step": (i32, [vp] * 10 + [i64, i32, u64, u64, u64, vp]),
+    "g2048_move_trial": (i32, [vp, vp, vp, vp, vp, i64, vp]),
+    "g2048_legal_mask": (i32, [vp, vp, i64, vp]),
+    "g2048_pack_i64": (i32, [vp, vp, i64, vp, vp]),
+    "g2048_unpack_i64": (i32, [vp, vp, i64, vp]),
+    "g2048_encode_onehot": (i32, [vp, vp, i64, i32, vp]),
+    "g2048_select_action": (i32, [vp, vp, vp, i64, f64, u64, u64, u64, vp]),
+    "g2048_rollout_random": (i32, [vp, vp, vp, i64, i64, i32, u64, u64, u64, vp, vp]),
+    "g2048_rollout_qlearn": (i32, [vp, vp, vp, vp, u64, i64, i64, i32, f32, f32, f64, u64, u64, u64, vp, vp]),
+    "g2048_qlearn_scratch_bytes": (sz, [i64]),
+    "g2048_qlearn_step": (i32, [vp, vp, vp, vp, u64, i64, i32, f32, f32, f64, i32, i32, u64, u64, u64, vp, vp, vp, vp,
+                                vp, sz, vp]),
+    "g2048_qtable_bytes": (sz, [u64]),
+    "g2048_qtable_clear": (i32, [vp, u64, vp]),
+    "g2048_qtable_lookup": (i32, [vp, u64, vp, i64, vp, vp, i32, vp]),
+    "g2048_choose_action": (i32, [vp, u64, vp, vp, i64, f64, u64, u64, u64, vp]),
+    "g2048_qtable_update": (i32, [vp, u64, vp, vp, vp, vp, vp, i64, f32, f32, i32, vp, sz, vp]),
+    "g2048_qtable_apply_deltas": (i32, [vp, u64, vp, vp, vp, i64, i32, vp, sz, vp]),
+    "g2048_qtable_size": (i32, [vp, u64, vp, vp]),
+    "g2048_qtable_export": (i32, [vp, u64, vp, vp, i64, vp, vp]),
+    "g2048_ctx_create": (vp, [i32, i64, u64]),
+    "g2048_ctx_destroy": (None, [vp]),
+    "g2048_ctx_env_reset": (i32, [vp, vp, vp, vp, vp, i64, u64, u64, u64]),
+    "g2048_ctx_env_step": (i32, [vp] * 10 + [i64, i32, u64, u64, u64]),
+    "g2048_ctx_legal_mask": (i32, [vp, vp, vp, i64]),
+    "g2048_ctx_move_trial": (i32, [vp, vp, vp, vp, vp, vp, i64]),
+    "g2048_ctx_rollout_random": (i32, [vp, vp, vp, vp, i64, i64, i32, u64, u64, u64, vp]),
+    "g2048_ctx_rollout_qlearn": (i32, [vp, vp, vp, vp, i64, i64, i32, f32, f32, f64, u64, u64, u64, vp]),
+    "g2048_ctx_qtable_lookup": (i32, [vp, vp, i64, vp, vp, i32]),
+    "g2048_ctx_choose_action": (i32, [vp, vp, vp, i64, f64, u64, u64, u64]),
+    "g2048_ctx_qtable_update": (i32, [vp, vp, vp, vp, vp, vp, i64, f32, f32, i32]),
+    "g2048_ctx_qtable_size": (i64, [vp]),
+    "g2048_ctx_qtable_export": (i64, [vp, vp, vp, i64]),
+    "g2048_ctx_qtable_clear": (i32, [vp]),
+    "g2048_ctx_table": (vp, [vp]),
+    "g2048_ctx_table_capacity": (u64, [vp]),
+    "g2048_ctx_stream": (vp, [vp]),
+}
+
+
+def lib():
+    """Load (building first if needed) libg2048.so and attach the prototypes."""
+    global _lib
+    if _lib is None:
+        path = build()
+        try:
+            handle = C.CDLL(path)
+        except OSError as e:  # e.g. libcudart missing
+            raise G2048Error(f"cannot load {path}: {e} (there is no CPU fallback)") from e
+        for name, (res, args) in _SIG.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().g2048_last_error().decode(errors="replace")
+        raise G2048Error(f"{what or 'g2048'} failed with code {rc}: {msg}")
+
+
+_inited: set[int] = set()
+
+
+def init(device: int = 0) -> None:
+    """g2048_init(device): raises if there is no usable CUDA device."""
+    if device not in _inited:
+        L = lib()
+        if L.g2048_device_count() <= device:
+            raise G2048Error(f"CUDA device {device} not available: the g2048 hot path has no CPU fallback")
+        check(L.g2048_init(device), "g2048_init")
+        _inited.add(device)

@@ -1,0 +1,1165 @@
+// g2048.cu -- kernels and C ABI of libg2048.so (see include/g2048.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+//
+// Kernels
+//   k_env_step        one step per env, state in HBM (HBM-bound: 22 / 38 B per step)
+//   k_rollout_random  K steps per env with the board in registers, row LUT staged in shared memory by
+//                     one bulk-async (TMA) copy, Philox spawn, in-kernel reset
+//   k_rollout_qlearn  the same loop with epsilon-greedy choose_action and the TD update on the HBM hash
+//                     table fused in (one 32-byte sector read + one float RED per step)
+//   k_qlearn_phase_a / k_q_update_phase_a / k_keys_to_records + k_apply_atomic / CUB radix sort +
+//   k_segment_apply   synchronous batched update, atomic and deterministic modes
+//   k_q_lookup, k_choose_action, k_q_size, k_q_export, k_legal_mask, k_pack, k_unpack, k_onehot,
+//   k_select_action
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_bf16.h>
+
+#include "g2048_device.cuh"
+
+using namespace g2048;
+
+// ============================================================================================ host state
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* what) {
+    if (code > 0)
+        snprintf(g_err, sizeof g_err, "%s: %s (%s)", what, cudaGetErrorString((cudaError_t)code),
+                 cudaGetErrorName((cudaError_t)code));
+    else
+        snprintf(g_err, sizeof g_err, "%s (code %d)", what, code);
+    return code;
+}
+#define CK(expr)                                       \
+    do {                                               \
+        cudaError_t e_ = (expr);                       \
+        if (e_ != cudaSuccess) return fail((int)e_, #expr); \
+    } while (0)
+
+constexpr int kMaxDevices = 64;
+constexpr size_t kLutRowBytes = 65536 * sizeof(uint16_t);
+constexpr size_t kLutBytes = kLutRowBytes + 65536;  // row table followed by the merged-level table
+constexpr int kRolloutThreads = 1024;
+
+struct DeviceState {
+    bool ready = false;
+    Tables tables{};
+    void* lut = nullptr;      // kLutBytes, 128-byte aligned
+    int sm_count = 0;
+};
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mu;
+
+// ---- host-side table construction -------------------------------------------------------------------
+// Row table: move_left on one row (Game2048_env.py:25-41) for all 65,536 rows.
+void build_row_tables(std::vector<uint16_t>& row, std::vector<uint8_t>& merged) {
+    row.resize(65536);
+    merged.resize(65536);
+    for (unsigned r = 0; r < 65536; ++r) {
+        int t[4] = {(int)(r & 15), (int)((r >> 4) & 15), (int)((r >> 8) & 15), (int)((r >> 12) & 15)};
+        int packed[4], n = 0;
+        for (int c = 0; c < 4; ++c)
+            if (t[c]) packed[n++] = t[c];
+        int out[4] = {0, 0, 0, 0}, m = 0, mg[2] = {0, 0}, k = 0;
+        for (int i = 0; i < n; ++i) {
+            bool pair = (i + 1 < n) && packed[i] == packed[i + 1] && packed[i] < 15;  // 2^16 does not fit a nibble
+            if (pair) { out[m++] = packed[i] + 1; mg[k++] = packed[i] + 1; ++i; }
+            else out[m++] = packed[i];
+        }
+        row[r] = (uint16_t)(out[0] | (out[1] << 4) | (out[2] << 8) | (out[3] << 12));
+        int hi = mg[0] > mg[1] ? mg[0] : mg[1], lo = mg[0] > mg[1] ? mg[1] : mg[0];
+        merged[r] = (uint8_t)((hi << 4) | lo);
+    }
+}
+// update_and_normalize (Game2048_env.py:197-205), same libm calls as CPython's math.log2
+double normalize_reward(double reward) {
+    if (reward >= 0) return std::fmin(std::log2(reward + 1), 10);
+    return -std::fmin(std::log2(std::fabs(reward - 1)), 10);
+}
+// calculate_reward (Game2048_env.py:136-184) tabulated over (level, progress step d, score/4).
+// The float64 expression order follows the reference statement by statement so that every entry has the
+// bits the Python code produces on the same host.
+void build_reward_tables(std::vector<double>& valid, std::vector<double>& invalid, std::vector<double>& pen) {
+    valid.assign(16 * 16 * 256, 0.0);
+    invalid.assign(2 * 16 * 16, 0.0);
+    for (int lvl = 1; lvl < 16; ++lvl)
+        for (int d = 0; d < 16; ++d) {
+            if (d > lvl - 1) continue;  // previous level = lvl - d >= 1
+            double current_level = (double)lvl;
+            double bonus = 0;
+            if (d > 0) bonus = (current_level - (double)(lvl - d)) * std::pow(current_level, 1.2);  // :148-149
+            for (int over = 0; over < 2; ++over) {
+                double reward = 0;
+                if (over) {
+                    if (lvl == 9 || lvl == 10 || lvl == 11) reward = bonus + std::pow(current_level, 1.2);  // :156-158
+                    else reward -= std::log2((double)((1ll << lvl) + 1));                                      // :160
+                } else {
+                    reward -= 0.1 * current_level;                                                             // :164
+                }
+                invalid[over * 256 + lvl * 16 + d] = normalize_reward(reward);
+            }
+            for (int s4 = 0; s4 < 256; ++s4) {
+                double reward = (double)(4 * s4);                                   // :168
+                if (bonus > 0) reward += bonus;                                     // :171-172
+                else if (bonus == 0) reward += current_level * 0.05;                // :173-174
+                if (lvl >= 9) reward += std::pow(current_level, 1.2) * 2;           // :176-177
+                valid[(lvl * 16 + d) * 256 + s4] = normalize_reward(reward);
+            }
+        }
+    pen.assign(32, -10.0);
+    double p = -1;                                                                  // :95
+    pen[0] = p;
+    for (int i = 1; i < 32; ++i) {                                                  // :124
+        double q = p * 1.1;
+        p = q > -10 ? q : -10;
+        pen[i] = p;
+    }
+}
+
+int current_device_state(DeviceState** out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices || !g_dev[dev].ready) return fail(G2048_ERR_NOINIT, "g2048_init(device) not called");
+    *out = &g_dev[dev];
+    return 0;
+}
+inline cudaStream_t S(void* stream) { return (cudaStream_t)stream; }
+inline int grid_for(int64_t n, int block, int sm_count, int per_sm = 8) {
+    int64_t g = (n + block - 1) / block;
+    int64_t cap = (int64_t)sm_count * per_sm;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+inline u64 eps_threshold(double eps) {
+    if (!(eps > 0)) return 0;
+    if (eps >= 1) return 1ull << 32;
+    return (u64)(eps * 4294967296.0);
+}
+inline bool pow2(uint64_t c) { return c && !(c & (c - 1)); }
+
+}  // namespace
+
+// ============================================================================================ kernels
+namespace {
+
+__device__ __forceinline__ Lut global_lut(const Tables& T) { return Lut{T.lut_row, T.lut_merged}; }
+
+// Stage the 192 KB row LUT into dynamic shared memory with one bulk-async copy (TMA, UBLKCP) completing
+// on an mbarrier; every thread then waits on phase 0.
+__device__ __forceinline__ Lut stage_lut(const Tables& T, unsigned char* smem) {
+    __shared__ __align__(8) unsigned long long mbar;
+    u32 bar = (u32)__cvta_generic_to_shared(&mbar);
+    u32 dst = (u32)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((u32)kLutBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(T.lut_row), "r"((u32)kLutBytes), "r"(bar)
+                     : "memory");
+    }
+    u32 ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar)
+            : "memory");
+    }
+    return Lut{reinterpret_cast<const uint16_t*>(smem), smem + kLutRowBytes};
+}
+
+template <bool REPLAY>
+__global__ void k_env_reset(u64* boards, int* score, const uint8_t* mask, const uint8_t* draws, long long n, u64 seed,
+                            u64 episode, u64 id_base) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (mask && !mask[i]) continue;
+        u64 b;
+        if (REPLAY) {
+            uchar4 d = reinterpret_cast<const uchar4*>(draws)[i];
+            b = fresh_board<true>(d.x, d.y, d.z, d.w);
+        } else {
+            Draw4 x = philox(seed, id_base + (u64)i, episode, G2048_STREAM_RESET);
+            b = fresh_board<false>(x.x0, x.x1, x.x2, x.x3);
+        }
+        boards[i] = b;
+        if (score) score[i] = 0;
+    }
+}
+
+template <int FLAVOUR, bool REPLAY>
+__global__ void __launch_bounds__(256)
+k_env_step(Tables T, u64* boards, u64* aux, int* score, const uint8_t* actions, const uint8_t* draws, double* rew64,
+           float* rew32, uint8_t* flags, uint8_t* maxlvl, int* move_score, long long n, u64 seed, u64 t, u64 id_base) {
+    Lut L = global_lut(T);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Env e;
+        e.board = boards[i];
+        env_from_aux(e, (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT);
+        e.score = score ? score[i] : 0;
+        int a = actions[i] & 3;
+        StepOut o;
+        if (REPLAY) {
+            uchar4 d = reinterpret_cast<const uchar4*>(draws)[i];
+            if (FLAVOUR == G2048_FLAVOUR_PENALTY) penalty_step<true>(e, a, d.x, d.y, L, T, o);
+            else nopenalty_step<true>(e, a, d.x, d.y, d.z, d.w, L, o);
+        } else {
+            Draw4 x = philox(seed, id_base + (u64)i, t, G2048_STREAM_STEP);
+            philox_step<FLAVOUR>(e, a, x, seed, id_base + (u64)i, t, L, T, o);
+        }
+        boards[i] = e.board;
+        if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
+        if (score) score[i] = e.score;
+        if (rew64) rew64[i] = o.reward;
+        if (rew32) rew32[i] = (float)o.reward;
+        if (flags)
+            flags[i] = (uint8_t)((o.valid ? G2048_FLAG_VALID : 0) | (o.game_over ? G2048_FLAG_GAME_OVER : 0) |
+                                 (o.done ? G2048_FLAG_DONE : 0) | (legal_mask(e.board) << 4));
+        if (maxlvl) maxlvl[i] = (uint8_t)o.maxlvl;
+        if (move_score) move_score[i] = o.move_score;
+    }
+}
+
+template <int FLAVOUR>
+__global__ void __launch_bounds__(kRolloutThreads, 1)
+k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long long k_steps, u64 seed, u64 step_base,
+                 u64 id_base, long long* counters, int smem_lut) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Lut L = smem_lut ? stage_lut(T, smem) : global_lut(T);
+    Counters c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Env e;
+        e.board = boards[i];
+        env_from_aux(e, (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT);
+        e.score = score ? score[i] : 0;
+        u64 id = id_base + (u64)i;
+        for (long long k = 0; k < k_steps; ++k) {
+            u64 t = step_base + (u64)k;
+            Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
+            StepOut o;
+            philox_step<FLAVOUR>(e, (int)(x.x3 >> 30), x, seed, id, t, L, T, o);
+            c.add(o);
+            if (o.done) philox_autoreset(e, seed, id, t);
+        }
+        boards[i] = e.board;
+        if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
+        if (score) score[i] = e.score;
+    }
+    flush_counters(c, counters);
+}
+
+// main.py:91-101 fused.  Per step: Philox -> epsilon-greedy from the carried row of s -> env step ->
+// find-or-insert s' (one 32-byte sector) -> RED.ADD on Q[s][a] -> carry (slot, row) of s' as the next s.
+template <int FLAVOUR>
+__global__ void __launch_bounds__(kRolloutThreads, 1)
+k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mask, long long n, long long k_steps,
+                 float lr, float gamma, u64 eps_thresh, u64 seed, u64 step_base, u64 id_base, long long* counters,
+                 int smem_lut) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Lut L = smem_lut ? stage_lut(T, smem) : global_lut(T);
+    Counters c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Env e;
+        e.board = boards[i];
+        env_from_aux(e, (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT);
+        e.score = score ? score[i] : 0;
+        u64 id = id_base + (u64)i;
+        float4 row;
+        int ins = 0;
+        u32 slot = table_find<true>(tab, mask, e.board, row, ins);
+        c.dropped += (slot == kNoSlot);
+        for (long long k = 0; k < k_steps; ++k) {
+            u64 t = step_base + (u64)k;
+            Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
+            int a = choose_action(row, x, eps_thresh);
+            StepOut o;
+            philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
+            c.add(o);
+            float4 row2 = row;
+            u32 slot2 = slot;
+            if (o.valid || FLAVOUR == G2048_FLAVOUR_NOPENALTY) {  // an invalid ENV-P move leaves s' == s
+                slot2 = table_find<true>(tab, mask, e.board, row2, ins);
+                c.dropped += (slot2 == kNoSlot);
+            }
+            if (slot != kNoSlot) {
+                float q_sa = q_at(row, a);
+                float delta = td_delta(lr, gamma, (float)o.reward, max4(row2), o.done, q_sa);
+                atomicAdd(&tab[slot].q[a], delta);
+                if (slot2 == slot) q_set(row2, a, __fadd_rn(q_sa, delta));
+            }
+            row = row2;
+            slot = slot2;
+            if (o.done) {
+                philox_autoreset(e, seed, id, t);
+                slot = table_find<true>(tab, mask, e.board, row, ins);
+                c.dropped += (slot == kNoSlot);
+            }
+        }
+        boards[i] = e.board;
+        if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
+        if (score) score[i] = e.score;
+        c.inserts += ins;
+    }
+    flush_counters(c, counters);
+}
+
+// Synchronous step, phase A: choose + env step + bootstrap on the snapshot; emits one record per env:
+// sort key = slot * 4 + action (all ones = no slot), delta, and optionally (state key, action).
+template <int FLAVOUR>
+__global__ void __launch_bounds__(256)
+k_qlearn_phase_a(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mask, long long n, float lr, float gamma,
+                 u64 eps_thresh, u64 seed, u64 t, u64 id_base, long long* counters, u64* sortkey, float* delta_out,
+                 u64* rec_key, uint8_t* rec_action, float* rec_delta) {
+    Lut L = global_lut(T);
+    Counters c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Env e;
+        e.board = boards[i];
+        env_from_aux(e, (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT);
+        e.score = score ? score[i] : 0;
+        u64 id = id_base + (u64)i;
+        float4 row, row2;
+        int ins = 0;
+        u64 s_key = e.board;
+        u32 slot = table_find<true>(tab, mask, s_key, row, ins);
+        c.dropped += (slot == kNoSlot);
+        Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
+        int a = choose_action(row, x, eps_thresh);
+        StepOut o;
+        philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
+        c.add(o);
+        u32 slot2 = table_find<true>(tab, mask, e.board, row2, ins);
+        c.dropped += (slot2 == kNoSlot);
+        float delta = td_delta(lr, gamma, (float)o.reward, max4(row2), o.done, q_at(row, a));
+        if (sortkey) sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)a);
+        if (delta_out) delta_out[i] = delta;
+        if (rec_key) rec_key[i] = s_key;
+        if (rec_action) rec_action[i] = (uint8_t)a;
+        if (rec_delta) rec_delta[i] = delta;
+        if (o.done) philox_autoreset(e, seed, id, t);
+        boards[i] = e.board;
+        if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
+        if (score) score[i] = e.score;
+        c.inserts += ins;
+    }
+    flush_counters(c, counters);
+}
+
+// update_q_value phase A on given transitions (teacher-forced): reads only, emits sort key + delta
+__global__ void __launch_bounds__(256)
+k_q_update_phase_a(Slot* tab, u64 mask, const u64* s, const uint8_t* a, const float* r, const u64* s2,
+                   const uint8_t* done, long long n, float lr, float gamma, u64* sortkey, float* delta_out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float4 row, row2;
+        int ins = 0;
+        table_find<true>(tab, mask, s2[i], row2, ins);
+        u32 slot = table_find<true>(tab, mask, s[i], row, ins);
+        int act = a[i] & 3;
+        sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)act);
+        delta_out[i] = td_delta(lr, gamma, r[i], max4(row2), done[i] != 0, q_at(row, act));
+    }
+}
+// (key, action, delta) records -> sort key (find-or-insert the key)
+__global__ void __launch_bounds__(256)
+k_keys_to_records(Slot* tab, u64 mask, const u64* keys, const uint8_t* a, long long n, u64* sortkey) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float4 row;
+        int ins = 0;
+        u32 slot = table_find<true>(tab, mask, keys[i], row, ins);
+        sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)(a[i] & 3));
+    }
+}
+__global__ void __launch_bounds__(256) k_apply_atomic(Slot* tab, const u64* sortkey, const float* delta, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        u64 k = sortkey[i];
+        if (k != ~0ull) atomicAdd(&tab[k >> 2].q[k & 3], delta[i]);
+    }
+}
+// sorted (stable) records: the head of every run sums its run in order and adds it to Q once
+__global__ void __launch_bounds__(256) k_segment_apply(Slot* tab, const u64* sortkey, const float* delta, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        u64 k = sortkey[i];
+        if (k == ~0ull || (i > 0 && sortkey[i - 1] == k)) continue;
+        float acc = delta[i];
+        for (long long j = i + 1; j < n && sortkey[j] == k; ++j) acc = __fadd_rn(acc, delta[j]);
+        float* q = &tab[k >> 2].q[k & 3];
+        *q = __fadd_rn(*q, acc);
+    }
+}
+
+template <bool INSERT>
+__global__ void __launch_bounds__(256)
+k_q_lookup(Slot* tab, u64 mask, const u64* keys, long long n, float4* rows, uint8_t* found) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float4 row;
+        int ins = 0;
+        u32 slot = table_find<INSERT>(tab, mask, keys[i], row, ins);
+        rows[i] = row;
+        if (found) found[i] = (slot != kNoSlot) && !ins;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_choose_action(Slot* tab, u64 mask, const u64* boards, uint8_t* actions, long long n, u64 eps_thresh, u64 seed, u64 t,
+                u64 id_base) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float4 row;
+        int ins = 0;
+        table_find<true>(tab, mask, boards[i], row, ins);
+        Draw4 x = philox(seed, id_base + (u64)i, t, G2048_STREAM_STEP);
+        actions[i] = (uint8_t)choose_action(row, x, eps_thresh);
+    }
+}
+__global__ void __launch_bounds__(256) k_q_size(const Slot* tab, u64 capacity, long long* count) {
+    long long c = 0;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < capacity; i += (u64)gridDim.x * blockDim.x)
+        c += __ldcg(&tab[i].key) != 0;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long*)count, (unsigned long long)c);
+}
+__global__ void __launch_bounds__(256)
+k_q_export(const Slot* tab, u64 capacity, u64* keys, float4* rows, long long max_out, long long* count) {
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < capacity; i += (u64)gridDim.x * blockDim.x) {
+        u64 k;
+        float4 q;
+        load_slot(tab + i, k, q);
+        if (k) {
+            long long j = (long long)atomicAdd((unsigned long long*)count, 1ull);
+            if (j < max_out) { keys[j] = k; rows[j] = q; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_move_trial(Tables T, const u64* in, const uint8_t* actions, u64* out, uint8_t* moved, int* move_score, long long n) {
+    Lut L = global_lut(T);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        u64 r;
+        u32 mm;
+        bool mv = do_move(in[i], actions[i] & 3, L, r, mm);
+        if (out) out[i] = r;
+        if (moved) moved[i] = mv;
+        if (move_score) move_score[i] = merge_score(mm);
+    }
+}
+__global__ void __launch_bounds__(256) k_legal_mask(const u64* boards, uint8_t* out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (uint8_t)legal_mask(boards[i]);
+}
+// one thread per cell: coalesced 8-byte tile reads, the 16 lanes of a board OR their nibbles together
+__global__ void __launch_bounds__(256) k_pack(const long long* tiles, u64* boards, long long n, long long* bad) {
+    long long total = n * 16;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < ((total + 31) & ~31ll);
+         j += (long long)gridDim.x * blockDim.x) {
+        long long v = j < total ? tiles[j] : 0;
+        int lvl = 0, is_bad = 0;
+        if (v != 0) {
+            lvl = 63 - __clzll(v);
+            if (v < 0 || (1ll << lvl) != v || lvl < 1 || lvl > 15) { is_bad = 1; lvl = 0; }
+        }
+        u64 nib = (u64)lvl << (4 * (j & 15));
+#pragma unroll
+        for (int s = 8; s > 0; s >>= 1) nib |= __shfl_xor_sync(0xFFFFFFFFu, nib, s);
+        if ((j & 15) == 0 && j < total) boards[j >> 4] = nib;
+        if (is_bad && bad) atomicAdd((unsigned long long*)bad, 1ull);
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack(const u64* boards, long long* tiles, long long n) {
+    long long total = n * 16;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
+        int lvl = (int)((boards[j >> 4] >> (4 * (j & 15))) & 15);
+        tiles[j] = lvl ? (1ll << lvl) : 0;
+    }
+}
+// encode_state: out[n][16][4][4]; one thread writes 4 consecutive cells (one row of one level plane)
+template <typename T4, typename MakeT4>
+__device__ __forceinline__ void onehot_body(const u64* boards, T4* out, long long n, MakeT4 mk) {
+    long long total = n * 64;  // 64 groups of 4 cells per board
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
+        u64 b = boards[j >> 6];
+        int lvl = (int)((j >> 2) & 15), r = (int)(j & 3);
+        u32 rowbits = (u32)(b >> (16 * r)) & 0xFFFFu;
+        out[j] = mk((rowbits & 15) == (u32)lvl, ((rowbits >> 4) & 15) == (u32)lvl, ((rowbits >> 8) & 15) == (u32)lvl,
+                    ((rowbits >> 12) & 15) == (u32)lvl);
+    }
+}
+__global__ void __launch_bounds__(256) k_onehot_f32(const u64* boards, float4* out, long long n) {
+    onehot_body(boards, out, n, [](bool a, bool b, bool c, bool d) {
+        return make_float4(a ? 1.f : 0.f, b ? 1.f : 0.f, c ? 1.f : 0.f, d ? 1.f : 0.f);
+    });
+}
+__global__ void __launch_bounds__(256) k_onehot_bf16(const u64* boards, uint2* out, long long n) {
+    onehot_body(boards, out, n, [](bool a, bool b, bool c, bool d) {  // bf16 1.0 = 0x3F80
+        return make_uint2((a ? 0x3F80u : 0u) | (b ? 0x3F800000u : 0u), (c ? 0x3F80u : 0u) | (d ? 0x3F800000u : 0u));
+    });
+}
+// act / act_ripetitive (Dqn8TestNOPERCNN.py:312-336)
+__global__ void __launch_bounds__(256)
+k_select_action(const float4* qv, const uint8_t* legal, uint8_t* actions, long long n, u64 eps_thresh, u64 seed, u64 t,
+                u64 id_base) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Draw4 x = philox(seed, id_base + (u64)i, t, G2048_STREAM_STEP);
+        u32 lm = legal ? (legal[i] & 15u) : 0u;
+        bool explore = (u64)x.x2 < eps_thresh;
+        int act;
+        if (lm == 0) {  // act(), or act_ripetitive with no legal move
+            act = explore ? (int)(x.x3 >> 30) : argmax4(qv[i]);
+        } else if (explore) {  // np.random.choice(legal_moves)
+            int j = (int)__umulhi(x.x3, (u32)__popc(lm));
+            u32 m = lm;
+            for (int s = 0; s < j; ++s) m &= m - 1;
+            act = __ffs((int)m) - 1;
+        } else {  // argmax over the legal moves, first maximum in ascending action order
+            float4 q = qv[i];
+            act = -1;
+            float best = 0.f;
+            for (int c = 0; c < 4; ++c)
+                if ((lm >> c) & 1u) {
+                    float v = q_at(q, c);
+                    if (act < 0 || v > best) { best = v; act = c; }
+                }
+        }
+        actions[i] = (uint8_t)act;
+    }
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+G2048_API int g2048_version(void) { return G2048_VERSION; }
+G2048_API const char* g2048_last_error(void) { return g_err; }
+G2048_API int g2048_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+G2048_API void* g2048_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { fail((int)cudaGetLastError(), "cudaHostAlloc"); return nullptr; }
+    return p;
+}
+G2048_API void g2048_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+G2048_API int g2048_init(int device) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (device < 0 || device >= kMaxDevices) return fail(G2048_ERR_ARG, "g2048_init: bad device index");
+    CK(cudaSetDevice(device));
+    DeviceState& d = g_dev[device];
+    if (d.ready) return 0;
+    std::vector<uint16_t> row;
+    std::vector<uint8_t> merged;
+    std::vector<double> valid, invalid, pen;
+    build_row_tables(row, merged);
+    build_reward_tables(valid, invalid, pen);
+    void *lut = nullptr, *rv = nullptr, *ri = nullptr, *pn = nullptr;
+    CK(cudaMalloc(&lut, kLutBytes));
+    CK(cudaMalloc(&rv, valid.size() * sizeof(double)));
+    CK(cudaMalloc(&ri, invalid.size() * sizeof(double)));
+    CK(cudaMalloc(&pn, pen.size() * sizeof(double)));
+    CK(cudaMemcpy(lut, row.data(), kLutRowBytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((char*)lut + kLutRowBytes, merged.data(), 65536, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rv, valid.data(), valid.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ri, invalid.data(), invalid.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pn, pen.data(), pen.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.lut = lut;
+    d.tables = Tables{(const uint16_t*)lut, (const uint8_t*)lut + kLutRowBytes, (const double*)rv, (const double*)ri,
+                      (const double*)pn};
+    CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaFuncSetAttribute(k_rollout_random<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_random<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_qlearn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_qlearn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    d.ready = true;
+    return 0;
+}
+
+#define DEVSTATE()                         \
+    DeviceState* D = nullptr;              \
+    {                                      \
+        int rc_ = current_device_state(&D); \
+        if (rc_) return rc_;               \
+    }
+#define LAUNCH_CHECK(what)                                   \
+    do {                                                     \
+        cudaError_t e_ = cudaGetLastError();                 \
+        if (e_ != cudaSuccess) return fail((int)e_, what);   \
+    } while (0)
+
+G2048_API int g2048_env_reset(uint64_t* boards, int32_t* score, const uint8_t* mask, const uint8_t* replay_draws,
+                              int64_t n, uint64_t seed, uint64_t episode_idx, uint64_t env_id_base, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && !boards)) return fail(G2048_ERR_ARG, "g2048_env_reset: bad arguments");
+    if (n == 0) return 0;
+    int g = grid_for(n, 256, D->sm_count);
+    if (replay_draws)
+        k_env_reset<true><<<g, 256, 0, S(stream)>>>((u64*)boards, score, mask, replay_draws, n, seed, episode_idx, env_id_base);
+    else
+        k_env_reset<false><<<g, 256, 0, S(stream)>>>((u64*)boards, score, mask, nullptr, n, seed, episode_idx, env_id_base);
+    LAUNCH_CHECK("k_env_reset");
+    return 0;
+}
+
+G2048_API int g2048_env_step(uint64_t* boards, uint64_t* aux, int32_t* score, const uint8_t* actions,
+                             const uint8_t* replay_draws, double* reward_f64, float* reward_f32, uint8_t* flags,
+                             uint8_t* maxlvl, int32_t* move_score, int64_t n, int flavour, uint64_t seed,
+                             uint64_t step_idx, uint64_t env_id_base, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!boards || !actions)) || (flavour != 0 && flavour != 1))
+        return fail(G2048_ERR_ARG, "g2048_env_step: bad arguments");
+    if (n == 0) return 0;
+    int g = grid_for(n, 256, D->sm_count);
+#define STEP(F, R)                                                                                                   \
+    k_env_step<F, R><<<g, 256, 0, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, actions, replay_draws,     \
+                                               reward_f64, reward_f32, flags, maxlvl, move_score, n, seed, step_idx, \
+                                               env_id_base)
+    if (flavour == 0) { if (replay_draws) STEP(0, true); else STEP(0, false); }
+    else { if (replay_draws) STEP(1, true); else STEP(1, false); }
+#undef STEP
+    LAUNCH_CHECK("k_env_step");
+    return 0;
+}
+
+G2048_API int g2048_move_trial(const uint64_t* boards_in, const uint8_t* actions, uint64_t* out_boards, uint8_t* moved,
+                               int32_t* move_score, int64_t n, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!boards_in || !actions))) return fail(G2048_ERR_ARG, "g2048_move_trial: bad arguments");
+    if (n == 0) return 0;
+    k_move_trial<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>(D->tables, (const u64*)boards_in, actions,
+                                                                        (u64*)out_boards, moved, move_score, n);
+    LAUNCH_CHECK("k_move_trial");
+    return 0;
+}
+G2048_API int g2048_legal_mask(const uint64_t* boards, uint8_t* out, int64_t n, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!boards || !out))) return fail(G2048_ERR_ARG, "g2048_legal_mask: bad arguments");
+    if (n == 0) return 0;
+    k_legal_mask<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((const u64*)boards, out, n);
+    LAUNCH_CHECK("k_legal_mask");
+    return 0;
+}
+G2048_API int g2048_pack_i64(const int64_t* tiles, uint64_t* boards, int64_t n, int64_t* bad_count, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!tiles || !boards))) return fail(G2048_ERR_ARG, "g2048_pack_i64: bad arguments");
+    if (n == 0) return 0;
+    k_pack<<<grid_for(n * 16, 256, D->sm_count), 256, 0, S(stream)>>>((const long long*)tiles, (u64*)boards, n,
+                                                                       (long long*)bad_count);
+    LAUNCH_CHECK("k_pack");
+    return 0;
+}
+G2048_API int g2048_unpack_i64(const uint64_t* boards, int64_t* tiles, int64_t n, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!tiles || !boards))) return fail(G2048_ERR_ARG, "g2048_unpack_i64: bad arguments");
+    if (n == 0) return 0;
+    k_unpack<<<grid_for(n * 16, 256, D->sm_count), 256, 0, S(stream)>>>((const u64*)boards, (long long*)tiles, n);
+    LAUNCH_CHECK("k_unpack");
+    return 0;
+}
+G2048_API int g2048_encode_onehot(const uint64_t* boards, void* out, int64_t n, int dtype, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!boards || !out)) || (dtype != G2048_DTYPE_F32 && dtype != G2048_DTYPE_BF16))
+        return fail(G2048_ERR_ARG, "g2048_encode_onehot: bad arguments");
+    if (n == 0) return 0;
+    int g = grid_for(n * 64, 256, D->sm_count, 16);
+    if (dtype == G2048_DTYPE_F32) k_onehot_f32<<<g, 256, 0, S(stream)>>>((const u64*)boards, (float4*)out, n);
+    else k_onehot_bf16<<<g, 256, 0, S(stream)>>>((const u64*)boards, (uint2*)out, n);
+    LAUNCH_CHECK("k_onehot");
+    return 0;
+}
+G2048_API int g2048_select_action(const float* qvalues, const uint8_t* legal_mask, uint8_t* actions, int64_t n,
+                                  double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!qvalues || !actions))) return fail(G2048_ERR_ARG, "g2048_select_action: bad arguments");
+    if (n == 0) return 0;
+    k_select_action<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((const float4*)qvalues, legal_mask, actions, n,
+                                                                           eps_threshold(eps), seed, step_idx, env_id_base);
+    LAUNCH_CHECK("k_select_action");
+    return 0;
+}
+
+// fused rollouts: one persistent CTA per SM with the LUT in shared memory once there is enough work to
+// amortise the 192 KB staging copy; small batches read the LUT through L1 instead.
+static inline void rollout_geometry(const DeviceState* D, int64_t n, int& grid, int& block, int& smem_lut, size_t& smem) {
+    if (n >= 16384) {
+        block = kRolloutThreads;
+        grid = (int)((n + block - 1) / block);
+        if (grid > D->sm_count) grid = D->sm_count;
+        smem_lut = 1;
+        smem = kLutBytes;
+    } else {
+        block = 128;
+        grid = (int)((n + block - 1) / block);
+        if (grid < 1) grid = 1;
+        smem_lut = 0;
+        smem = 0;
+    }
+}
+
+G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n, int64_t k_steps,
+                                   int flavour, uint64_t seed, uint64_t step_base, uint64_t env_id_base,
+                                   int64_t* counters, void* stream) {
+    DEVSTATE();
+    if (n < 0 || k_steps < 0 || (n && !boards) || (flavour != 0 && flavour != 1))
+        return fail(G2048_ERR_ARG, "g2048_rollout_random: bad arguments");
+    if (n == 0 || k_steps == 0) return 0;
+    int grid, block, smem_lut;
+    size_t smem;
+    rollout_geometry(D, n, grid, block, smem_lut, smem);
+    if (flavour == 0)
+        k_rollout_random<0><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, n, k_steps, seed,
+                                                              step_base, env_id_base, (long long*)counters, smem_lut);
+    else
+        k_rollout_random<1><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, n, k_steps, seed,
+                                                              step_base, env_id_base, (long long*)counters, smem_lut);
+    LAUNCH_CHECK("k_rollout_random");
+    return 0;
+}
+
+G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
+                                   int64_t n, int64_t k_steps, int flavour, float lr, float gamma, double eps,
+                                   uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t* counters,
+                                   void* stream) {
+    DEVSTATE();
+    if (n < 0 || k_steps < 0 || (n && !boards) || !table || !pow2(capacity) || capacity > (1ull << 32) ||
+        (flavour != 0 && flavour != 1))
+        return fail(G2048_ERR_ARG, "g2048_rollout_qlearn: bad arguments");
+    if (n == 0 || k_steps == 0) return 0;
+    int grid, block, smem_lut;
+    size_t smem;
+    rollout_geometry(D, n, grid, block, smem_lut, smem);
+    if (flavour == 0)
+        k_rollout_qlearn<0><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table,
+                                                              capacity - 1, n, k_steps, lr, gamma, eps_threshold(eps),
+                                                              seed, step_base, env_id_base, (long long*)counters, smem_lut);
+    else
+        k_rollout_qlearn<1><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table,
+                                                              capacity - 1, n, k_steps, lr, gamma, eps_threshold(eps),
+                                                              seed, step_base, env_id_base, (long long*)counters, smem_lut);
+    LAUNCH_CHECK("k_rollout_qlearn");
+    return 0;
+}
+
+// ---- scratch layout for the synchronous update: key_in | key_out | val_in | val_out | cub temp
+namespace {
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct Scratch {
+    u64 *key_in, *key_out;
+    float *val_in, *val_out;
+    void* cub_temp;
+    size_t cub_bytes;
+};
+size_t cub_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const u64*)nullptr, (u64*)nullptr, (const float*)nullptr,
+                                    (float*)nullptr, (int64_t)n, 0, 64, (cudaStream_t)0);
+    return bytes;
+}
+size_t scratch_bytes(int64_t n) {
+    size_t m = (size_t)(n > 0 ? n : 1);
+    return 2 * align256(m * 8) + 2 * align256(m * 4) + align256(cub_temp_bytes(n)) + 256;
+}
+int carve(void* scratch, size_t bytes, int64_t n, Scratch& s) {
+    if (!scratch || bytes < scratch_bytes(n)) return fail(G2048_ERR_NOMEM, "scratch buffer missing or smaller than g2048_qlearn_scratch_bytes(n)");
+    size_t m = (size_t)(n > 0 ? n : 1);
+    char* p = (char*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    s.key_in = (u64*)p; p += align256(m * 8);
+    s.key_out = (u64*)p; p += align256(m * 8);
+    s.val_in = (float*)p; p += align256(m * 4);
+    s.val_out = (float*)p; p += align256(m * 4);
+    s.cub_temp = p;
+    s.cub_bytes = cub_temp_bytes(n);
+    return 0;
+}
+// apply the records in s.key_in / s.val_in
+int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, int mode, cudaStream_t st) {
+    int g = grid_for(n, 256, D->sm_count);
+    if (mode == G2048_MODE_ATOMIC) {
+        k_apply_atomic<<<g, 256, 0, st>>>(tab, s.key_in, s.val_in, n);
+        LAUNCH_CHECK("k_apply_atomic");
+        return 0;
+    }
+    (void)capacity;
+    // all 64 key bits take part so that the all-ones "no slot" key sorts last; the sort is stable, so
+    // equal keys keep ascending record (= env) order
+    CK(cub::DeviceRadixSort::SortPairs(s.cub_temp, s.cub_bytes, (const u64*)s.key_in, s.key_out, (const float*)s.val_in,
+                                       s.val_out, (int64_t)n, 0, 64, st));
+    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, n);
+    LAUNCH_CHECK("k_segment_apply");
+    return 0;
+}
+}  // namespace
+
+G2048_API size_t g2048_qlearn_scratch_bytes(int64_t n) { return scratch_bytes(n); }
+
+G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
+                                int64_t n, int flavour, float lr, float gamma, double eps, int mode, int apply,
+                                uint64_t seed, uint64_t step_idx, uint64_t env_id_base, int64_t* counters,
+                                uint64_t* rec_key, uint8_t* rec_action, float* rec_delta, void* scratch,
+                                size_t scratch_bytes_, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && !boards) || !table || !pow2(capacity) || capacity > (1ull << 32) ||
+        (flavour != 0 && flavour != 1) || (mode != 0 && mode != 1))
+        return fail(G2048_ERR_ARG, "g2048_qlearn_step: bad arguments");
+    if (n == 0) return 0;
+    Scratch s{};
+    if (apply) {
+        int rc = carve(scratch, scratch_bytes_, n, s);
+        if (rc) return rc;
+    }
+    int g = grid_for(n, 256, D->sm_count);
+#define PHASE_A(F)                                                                                                    \
+    k_qlearn_phase_a<F><<<g, 256, 0, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table, capacity - 1, \
+                                                  n, lr, gamma, eps_threshold(eps), seed, step_idx, env_id_base,      \
+                                                  (long long*)counters, s.key_in, s.val_in, (u64*)rec_key, rec_action, \
+                                                  rec_delta)
+    if (flavour == 0) PHASE_A(0); else PHASE_A(1);
+#undef PHASE_A
+    LAUNCH_CHECK("k_qlearn_phase_a");
+    if (apply) return apply_records(D, (Slot*)table, capacity, s, n, mode, S(stream));
+    return 0;
+}
+
+G2048_API size_t g2048_qtable_bytes(uint64_t capacity) { return (size_t)capacity * sizeof(Slot); }
+G2048_API int g2048_qtable_clear(void* table, uint64_t capacity, void* stream) {
+    if (!table || !pow2(capacity)) return fail(G2048_ERR_ARG, "g2048_qtable_clear: bad arguments");
+    CK(cudaMemsetAsync(table, 0, (size_t)capacity * sizeof(Slot), S(stream)));
+    return 0;
+}
+G2048_API int g2048_qtable_lookup(void* table, uint64_t capacity, const uint64_t* keys, int64_t n, float* rows,
+                                  uint8_t* found, int insert, void* stream) {
+    DEVSTATE();
+    if (n < 0 || !table || !pow2(capacity) || (n && (!keys || !rows))) return fail(G2048_ERR_ARG, "g2048_qtable_lookup: bad arguments");
+    if (n == 0) return 0;
+    int g = grid_for(n, 256, D->sm_count);
+    if (insert) k_q_lookup<true><<<g, 256, 0, S(stream)>>>((Slot*)table, capacity - 1, (const u64*)keys, n, (float4*)rows, found);
+    else k_q_lookup<false><<<g, 256, 0, S(stream)>>>((Slot*)table, capacity - 1, (const u64*)keys, n, (float4*)rows, found);
+    LAUNCH_CHECK("k_q_lookup");
+    return 0;
+}
+G2048_API int g2048_choose_action(void* table, uint64_t capacity, const uint64_t* boards, uint8_t* actions, int64_t n,
+                                  double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base, void* stream) {
+    DEVSTATE();
+    if (n < 0 || !table || !pow2(capacity) || (n && (!boards || !actions))) return fail(G2048_ERR_ARG, "g2048_choose_action: bad arguments");
+    if (n == 0) return 0;
+    k_choose_action<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((Slot*)table, capacity - 1, (const u64*)boards,
+                                                                           actions, n, eps_threshold(eps), seed, step_idx,
+                                                                           env_id_base);
+    LAUNCH_CHECK("k_choose_action");
+    return 0;
+}
+G2048_API int g2048_qtable_update(void* table, uint64_t capacity, const uint64_t* s, const uint8_t* a, const float* r,
+                                  const uint64_t* s2, const uint8_t* done, int64_t n, float lr, float gamma, int mode,
+                                  void* scratch, size_t scratch_bytes_, void* stream) {
+    DEVSTATE();
+    if (n < 0 || !table || !pow2(capacity) || capacity > (1ull << 32) || (n && (!s || !a || !r || !s2 || !done)) ||
+        (mode != 0 && mode != 1))
+        return fail(G2048_ERR_ARG, "g2048_qtable_update: bad arguments");
+    if (n == 0) return 0;
+    Scratch sc{};
+    int rc = carve(scratch, scratch_bytes_, n, sc);
+    if (rc) return rc;
+    k_q_update_phase_a<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((Slot*)table, capacity - 1, (const u64*)s, a, r,
+                                                                              (const u64*)s2, done, n, lr, gamma,
+                                                                              sc.key_in, sc.val_in);
+    LAUNCH_CHECK("k_q_update_phase_a");
+    return apply_records(D, (Slot*)table, capacity, sc, n, mode, S(stream));
+}
+G2048_API int g2048_qtable_apply_deltas(void* table, uint64_t capacity, const uint64_t* keys, const uint8_t* a,
+                                        const float* delta, int64_t n, int mode, void* scratch, size_t scratch_bytes_,
+                                        void* stream) {
+    DEVSTATE();
+    if (n < 0 || !table || !pow2(capacity) || capacity > (1ull << 32) || (n && (!keys || !a || !delta)) ||
+        (mode != 0 && mode != 1))
+        return fail(G2048_ERR_ARG, "g2048_qtable_apply_deltas: bad arguments");
+    if (n == 0) return 0;
+    Scratch sc{};
+    int rc = carve(scratch, scratch_bytes_, n, sc);
+    if (rc) return rc;
+    k_keys_to_records<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((Slot*)table, capacity - 1, (const u64*)keys, a,
+                                                                             n, sc.key_in);
+    LAUNCH_CHECK("k_keys_to_records");
+    CK(cudaMemcpyAsync(sc.val_in, delta, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, S(stream)));
+    return apply_records(D, (Slot*)table, capacity, sc, n, mode, S(stream));
+}
+G2048_API int g2048_qtable_size(const void* table, uint64_t capacity, int64_t* count, void* stream) {
+    DEVSTATE();
+    if (!table || !pow2(capacity) || !count) return fail(G2048_ERR_ARG, "g2048_qtable_size: bad arguments");
+    CK(cudaMemsetAsync(count, 0, sizeof(int64_t), S(stream)));
+    k_q_size<<<grid_for((int64_t)capacity, 256, D->sm_count, 16), 256, 0, S(stream)>>>((const Slot*)table, capacity,
+                                                                                        (long long*)count);
+    LAUNCH_CHECK("k_q_size");
+    return 0;
+}
+G2048_API int g2048_qtable_export(const void* table, uint64_t capacity, uint64_t* keys, float* rows, int64_t max_out,
+                                  int64_t* count, void* stream) {
+    DEVSTATE();
+    if (!table || !pow2(capacity) || !count || max_out < 0 || (max_out && (!keys || !rows)))
+        return fail(G2048_ERR_ARG, "g2048_qtable_export: bad arguments");
+    k_q_export<<<grid_for((int64_t)capacity, 256, D->sm_count, 16), 256, 0, S(stream)>>>((const Slot*)table, capacity,
+                                                                                          (u64*)keys, (float4*)rows, max_out,
+                                                                                          (long long*)count);
+    LAUNCH_CHECK("k_q_export");
+    return 0;
+}
+
+// ============================================================================================ host-buffer API
+struct g2048_ctx {
+    int device = 0;
+    int64_t max_envs = 0;
+    uint64_t capacity = 0;
+    cudaStream_t stream = nullptr;
+    void* table = nullptr;
+    // device staging, sized for max_envs
+    u64 *boards = nullptr, *aux = nullptr, *keys2 = nullptr;
+    int *score = nullptr, *move_score = nullptr;
+    uint8_t *bytes_a = nullptr, *bytes_b = nullptr, *flags = nullptr, *maxlvl = nullptr, *draws = nullptr;
+    double* rew64 = nullptr;
+    float *rows = nullptr, *rew32 = nullptr;
+    long long* counters = nullptr;  // G2048_N_COUNTERS + 1 (export/size count)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+G2048_API g2048_ctx* g2048_ctx_create(int device, int64_t max_envs, uint64_t table_capacity) {
+    if (max_envs <= 0 || (table_capacity && !pow2(table_capacity))) { fail(G2048_ERR_ARG, "g2048_ctx_create: bad arguments"); return nullptr; }
+    if (g2048_init(device)) return nullptr;
+    g2048_ctx* c = new g2048_ctx();
+    c->device = device; c->max_envs = max_envs; c->capacity = table_capacity;
+    size_t m = (size_t)max_envs;
+    c->scratch_bytes = scratch_bytes(max_envs);
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&c->boards, m * 8) == cudaSuccess && cudaMalloc(&c->aux, m * 8) == cudaSuccess &&
+              cudaMalloc(&c->keys2, m * 8) == cudaSuccess && cudaMalloc(&c->score, m * 4) == cudaSuccess &&
+              cudaMalloc(&c->move_score, m * 4) == cudaSuccess && cudaMalloc(&c->bytes_a, m) == cudaSuccess &&
+              cudaMalloc(&c->bytes_b, m) == cudaSuccess && cudaMalloc(&c->flags, m) == cudaSuccess &&
+              cudaMalloc(&c->maxlvl, m) == cudaSuccess && cudaMalloc(&c->draws, m * 4) == cudaSuccess &&
+              cudaMalloc(&c->rew64, m * 8) == cudaSuccess && cudaMalloc(&c->rows, m * 16) == cudaSuccess &&
+              cudaMalloc(&c->rew32, m * 4) == cudaSuccess &&
+              cudaMalloc(&c->counters, (G2048_N_COUNTERS + 1) * sizeof(long long)) == cudaSuccess &&
+              cudaMalloc(&c->scratch, c->scratch_bytes) == cudaSuccess;
+    if (ok && table_capacity) {
+        ok = cudaMalloc(&c->table, g2048_qtable_bytes(table_capacity)) == cudaSuccess &&
+             cudaMemsetAsync(c->table, 0, g2048_qtable_bytes(table_capacity), c->stream) == cudaSuccess &&
+             cudaStreamSynchronize(c->stream) == cudaSuccess;
+    }
+    if (!ok) {
+        fail((int)cudaGetLastError(), "g2048_ctx_create: allocation failed");
+        g2048_ctx_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+G2048_API void g2048_ctx_destroy(g2048_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    void* ptrs[] = {c->boards, c->aux, c->keys2, c->score, c->move_score, c->bytes_a, c->bytes_b, c->flags, c->maxlvl,
+                    c->draws, c->rew64, c->rows, c->rew32, c->counters, c->scratch, c->table};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+G2048_API void* g2048_ctx_table(g2048_ctx* c) { return c ? c->table : nullptr; }
+G2048_API uint64_t g2048_ctx_table_capacity(g2048_ctx* c) { return c ? c->capacity : 0; }
+G2048_API void* g2048_ctx_stream(g2048_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+#define CTX_ENTER(need_table)                                                                    \
+    if (!c) return fail(G2048_ERR_ARG, "null context");                                          \
+    if (n < 0 || n > c->max_envs) return fail(G2048_ERR_ARG, "n exceeds the context's max_envs"); \
+    if ((need_table) && !c->table) return fail(G2048_ERR_ARG, "context has no Q-table");         \
+    CK(cudaSetDevice(c->device));                                                                \
+    cudaStream_t st = c->stream;                                                                 \
+    (void)st
+#define H2D(dst, src, bytes) \
+    if (src) CK(cudaMemcpyAsync(dst, src, (size_t)(bytes), cudaMemcpyHostToDevice, st))
+#define D2H(dst, src, bytes) \
+    if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(bytes), cudaMemcpyDeviceToHost, st))
+#define RC(expr)              \
+    do {                      \
+        int rc_ = (expr);     \
+        if (rc_) return rc_;  \
+    } while (0)
+
+G2048_API int g2048_ctx_env_reset(g2048_ctx* c, uint64_t* boards, int32_t* score, const uint8_t* mask,
+                                  const uint8_t* replay_draws, int64_t n, uint64_t seed, uint64_t episode_idx,
+                                  uint64_t env_id_base) {
+    CTX_ENTER(false);
+    if (!boards) return fail(G2048_ERR_ARG, "g2048_ctx_env_reset: boards is null");
+    if (mask) { H2D(c->boards, boards, n * 8); H2D(c->score, score, n * 4); H2D(c->bytes_a, mask, n); }
+    H2D(c->draws, replay_draws, n * 4);
+    RC(g2048_env_reset((uint64_t*)c->boards, score ? c->score : nullptr, mask ? c->bytes_a : nullptr,
+                       replay_draws ? c->draws : nullptr, n, seed, episode_idx, env_id_base, st));
+    D2H(boards, c->boards, n * 8);
+    D2H(score, c->score, n * 4);
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+G2048_API int g2048_ctx_env_step(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* score, const uint8_t* actions,
+                                 const uint8_t* replay_draws, double* reward_f64, uint8_t* flags, uint8_t* maxlvl,
+                                 int32_t* move_score, int64_t n, int flavour, uint64_t seed, uint64_t step_idx,
+                                 uint64_t env_id_base) {
+    CTX_ENTER(false);
+    if (!boards || !actions) return fail(G2048_ERR_ARG, "g2048_ctx_env_step: boards/actions is null");
+    H2D(c->boards, boards, n * 8);
+    H2D(c->aux, aux, n * 8);
+    H2D(c->score, score, n * 4);
+    H2D(c->bytes_a, actions, n);
+    H2D(c->draws, replay_draws, n * 4);
+    RC(g2048_env_step((uint64_t*)c->boards, aux ? (uint64_t*)c->aux : nullptr, score ? c->score : nullptr, c->bytes_a,
+                      replay_draws ? c->draws : nullptr, reward_f64 ? c->rew64 : nullptr, nullptr,
+                      flags ? c->flags : nullptr, maxlvl ? c->maxlvl : nullptr, move_score ? c->move_score : nullptr, n,
+                      flavour, seed, step_idx, env_id_base, st));
+    D2H(boards, c->boards, n * 8);
+    D2H(aux, c->aux, n * 8);
+    D2H(score, c->score, n * 4);
+    D2H(reward_f64, c->rew64, n * 8);
+    D2H(flags, c->flags, n);
+    D2H(maxlvl, c->maxlvl, n);
+    D2H(move_score, c->move_score, n * 4);
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+G2048_API int g2048_ctx_legal_mask(g2048_ctx* c, const uint64_t* boards, uint8_t* out, int64_t n) {
+    CTX_ENTER(false);
+    if (n && (!boards || !out)) return fail(G2048_ERR_ARG, "g2048_ctx_legal_mask: null pointer");
+    H2D(c->boards, boards, n * 8);
+    RC(g2048_legal_mask((const uint64_t*)c->boards, c->flags, n, st));
+    D2H(out, c->flags, n);
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+G2048_API int g2048_ctx_move_trial(g2048_ctx* c, const uint64_t* boards_in, const uint8_t* actions, uint64_t* out_boards,
+                                   uint8_t* moved, int32_t* move_score, int64_t n) {
+    CTX_ENTER(false);
+    if (n && (!boards_in || !actions)) return fail(G2048_ERR_ARG, "g2048_ctx_move_trial: null pointer");
+    H2D(c->boards, boards_in, n * 8);
+    H2D(c->bytes_a, actions, n);
+    RC(g2048_move_trial((const uint64_t*)c->boards, c->bytes_a, (uint64_t*)c->keys2, c->flags, c->move_score, n, st));
+    D2H(out_boards, c->keys2, n * 8);
+    D2H(moved, c->flags, n);
+    D2H(move_score, c->move_score, n * 4);
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n, int64_t k_steps,
+                       int flavour, float lr, float gamma, double eps, uint64_t seed, uint64_t step_base,
+                       uint64_t env_id_base, int64_t* counters, bool qlearn) {
+    CTX_ENTER(qlearn);
+    if (!boards) return fail(G2048_ERR_ARG, "rollout: boards is null");
+    H2D(c->boards, boards, n * 8);
+    H2D(c->aux, aux, n * 8);
+    H2D(c->score, score, n * 4);
+    CK(cudaMemsetAsync(c->counters, 0, G2048_N_COUNTERS * sizeof(long long), st));
+    if (qlearn)
+        RC(g2048_rollout_qlearn((uint64_t*)c->boards, aux ? (uint64_t*)c->aux : nullptr, score ? c->score : nullptr,
+                                c->table, c->capacity, n, k_steps, flavour, lr, gamma, eps, seed, step_base, env_id_base,
+                                (int64_t*)c->counters, st));
+    else
+        RC(g2048_rollout_random((uint64_t*)c->boards, aux ? (uint64_t*)c->aux : nullptr, score ? c->score : nullptr, n,
+                                k_steps, flavour, seed, step_base, env_id_base, (int64_t*)c->counters, st));
+    D2H(boards, c->boards, n * 8);
+    D2H(aux, c->aux, n * 8);
+    D2H(score, c->score, n * 4);
+    D2H(counters, c->counters, G2048_N_COUNTERS * sizeof(long long));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+G2048_API int g2048_ctx_rollout_random(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n,
+                                       int64_t k_steps, int flavour, uint64_t seed, uint64_t step_base,
+                                       uint64_t env_id_base, int64_t* counters) {
+    return ctx_rollout(c, boards, aux, score, n, k_steps, flavour, 0.f, 0.f, 0.0, seed, step_base, env_id_base, counters, false);
+}
+G2048_API int g2048_ctx_rollout_qlearn(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n,
+                                       int64_t k_steps, int flavour, float lr, float gamma, double eps, uint64_t seed,
+                                       uint64_t step_base, uint64_t env_id_base, int64_t* counters) {
+    return ctx_rollout(c, boards, aux, score, n, k_steps, flavour, lr, gamma, eps, seed, step_base, env_id_base, counters, true);
+}
+G2048_API int g2048_ctx_qtable_lookup(g2048_ctx* c, const uint64_t* keys, int64_t n, float* rows, uint8_t* found,
+                                      int insert) {
+    CTX_ENTER(true);
+    if (n && (!keys || !rows)) return fail(G2048_ERR_ARG, "g2048_ctx_qtable_lookup: null pointer");
+    H2D(c->boards, keys, n * 8);
+    RC(g2048_qtable_lookup(c->table, c->capacity, (const uint64_t*)c->boards, n, c->rows, found ? c->flags : nullptr,
+                           insert, st));
+    D2H(rows, c->rows, n * 16);
+    D2H(found, c->flags, n);
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+G2048_API int g2048_ctx_choose_action(g2048_ctx* c, const uint64_t* boards, uint8_t* actions, int64_t n, double eps,
+                                      uint64_t seed, uint64_t step_idx, uint64_t env_id_base) {
+    CTX_ENTER(true);
+    if (n && (!boards || !actions)) return fail(G2048_ERR_ARG, "g2048_ctx_choose_action: null pointer");
+    H2D(c->boards, boards, n * 8);
+    RC(g2048_choose_action(c->table, c->capacity, (const uint64_t*)c->boards, c->bytes_a, n, eps, seed, step_idx,
+                           env_id_base, st));
+    D2H(actions, c->bytes_a, n);
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+G2048_API int g2048_ctx_qtable_update(g2048_ctx* c, const uint64_t* s, const uint8_t* a, const float* r,
+                                      const uint64_t* s2, const uint8_t* done, int64_t n, float lr, float gamma,
+                                      int mode) {
+    CTX_ENTER(true);
+    if (n && (!s || !a || !r || !s2 || !done)) return fail(G2048_ERR_ARG, "g2048_ctx_qtable_update: null pointer");
+    H2D(c->boards, s, n * 8);
+    H2D(c->keys2, s2, n * 8);
+    H2D(c->bytes_a, a, n);
+    H2D(c->bytes_b, done, n);
+    H2D(c->rew32, r, n * 4);
+    RC(g2048_qtable_update(c->table, c->capacity, (const uint64_t*)c->boards, c->bytes_a, c->rew32,
+                           (const uint64_t*)c->keys2, c->bytes_b, n, lr, gamma, mode, c->scratch, c->scratch_bytes, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+G2048_API int64_t g2048_ctx_qtable_size(g2048_ctx* c) {
+    if (!c || !c->table) { fail(G2048_ERR_ARG, "context has no Q-table"); return -1; }
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1;
+    long long* cnt = c->counters + G2048_N_COUNTERS;
+    if (g2048_qtable_size(c->table, c->capacity, (int64_t*)cnt, c->stream)) return -1;
+    long long h = 0;
+    if (cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) { fail((int)cudaGetLastError(), "g2048_ctx_qtable_size"); return -1; }
+    return h;
+}
+G2048_API int64_t g2048_ctx_qtable_export(g2048_ctx* c, uint64_t* keys, float* rows, int64_t max_out) {
+    if (!c || !c->table || max_out < 0) { fail(G2048_ERR_ARG, "g2048_ctx_qtable_export: bad arguments"); return -1; }
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1;
+    long long* cnt = c->counters + G2048_N_COUNTERS;
+    u64* dk = nullptr;
+    float* dr = nullptr;
+    long long h = -1;
+    size_t m = (size_t)(max_out > 0 ? max_out : 1);
+    if (cudaMalloc(&dk, m * 8) != cudaSuccess || cudaMalloc(&dr, m * 16) != cudaSuccess) {
+        fail((int)cudaGetLastError(), "g2048_ctx_qtable_export: cudaMalloc");
+    } else if (cudaMemsetAsync(cnt, 0, sizeof(long long), c->stream) == cudaSuccess &&
+               g2048_qtable_export(c->table, c->capacity, (uint64_t*)dk, dr, max_out, (int64_t*)cnt, c->stream) == 0 &&
+               cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+               cudaStreamSynchronize(c->stream) == cudaSuccess) {
+        long long w = h < max_out ? h : max_out;
+        if (w > 0 && (cudaMemcpy(keys, dk, (size_t)w * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                      cudaMemcpy(rows, dr, (size_t)w * 16, cudaMemcpyDeviceToHost) != cudaSuccess)) {
+            fail((int)cudaGetLastError(), "g2048_ctx_qtable_export: copy");
+            h = -1;
+        }
+    } else {
+        fail((int)cudaGetLastError(), "g2048_ctx_qtable_export");
+        h = -1;
+    }
+    if (dk) cudaFree(dk);
+    if (dr) cudaFree(dr);
+    return h;
+}
+G2048_API int g2048_ctx_qtable_clear(g2048_ctx* c) {
+    if (!c || !c->table) return fail(G2048_ERR_ARG, "context has no Q-table");
+    CK(cudaSetDevice(c->device));
+    RC(g2048_qtable_clear(c->table, c->capacity, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}

@@ -1,0 +1,412 @@
+// g2048_device.cuh -- device-side building blocks of the batched 2048 env and the
+// HBM hash Q-table (sm_100a).  Board = uint64, cell (r,c) = nibble 4r+c holding
+// log2(tile), 0 = empty; row r = bits 16r..16r+15, "left" = towards nibble 0.
+//
+// Reference semantics (paths relative to the reference root):
+//   QLearningBase/environment/Game2048_env.py        penalty-flavour env
+//   Deep_QLearning/environment/Game2048_nopenalty_env.py + mainDQL_CNN_step2.py:163-237
+//   QLearningBase/Agent/main.py:34-43                choose_action / update_q_value
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/g2048.h"
+
+namespace g2048 {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr u64 kNib1 = 0x1111111111111111ull;   // LSB of every nibble
+constexpr u64 kColsLeft3 = 0x0111011101110111ull;  // cells with a right-hand neighbour in the same row
+constexpr u64 kRowsTop3 = 0x0000111111111111ull;   // cells with a neighbour below
+constexpr u32 kIs4Thresh = 0xE6666666u;        // floor(0.9 * 2^32): `random() < 0.9 -> 2`, Game2048_env.py:20
+constexpr int kPenSat = 25;                    // stall penalty table saturates at -10 from index 25 on
+constexpr u32 kNoSlot = 0xFFFFFFFFu;
+constexpr int kMaxProbe = 256;
+
+// Host-built tables resident in HBM/L2 (built once per device by g2048_init).
+struct Tables {
+    const uint16_t* lut_row;      // [65536] row moved left
+    const uint8_t* lut_merged;    // [65536] the (at most two) merged levels, hi nibble >= lo nibble
+    const double* rew_valid;      // [16 lvl][16 d][256 score/4] normalised reward of a valid move
+    const double* rew_invalid;    // [2 game_over][16 lvl][16 d]
+    const double* pen;            // [32] stall penalty sequence, pen[0] = -1
+};
+
+// Row LUT view (shared-memory copy in the fused kernels, global copy otherwise).
+struct Lut {
+    const uint16_t* row;
+    const uint8_t* merged;
+};
+
+// ------------------------------------------------------------------ Philox4x32-10
+// counter = (env id lo, env id hi, step lo, stream<<24 | step hi), key = seed
+struct Draw4 { u32 x0, x1, x2, x3; };
+__device__ __forceinline__ Draw4 philox(u64 seed, u64 env_id, u64 step, u32 stream) {
+    u32 c0 = (u32)env_id, c1 = (u32)(env_id >> 32), c2 = (u32)step;
+    u32 c3 = (stream << 24) | ((u32)(step >> 32) & 0x00FFFFFFu);
+    u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        u32 h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        u32 h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1;
+        c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return Draw4{c0, c1, c2, c3};
+}
+
+// ------------------------------------------------------------------ board bit tricks
+__device__ __forceinline__ u64 nzmask(u64 b) {  // bit 4i set iff nibble i != 0
+    u64 t = b | (b >> 1);
+    t |= t >> 2;
+    return t & kNib1;
+}
+__device__ __forceinline__ u64 is15mask(u64 b) {  // bit 4i set iff nibble i == 15
+    u64 t = b & (b >> 1);
+    t &= t >> 2;
+    return t & kNib1;
+}
+__device__ __forceinline__ u32 rev_rows32(u32 x) {  // reverse the 4 nibbles of each 16-bit row
+    x = __byte_perm(x, 0, 0x2301);
+    return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+}
+__device__ __forceinline__ u64 reverse_rows(u64 b) {
+    return ((u64)rev_rows32((u32)(b >> 32)) << 32) | rev_rows32((u32)b);
+}
+__device__ __forceinline__ u64 transpose(u64 x) {  // 4x4 nibble matrix transpose
+    u64 a1 = x & 0xF0F00F0FF0F00F0Full;
+    u64 a2 = x & 0x0000F0F00000F0F0ull;
+    u64 a3 = x & 0x0F0F00000F0F0000ull;
+    u64 a = a1 | (a2 << 12) | (a3 >> 12);
+    u64 b1 = a & 0xFF00FF0000FF00FFull;
+    u64 b2 = a & 0x00FF00FF00000000ull;
+    u64 b3 = a & 0x00000000FF00FF00ull;
+    return b1 | (b2 >> 24) | (b3 << 24);
+}
+__device__ __forceinline__ int max_level(u64 b) {  // largest nibble
+    u32 lo = (u32)b, hi = (u32)(b >> 32);
+    u32 v0 = lo & 0x0F0F0F0Fu, v1 = (lo >> 4) & 0x0F0F0F0Fu, v2 = hi & 0x0F0F0F0Fu, v3 = (hi >> 4) & 0x0F0F0F0Fu;
+    // bytewise max of values < 128: bit 7 of ((a|0x80..) - b) is set iff a >= b
+    auto bmax = [](u32 a, u32 b) -> u32 {
+        u32 ge = (((a | 0x80808080u) - b) >> 7) & 0x01010101u;
+        u32 m = ge * 0xFFu;
+        return (a & m) | (b & ~m);
+    };
+    u32 m = bmax(bmax(v0, v1), bmax(v2, v3));
+    m = bmax(m, m >> 16);
+    m = bmax(m, m >> 8);
+    return (int)(m & 0xFFu);
+}
+
+// move towards nibble 0 of every row through the row LUT (move_left, Game2048_env.py:22-46).
+// mm receives the four rows' merged-level bytes.
+__device__ __forceinline__ u64 move_left_lut(u64 t, const Lut& L, u32& mm) {
+    u32 lo = (u32)t, hi = (u32)(t >> 32);
+    u32 i0 = lo & 0xFFFFu, i1 = lo >> 16, i2 = hi & 0xFFFFu, i3 = hi >> 16;
+    u32 r0 = L.row[i0], r1 = L.row[i1], r2 = L.row[i2], r3 = L.row[i3];
+    u32 m0 = L.merged[i0], m1 = L.merged[i1], m2 = L.merged[i2], m3 = L.merged[i3];
+    mm = m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
+    return ((u64)(r2 | (r3 << 16)) << 32) | (u64)(r0 | (r1 << 16));
+}
+// sum over the 8 merged-level nibbles of 2^level (level 0 = no merge) (score += merged value, :35)
+__device__ __forceinline__ int merge_score(u32 mm) {
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (int)((1u << ((mm >> (4 * i)) & 0xFu)) & ~1u);
+    return s;
+}
+// Game2048.move without the spawn (Game2048_env.py:51-60), branch-free in the action:
+// 0 left | 1 up = transpose,left,transpose | 2 right = reverse,left,reverse | 3 down = both.
+__device__ __forceinline__ bool do_move(u64 b, int a, const Lut& L, u64& out, u32& mm) {
+    u64 t = (a & 1) ? transpose(b) : b;
+    t = (a & 2) ? reverse_rows(t) : t;
+    u64 r = move_left_lut(t, L, mm);
+    bool moved = (r != t);
+    r = (a & 2) ? reverse_rows(r) : r;
+    out = (a & 1) ? transpose(r) : r;
+    return moved;
+}
+
+// position (bit offset, multiple of 4) of the k-th set bit of E (bits only at nibble LSBs),
+// counted from nibble 0 = row-major order of np.where (add_number, Game2048_env.py:17-19)
+__device__ __forceinline__ int kth_empty_pos(u64 E, int k) {
+    u32 w = (u32)E;
+    int base = 0, c = __popc(w);
+    if (k >= c) { k -= c; w = (u32)(E >> 32); base = 32; }
+    c = __popc(w & 0xFFFFu);
+    if (k >= c) { k -= c; w >>= 16; base += 16; }
+    c = __popc(w & 0xFFu);
+    if (k >= c) { k -= c; w >>= 8; base += 8; }
+    if (k >= (int)(w & 1u)) base += 4;
+    return base;
+}
+// add_number (Game2048_env.py:16-20).  REPLAY: d0 = recorded cell index k, d1 = recorded is-4 flag;
+// otherwise d0/d1 are 32-bit uniform draws: k = floor(d0 * n_empty / 2^32), 4 iff d1 >= 0.9 * 2^32.
+template <bool REPLAY>
+__device__ __forceinline__ u64 spawn(u64 b, u32 d0, u32 d1) {
+    u64 E = ~nzmask(b) & kNib1;
+    int ne = __popcll(E);
+    if (ne == 0) return b;
+    int k = REPLAY ? (int)d0 : (int)__umulhi(d0, (u32)ne);
+    if (k >= ne) k = ne - 1;  // malformed replay input: stay in range
+    bool is4 = REPLAY ? (d1 != 0) : (d1 >= kIs4Thresh);
+    return b | ((u64)(is4 ? 2 : 1) << kth_empty_pos(E, k));
+}
+// Game2048.__init__ (Game2048_env.py:11-14): empty board + two spawns
+template <bool REPLAY>
+__device__ __forceinline__ u64 fresh_board(u32 d0, u32 d1, u32 d2, u32 d3) {
+    int ka = REPLAY ? (int)(d0 & 15u) : (int)__umulhi(d0, 16u);
+    int kb = REPLAY ? (int)d2 : (int)__umulhi(d2, 15u);
+    if (kb > 14) kb = 14;
+    bool fa = REPLAY ? (d1 != 0) : (d1 >= kIs4Thresh);
+    bool fb = REPLAY ? (d3 != 0) : (d3 >= kIs4Thresh);
+    int pb = kb < ka ? kb : kb + 1;
+    return ((u64)(fa ? 2 : 1) << (4 * ka)) | ((u64)(fb ? 2 : 1) << (4 * pb));
+}
+
+// pairs of equal neighbours that can merge (level 15 cannot: 65536 is unrepresentable)
+__device__ __forceinline__ void equal_pairs(u64 b, u64 F, u64& eqH, u64& eqV) {
+    u64 ok = F & ~is15mask(b);
+    eqH = ~nzmask(b ^ (b >> 4)) & kColsLeft3 & ok;
+    eqV = ~nzmask(b ^ (b >> 16)) & kRowsTop3 & ok;
+}
+// is_game_over as a predicate (Game2048_env.py:65-75): full and nothing merges
+__device__ __forceinline__ bool is_dead(u64 b) {
+    u64 F = nzmask(b);
+    if (F != kNib1) return false;
+    u64 eqH, eqV;
+    equal_pairs(b, F, eqH, eqV);
+    return (eqH | eqV) == 0;
+}
+// bit a set iff move(a, trial=True) would move (mainDQL_CNN_step2.py:169-174)
+__device__ __forceinline__ u32 legal_mask(u64 b) {
+    u64 F = nzmask(b), E = ~F & kNib1, eqH, eqV;
+    equal_pairs(b, F, eqH, eqV);
+    u32 left = ((E & (F >> 4) & kColsLeft3) | eqH) != 0;
+    u32 right = ((F & (E >> 4) & kColsLeft3) | eqH) != 0;
+    u32 up = ((E & (F >> 16) & kRowsTop3) | eqV) != 0;
+    u32 down = ((F & (E >> 16) & kRowsTop3) | eqV) != 0;
+    return left | (up << 1) | (right << 2) | (down << 3);
+}
+
+// ------------------------------------------------------------------ env state in registers
+struct Env {
+    u64 board;
+    u32 cons_count;   // consecutive_count (saturating)
+    u32 small;        // prev_level | cons_action << 8 | pen_idx << 16   (aux low word)
+    int score;        // env.score
+};
+__device__ __forceinline__ void env_from_aux(Env& e, u64 aux) { e.small = (u32)aux; e.cons_count = (u32)(aux >> 32); }
+__device__ __forceinline__ u64 env_to_aux(const Env& e) { return ((u64)e.cons_count << 32) | e.small; }
+
+struct StepOut {
+    double reward;
+    int move_score;
+    int maxlvl;
+    bool valid, game_over, done;
+};
+
+// calculate_reward + update_and_normalize (Game2048_env.py:136-184, 197-205) through host-built
+// tables: the normalised reward of an invalid move depends only on (game_over, level, d) and that of
+// a valid move on (level, d, score) with score a multiple of 4; score >= 1024 gives exactly 10.
+// d = max(level - prev_level, 0) is the progress step (previous_max is raised even when the move was
+// invalid and the bonus discarded, :148-150).
+__device__ __forceinline__ double shaped_reward(int score, bool valid, bool game_over, int lvl, int& prev_level,
+                                                const Tables& T) {
+    int d = lvl > prev_level ? lvl - prev_level : 0;
+    if (lvl > prev_level) prev_level = lvl;
+    if (!valid) return __ldg(T.rew_invalid + ((game_over ? 256 : 0) + lvl * 16 + d));
+    if (score >= 1024) return 10.0;
+    return __ldg(T.rew_valid + ((lvl * 16 + d) * 256 + (score >> 2)));
+}
+
+// Game2048_env.step, penalty flavour (Game2048_env.py:97-129).  d0,d1: spawn draws of the move.
+template <bool REPLAY>
+__device__ __forceinline__ void penalty_step(Env& e, int a, u32 d0, u32 d1, const Lut& L, const Tables& T, StepOut& o) {
+    u64 b1;
+    u32 mm;
+    bool valid = do_move(e.board, a, L, b1, mm);                 // :98
+    int ms = merge_score(mm);
+    if (valid) b1 = spawn<REPLAY>(b1, d0, d1);                   // :61-62
+    bool game_over = is_dead(b1);                                // :99
+    int lvl = max_level(b1);                                     // :100
+    if (lvl < 1) lvl = 1;                                        // max(2, max_number) :141
+    e.board = b1;
+    e.score += ms;                                               // :104
+    int prev_level = (int)(e.small & 0xFFu), cons_action = (int)((e.small >> 8) & 0xFFu);
+    int pen_idx = (int)((e.small >> 16) & 0xFFu);
+    double reward = shaped_reward(ms, valid, game_over, lvl, prev_level, T);  // :107
+    if (a == cons_action) {                                      // :110-115
+        if (e.cons_count != 0xFFFFFFFFu) e.cons_count += 1;
+    } else {
+        cons_action = a;
+        e.cons_count = 1;
+        pen_idx = 0;
+    }
+    bool done = !valid && game_over;                             // :117-118
+    if (e.cons_count > 10) {                                     // :121-127
+        if (e.cons_count > 100) done = true;
+        if (pen_idx < kPenSat) pen_idx += 1;
+        reward = __dadd_rn(reward, __ldg(T.pen + pen_idx));
+    }
+    e.small = (u32)prev_level | ((u32)cons_action << 8) | ((u32)pen_idx << 16);
+    o.reward = reward; o.move_score = ms; o.maxlvl = lvl;
+    o.valid = valid; o.game_over = game_over; o.done = done;
+}
+
+// Game2048_env.step, nopenalty flavour (Game2048_nopenalty_env.py:106-138) under the caller protocol
+// of mainDQL_CNN_step2.py:163-237: e.board is the committed board S on entry and the returned
+// moved_board M on exit.  (q0,q1): draws of the spawn inside is_game_over when S is full and some
+// action a' is legal -- the returned board is then the result of the FIRST legal a', not of the
+// agent's action (full-board quirk).
+template <bool REPLAY>
+__device__ __forceinline__ void nopenalty_step(Env& e, int a, u32 d0, u32 d1, u32 q0, u32 q1, const Lut& L, StepOut& o) {
+    u64 S = e.board, M;
+    u32 mm;
+    bool valid = do_move(S, a, L, M, mm);                        // :53-66
+    int ms = merge_score(mm);
+    if (valid) M = spawn<REPLAY>(M, d0, d1);
+    bool game_over = false;
+    if (nzmask(S) == kNib1) {                                    // :68-78, evaluated on S
+        u32 lm = legal_mask(S);
+        if (lm == 0) {
+            game_over = true;
+            M = S;
+        } else {
+            u32 mm2;
+            do_move(S, __ffs((int)lm) - 1, L, M, mm2);
+            M = spawn<REPLAY>(M, q0, q1);
+        }
+    }
+    int lvl = max_level(M);                                      // :108
+    e.board = M;
+    e.score += ms;                                               // :111
+    o.reward = (!valid && !game_over) ? -10.0 : (double)ms;      // :122-128
+    o.move_score = ms; o.maxlvl = lvl;
+    o.valid = valid; o.game_over = game_over; o.done = game_over; // :117-118
+}
+
+// one env step with Philox draws x (STREAM_STEP); the nopenalty quirk spawn draws its own stream
+template <int FLAVOUR>
+__device__ __forceinline__ void philox_step(Env& e, int a, const Draw4& x, u64 seed, u64 env_id, u64 t, const Lut& L,
+                                            const Tables& T, StepOut& o) {
+    if (FLAVOUR == G2048_FLAVOUR_PENALTY) {
+        penalty_step<false>(e, a, x.x0, x.x1, L, T, o);
+    } else {
+        u32 q0 = 0, q1 = 0;
+        if (nzmask(e.board) == kNib1) {
+            Draw4 y = philox(seed, env_id, t, G2048_STREAM_QUIRK);
+            q0 = y.x0; q1 = y.x1;
+        }
+        nopenalty_step<false>(e, a, x.x0, x.x1, q0, q1, L, o);
+    }
+}
+__device__ __forceinline__ void philox_autoreset(Env& e, u64 seed, u64 env_id, u64 t) {
+    Draw4 y = philox(seed, env_id, t, G2048_STREAM_AUTORESET);
+    e.board = fresh_board<false>(y.x0, y.x1, y.x2, y.x3);
+    e.score = 0;   // reset() zeroes env.score only (Game2048_env.py:187-191); aux state survives
+}
+
+// ------------------------------------------------------------------ HBM hash Q-table
+// 32-byte slots (one DRAM sector): key, meta (unused), float q[4].  key 0 = empty (an all-empty
+// board never occurs).  Open addressing, linear probing, capacity a power of two.
+struct __align__(32) Slot {
+    u64 key;
+    u64 meta;
+    float q[4];
+};
+static_assert(sizeof(Slot) == G2048_QTABLE_SLOT_BYTES, "slot size");
+
+__device__ __forceinline__ u64 mix64(u64 x) {  // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+// one 256-bit L2-coherent load of a whole slot (L1 is bypassed: other SMs update rows with atomics)
+__device__ __forceinline__ void load_slot(const Slot* s, u64& key, float4& q) {
+    u64 k, m, q01, q23;
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(m), "=l"(q01), "=l"(q23) : "l"(s));
+    key = k;
+    q.x = __uint_as_float((u32)q01); q.y = __uint_as_float((u32)(q01 >> 32));
+    q.z = __uint_as_float((u32)q23); q.w = __uint_as_float((u32)(q23 >> 32));
+}
+// defaultdict semantics (main.py:16): reading a state creates its zero row.  Returns the slot index
+// (kNoSlot if the probe limit is hit: the state is then treated as a zero row and not updated).
+template <bool INSERT>
+__device__ __forceinline__ u32 table_find(Slot* tab, u64 mask, u64 key, float4& q, int& inserted) {
+    u64 h = mix64(key) & mask;
+    for (int p = 0; p < kMaxProbe; ++p, h = (h + 1) & mask) {
+        u64 k;
+        load_slot(tab + h, k, q);
+        if (k == key) return (u32)h;
+        if (k == 0) {
+            if (!INSERT) break;
+            u64 old = atomicCAS(&tab[h].key, 0ull, key);
+            if (old == 0) { inserted += 1; q = make_float4(0.f, 0.f, 0.f, 0.f); return (u32)h; }
+            if (old == key) { load_slot(tab + h, k, q); return (u32)h; }
+        }
+    }
+    q = make_float4(0.f, 0.f, 0.f, 0.f);
+    return kNoSlot;
+}
+__device__ __forceinline__ float q_at(const float4& q, int a) { return a == 0 ? q.x : a == 1 ? q.y : a == 2 ? q.z : q.w; }
+__device__ __forceinline__ void q_set(float4& q, int a, float v) {
+    if (a == 0) q.x = v; else if (a == 1) q.y = v; else if (a == 2) q.z = v; else q.w = v;
+}
+// np.argmax: first maximum (main.py:38, :41)
+__device__ __forceinline__ int argmax4(const float4& q) {
+    int b = 0; float v = q.x;
+    if (q.y > v) { v = q.y; b = 1; }
+    if (q.z > v) { v = q.z; b = 2; }
+    if (q.w > v) { b = 3; }
+    return b;
+}
+__device__ __forceinline__ float max4(const float4& q) { return q_at(q, argmax4(q)); }
+// choose_action (main.py:34-38): explore iff x2 < floor(eps * 2^32), random action = x3 >> 30
+__device__ __forceinline__ int choose_action(const float4& q, const Draw4& x, u64 eps_thresh) {
+    return ((u64)x.x2 < eps_thresh) ? (int)(x.x3 >> 30) : argmax4(q);
+}
+// update_q_value (main.py:40-43) in float32, every operation rounded on its own (-fmad=false):
+// delta = lr * ((r + (done ? 0 : gamma * best_next)) - q_sa)
+__device__ __forceinline__ float td_delta(float lr, float gamma, float r, float best_next, bool done, float q_sa) {
+    float g = __fmul_rn(gamma, best_next);
+    float target = __fadd_rn(r, done ? 0.0f : g);
+    return __fmul_rn(lr, __fsub_rn(target, q_sa));
+}
+
+// ------------------------------------------------------------------ counters
+struct Counters {
+    long long steps = 0, valid = 0, episodes = 0, score = 0, reward_fx = 0, inserts = 0, dropped = 0;
+    int maxlvl = 0;
+    __device__ __forceinline__ void add(const StepOut& o) {
+        steps += 1; valid += o.valid; episodes += o.done; score += o.move_score;
+        maxlvl = o.maxlvl > maxlvl ? o.maxlvl : maxlvl;
+        reward_fx += (long long)(o.reward * 1048576.0);
+    }
+};
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, s);
+    return v;
+}
+__device__ __forceinline__ void flush_counters(const Counters& c, long long* out) {
+    if (!out) return;
+    long long v[7] = {c.steps, c.valid, c.episodes, c.score, c.reward_fx, c.inserts, c.dropped};
+    const int idx[7] = {G2048_C_STEPS, G2048_C_VALID, G2048_C_EPISODES, G2048_C_SCORE, G2048_C_REWARD_FX,
+                        G2048_C_INSERTS, G2048_C_DROPPED};
+    int mx = c.maxlvl;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, s));
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        long long s = warp_sum(v[i]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd((unsigned long long*)(out + idx[i]), (unsigned long long)s);
+    }
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(out + G2048_C_MAXLVL, (long long)mx);
+}
+
+}  // namespace g2048

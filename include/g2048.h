@@ -1,0 +1,227 @@
+/*
+ * g2048.h -- C ABI of libg2048.so: the B200 (sm_100a) batched 2048 environment,
+ * epsilon-greedy action selection and tabular Q-learning update.
+ *
+ * This is the drop-in boundary for the hot path of Rocco9999/2048_Q-Learning.
+ * The reference is pure Python and has no FFI of its own; each entry point cites
+ * the reference interface it replaces (paths relative to the reference root):
+ *   ENV-P  QLearningBase/environment/Game2048_env.py            (penalty flavour)
+ *   ENV-N  Deep_QLearning/environment/Game2048_nopenalty_env.py (nopenalty flavour)
+ *   AGENT  QLearningBase/Agent/main.py
+ *   DQN    Deep_QLearning/main_dir/Dqn8TestNOPERCNN.py, mainDQL_CNN_step2.py
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  g2048_* functions taking `stream` work on
+ *    DEVICE pointers owned by the caller (e.g. torch tensors' data_ptr()) and are
+ *    asynchronous on that CUDA stream (a cudaStream_t passed as void*, NULL = the
+ *    default stream).  g2048_ctx_* functions take HOST pointers, stage through
+ *    device buffers owned by the context and return when the results are in host
+ *    memory.
+ *  - Return value: 0 = ok, > 0 = a cudaError_t, < 0 = a G2048_ERR_* code;
+ *    g2048_last_error() describes the last failure of the calling thread.
+ *  - No CPU fallback exists: every compute entry point needs a CUDA device.
+ *  - A board is a uint64: cell (r,c) = nibble 4r+c = log2(tile), 0 = empty.
+ *  - One host thread (or process) per GPU; handles are not thread-safe.
+ */
+#ifndef G2048_H
+#define G2048_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define G2048_API extern "C" __attribute__((visibility("default")))
+#else
+#define G2048_API __attribute__((visibility("default")))
+#endif
+
+#define G2048_VERSION 100
+
+/* error codes (< 0) */
+#define G2048_ERR_ARG (-1)      /* bad argument (null pointer, bad flavour/mode, capacity not 2^k ...) */
+#define G2048_ERR_NOINIT (-2)   /* g2048_init(device) was not called for the current device */
+#define G2048_ERR_NOMEM (-3)    /* scratch buffer too small / allocation failed */
+
+/* env flavours */
+#define G2048_FLAVOUR_PENALTY 0    /* ENV-P: shaped float64 reward, stall penalty, lagged done */
+#define G2048_FLAVOUR_NOPENALTY 1  /* ENV-N + caller-commit protocol, integer reward, full-board quirk */
+
+/* flags byte written by env_step: bit0 valid, bit1 game_over, bit2 done, bits 4-7 legal-move mask of the
+ * resulting board (bit 4+a set iff action a would move it; mainDQL_CNN_step2.py:169-174) */
+#define G2048_FLAG_VALID 1
+#define G2048_FLAG_GAME_OVER 2
+#define G2048_FLAG_DONE 4
+
+/* per-env persistent state of ENV-P (Game2048_env.py:84-95; survives reset(), :187-191), one uint64:
+ * bits 0-7 log2(previous_max) | 8-15 consecutive_action (0xFF = None) | 16-23 index into the stall
+ * penalty sequence (last_consecutive_penalty) | 32-63 consecutive_count */
+#define G2048_AUX_INIT 0x000000000000FF01ull
+
+/* Philox streams: counter = (env id, step, stream), key = seed */
+#define G2048_STREAM_STEP 0       /* x0,x1 spawn of the move; x2 epsilon test; x3 random action */
+#define G2048_STREAM_RESET 1      /* explicit env_reset: x0..x3 = the two spawns */
+#define G2048_STREAM_QUIRK 2      /* ENV-N full-board spawn */
+#define G2048_STREAM_AUTORESET 3  /* in-rollout reset after done */
+
+/* counters (int64[G2048_N_COUNTERS], accumulated with atomics; the caller zeroes them) */
+#define G2048_C_STEPS 0
+#define G2048_C_VALID 1
+#define G2048_C_EPISODES 2
+#define G2048_C_SCORE 3      /* sum of merge scores */
+#define G2048_C_MAXLVL 4     /* max log2(tile) seen */
+#define G2048_C_REWARD_FX 5  /* sum of trunc(reward * 2^20): order-independent checksum of the rewards */
+#define G2048_C_INSERTS 6    /* new Q-table states */
+#define G2048_C_DROPPED 7    /* lookups that hit the probe limit (table too full) */
+#define G2048_N_COUNTERS 8
+
+/* Q-learning modes */
+#define G2048_MODE_ATOMIC 0         /* deltas applied with float atomics (sum order unspecified) */
+#define G2048_MODE_DETERMINISTIC 1  /* sort by (state, action) + segmented sum in ascending env order */
+
+#define G2048_QTABLE_SLOT_BYTES 32  /* key u64 | meta u64 | float q[4] */
+
+/* one-hot dtypes */
+#define G2048_DTYPE_F32 0
+#define G2048_DTYPE_BF16 1
+
+/* ------------------------------------------------------------------ library */
+G2048_API int g2048_version(void);
+G2048_API const char* g2048_last_error(void);
+/* Builds the 64K-entry row LUT and the reward tables and uploads them to `device`; idempotent. */
+G2048_API int g2048_init(int device);
+G2048_API int g2048_device_count(void);
+/* pinned host memory for the ctx API (cudaHostAlloc / cudaFreeHost) */
+G2048_API void* g2048_host_alloc(size_t bytes);
+G2048_API void g2048_host_free(void* p);
+
+/* ------------------------------------------------------------------ env (device pointers) */
+/* ENV-P/ENV-N reset() -> Game2048.__init__ (Game2048_env.py:11-14, :187-191): empty board + two spawns,
+ * score = 0, aux untouched.  mask: NULL = all, else only envs with mask[i] != 0.
+ * replay_draws: NULL = Philox(seed, env id, episode_idx, STREAM_RESET), else uint8[n][4] =
+ * {k_a, is4_a, k_b, is4_b} as drawn by the reference (np.random.randint / random() >= 0.9). */
+G2048_API int g2048_env_reset(uint64_t* boards, int32_t* score, const uint8_t* mask, const uint8_t* replay_draws,
+                              int64_t n, uint64_t seed, uint64_t episode_idx, uint64_t env_id_base, void* stream);
+
+/* Game2048_env.step(action) for n envs (ENV-P Game2048_env.py:97-129; ENV-N
+ * Game2048_nopenalty_env.py:106-120 with the caller's commit of mainDQL_CNN_step2.py:237 folded in).
+ * In/out: boards, aux (ENV-P, may be NULL for ENV-N), score (may be NULL).
+ * replay_draws: NULL = Philox(seed, env id, step_idx), else uint8[n][4] = {k, is4, k_quirk, is4_quirk}
+ * recorded from the reference (bit-exact replay).  Outputs (each may be NULL): reward_f64 / reward_f32,
+ * flags, maxlvl (log2 of the returned max_number), move_score. */
+G2048_API int g2048_env_step(uint64_t* boards, uint64_t* aux, int32_t* score, const uint8_t* actions,
+                             const uint8_t* replay_draws, double* reward_f64, float* reward_f32, uint8_t* flags,
+                             uint8_t* maxlvl, int32_t* move_score, int64_t n, int flavour, uint64_t seed,
+                             uint64_t step_idx, uint64_t env_id_base, void* stream);
+
+/* Game2048.move(action, trial=True) (Game2048_nopenalty_env.py:53-66): the move without the spawn.
+ * out_boards (may be NULL) receives the moved boards, moved[n] / move_score[n] (each may be NULL) the
+ * reference's (moved, score) return pair.  boards_in is not modified. */
+G2048_API int g2048_move_trial(const uint64_t* boards_in, const uint8_t* actions, uint64_t* out_boards, uint8_t* moved,
+                               int32_t* move_score, int64_t n, void* stream);
+
+/* game.move(a, trial=True) for a in 0..3 -> 4-bit mask (mainDQL_CNN_step2.py:169-174); mask 0 == is_game_over */
+G2048_API int g2048_legal_mask(const uint64_t* boards, uint8_t* out, int64_t n, void* stream);
+
+/* np.int64[n][16] raw tile values (the reference's board arrays) <-> packed boards.  bad_count (device
+ * int64, may be NULL) counts cells that are not 0 or a power of two in 2..32768. */
+G2048_API int g2048_pack_i64(const int64_t* tiles, uint64_t* boards, int64_t n, int64_t* bad_count, void* stream);
+G2048_API int g2048_unpack_i64(const uint64_t* boards, int64_t* tiles, int64_t n, void* stream);
+
+/* DQNAgent.encode_state (Dqn8TestNOPERCNN.py:271-277): out[n][16 level][4][4], float32 or bfloat16 */
+G2048_API int g2048_encode_onehot(const uint64_t* boards, void* out, int64_t n, int dtype, void* stream);
+
+/* DQNAgent.act / act_ripetitive (Dqn8TestNOPERCNN.py:312-336) on network outputs qvalues[n][4]:
+ * explore iff x2 < floor(eps * 2^32) (Philox STREAM_STEP); legal_mask NULL = act (uniform over 4 / plain argmax), else
+ * act_ripetitive (uniform over legal moves / argmax over legal moves; no legal move = act). */
+G2048_API int g2048_select_action(const float* qvalues, const uint8_t* legal_mask, uint8_t* actions, int64_t n,
+                                  double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base, void* stream);
+
+/* ------------------------------------------------------------------ fused rollouts (boards in registers) */
+/* k_steps env steps per env under the uniform-random policy (action = x3 >> 30), in-kernel reset on done. */
+G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n, int64_t k_steps,
+                                   int flavour, uint64_t seed, uint64_t step_base, uint64_t env_id_base,
+                                   int64_t* counters, void* stream);
+
+/* The loop of main.py:91-101 for n envs and k_steps steps each, fused: epsilon-greedy choose_action
+ * (main.py:34-38) -> env step -> update_q_value (main.py:40-43) on the HBM hash table, asynchronously
+ * (each env applies its update at once with a float atomic; N = 1 is the reference's sequential order). */
+G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
+                                   int64_t n, int64_t k_steps, int flavour, float lr, float gamma, double eps,
+                                   uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t* counters,
+                                   void* stream);
+
+/* One synchronous batched Q-learning step: every env chooses from and bootstraps
+ * on the table as it is at step start; the deltas are applied afterwards (mode ATOMIC or DETERMINISTIC).
+ * rec_key/rec_action/rec_delta (each may be NULL) export the (state, action, delta) records, e.g. for the
+ * cross-GPU exchange; apply = 0 only emits them and leaves the Q values untouched. */
+G2048_API size_t g2048_qlearn_scratch_bytes(int64_t n);
+G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
+                                int64_t n, int flavour, float lr, float gamma, double eps, int mode, int apply,
+                                uint64_t seed, uint64_t step_idx, uint64_t env_id_base, int64_t* counters,
+                                uint64_t* rec_key, uint8_t* rec_action, float* rec_delta, void* scratch,
+                                size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------ Q-table (device pointers) */
+/* QLearningAgent.q_table (main.py:16): `table` is capacity * 32 bytes of device memory, capacity = 2^k. */
+G2048_API size_t g2048_qtable_bytes(uint64_t capacity);
+G2048_API int g2048_qtable_clear(void* table, uint64_t capacity, void* stream);
+/* q_table[state] for n states -> rows[n][4]; found[n] (may be NULL); insert != 0 creates missing zero rows
+ * like the reference's defaultdict. */
+G2048_API int g2048_qtable_lookup(void* table, uint64_t capacity, const uint64_t* keys, int64_t n, float* rows,
+                                  uint8_t* found, int insert, void* stream);
+/* choose_action (main.py:34-38) for n states with Philox(seed, env id, step_idx) draws */
+G2048_API int g2048_choose_action(void* table, uint64_t capacity, const uint64_t* boards, uint8_t* actions, int64_t n,
+                                  double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base, void* stream);
+/* update_q_value (main.py:40-43) for n transitions as ONE synchronous batch (N = 1: the reference). */
+G2048_API int g2048_qtable_update(void* table, uint64_t capacity, const uint64_t* s, const uint8_t* a, const float* r,
+                                  const uint64_t* s2, const uint8_t* done, int64_t n, float lr, float gamma, int mode,
+                                  void* scratch, size_t scratch_bytes, void* stream);
+/* Q[key][a] += delta for n records (e.g. all-gathered from the other ranks), same modes. */
+G2048_API int g2048_qtable_apply_deltas(void* table, uint64_t capacity, const uint64_t* keys, const uint8_t* a,
+                                        const float* delta, int64_t n, int mode, void* scratch, size_t scratch_bytes,
+                                        void* stream);
+/* number of states -> *count (device int64) */
+G2048_API int g2048_qtable_size(const void* table, uint64_t capacity, int64_t* count, void* stream);
+/* compact (key, row) pairs into keys[max_out], rows[max_out][4]; *count (device int64, zeroed by the caller)
+ * receives the number of states (may exceed max_out: the excess is not written) */
+G2048_API int g2048_qtable_export(const void* table, uint64_t capacity, uint64_t* keys, float* rows, int64_t max_out,
+                                  int64_t* count, void* stream);
+
+/* ------------------------------------------------------------------ host-buffer API */
+typedef struct g2048_ctx g2048_ctx;
+/* device buffers for up to max_envs envs, one stream, and (table_capacity > 0) a Q-table in HBM */
+G2048_API g2048_ctx* g2048_ctx_create(int device, int64_t max_envs, uint64_t table_capacity);
+G2048_API void g2048_ctx_destroy(g2048_ctx* ctx);
+G2048_API int g2048_ctx_env_reset(g2048_ctx* ctx, uint64_t* boards, int32_t* score, const uint8_t* mask,
+                                  const uint8_t* replay_draws, int64_t n, uint64_t seed, uint64_t episode_idx,
+                                  uint64_t env_id_base);
+G2048_API int g2048_ctx_env_step(g2048_ctx* ctx, uint64_t* boards, uint64_t* aux, int32_t* score,
+                                 const uint8_t* actions, const uint8_t* replay_draws, double* reward_f64,
+                                 uint8_t* flags, uint8_t* maxlvl, int32_t* move_score, int64_t n, int flavour,
+                                 uint64_t seed, uint64_t step_idx, uint64_t env_id_base);
+G2048_API int g2048_ctx_legal_mask(g2048_ctx* ctx, const uint64_t* boards, uint8_t* out, int64_t n);
+G2048_API int g2048_ctx_move_trial(g2048_ctx* ctx, const uint64_t* boards_in, const uint8_t* actions,
+                                   uint64_t* out_boards, uint8_t* moved, int32_t* move_score, int64_t n);
+G2048_API int g2048_ctx_rollout_random(g2048_ctx* ctx, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n,
+                                       int64_t k_steps, int flavour, uint64_t seed, uint64_t step_base,
+                                       uint64_t env_id_base, int64_t* counters);
+G2048_API int g2048_ctx_rollout_qlearn(g2048_ctx* ctx, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n,
+                                       int64_t k_steps, int flavour, float lr, float gamma, double eps, uint64_t seed,
+                                       uint64_t step_base, uint64_t env_id_base, int64_t* counters);
+G2048_API int g2048_ctx_qtable_lookup(g2048_ctx* ctx, const uint64_t* keys, int64_t n, float* rows, uint8_t* found,
+                                      int insert);
+G2048_API int g2048_ctx_choose_action(g2048_ctx* ctx, const uint64_t* boards, uint8_t* actions, int64_t n, double eps,
+                                      uint64_t seed, uint64_t step_idx, uint64_t env_id_base);
+G2048_API int g2048_ctx_qtable_update(g2048_ctx* ctx, const uint64_t* s, const uint8_t* a, const float* r,
+                                      const uint64_t* s2, const uint8_t* done, int64_t n, float lr, float gamma,
+                                      int mode);
+G2048_API int64_t g2048_ctx_qtable_size(g2048_ctx* ctx);
+G2048_API int64_t g2048_ctx_qtable_export(g2048_ctx* ctx, uint64_t* keys, float* rows, int64_t max_out);
+G2048_API int g2048_ctx_qtable_clear(g2048_ctx* ctx);
+/* raw handles for callers that mix both APIs */
+G2048_API void* g2048_ctx_table(g2048_ctx* ctx);
+G2048_API uint64_t g2048_ctx_table_capacity(g2048_ctx* ctx);
+G2048_API void* g2048_ctx_stream(g2048_ctx* ctx);
+
+#endif /* G2048_H */

@@ -70,7 +70,7 @@ def load():
             "orc_rollout_random": (None, [vp, vp, vp, i64, i64, i32, u64, u64, u64, vp]),
             "orc_choose_action": (None, [vp, vp, i64, u64, u64, u64, u64, vp]),
             "orc_rollout_qlearn_seq": (None, [vp, vp, vp, vp, i64, i64, i32, f32, f32, u64, u64, u64, u64, vp]),
-            "orc_qlearn_step_sync": (None, [vp, vp, vp, vp, i64, i32, f32, f32, u64, u64, u64, u64, vp, vp, vp, vp]),
+            "orc_qlearn_step_sync": (None, [vp, vp, vp, vp, i64, i32, f32, f32, u64, u64, u64, u64, vp, vp, vp, vp, i32]),
             "orc_rollout_random_mt": (None, [vp, vp, vp, i64, i64, i32, u64, u64, u64, vp, i32]),
             "orc_rollout_qlearn_mt": (None, [vp, vp, vp, i64, i64, i32, f32, f32, u64, u64, u64, u64, vp, u64, i32]),
         }
@@ -244,7 +244,7 @@ def rollout_qlearn_mt(boards, aux, score, k_steps, lr, gamma, eps, table_capacit
 
 
 def qlearn_step_sync(boards, aux, score, table: QTable, lr, gamma, eps, flavour=FLAVOUR_PENALTY, seed=0, step=0,
-                     env_id_base=0, records=False):
+                     env_id_base=0, records=False, apply=True):
     n = len(boards)
     counters = np.zeros(N_COUNTERS, np.int64)
     rk = np.zeros(n, np.uint64) if records else None
@@ -252,7 +252,7 @@ def qlearn_step_sync(boards, aux, score, table: QTable, lr, gamma, eps, flavour=
     rd = np.zeros(n, np.float32) if records else None
     load().orc_qlearn_step_sync(_p(boards, np.uint64), _p(aux, np.uint64), _p(score, np.int32), table.h, n, flavour,
                                 lr, gamma, eps_threshold(eps), seed, step, env_id_base, _p(counters, np.int64),
-                                _p(rk, np.uint64), _p(ra, np.uint8), _p(rd, np.float32))
+                                _p(rk, np.uint64), _p(ra, np.uint8), _p(rd, np.float32), int(apply))
     return counters, (rk, ra, rd)
 
 

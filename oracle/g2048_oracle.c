@@ -269,6 +269,7 @@ typedef struct {
 
 /* Game2048_env.step, penalty flavour (Game2048_env.py:97-129).
  * d = {k, is4} spawn draws for the agent's move (used iff the move is valid). */
+static int g_want_legal = 1; /* rollouts do not need the legal-move nibble of flags */
 static void penalty_step(env_t *e, int action, int k, int is4, out_t *o) {
     int prev_level = (int)(e->aux & 0xFF);
     int cons_action = (int)((e->aux >> 8) & 0xFF);
@@ -301,7 +302,7 @@ static void penalty_step(env_t *e, int action, int k, int is4, out_t *o) {
     o->reward = reward;
     o->move_score = (int32_t)score;
     o->flags = (uint8_t)((valid ? FLAG_VALID : 0) | (game_over ? FLAG_GAME_OVER : 0) |
-                         (done ? FLAG_DONE : 0) | (legal_mask(e->board) << 4));
+                         (done ? FLAG_DONE : 0) | (g_want_legal ? legal_mask(e->board) << 4 : 0));
     o->maxlvl = (uint8_t)lvl;
 }
 
@@ -339,7 +340,7 @@ static void nopenalty_step(env_t *e, int action, int k1, int f1, int k2, int f2,
     o->reward = reward;
     o->move_score = (int32_t)score;
     o->flags = (uint8_t)((valid ? FLAG_VALID : 0) | (game_over ? FLAG_GAME_OVER : 0) |
-                         (done ? FLAG_DONE : 0) | (legal_mask(M) << 4));
+                         (done ? FLAG_DONE : 0) | (g_want_legal ? legal_mask(M) << 4 : 0));
     o->maxlvl = (uint8_t)lvl;
 }
 
@@ -396,6 +397,7 @@ ORC_API void orc_env_step(uint64_t *boards, uint64_t *aux, int32_t *score, const
                           const uint8_t *replay_draws, double *reward, uint8_t *flags, uint8_t *maxlvl,
                           int32_t *move_score, int64_t n, int flavour, uint64_t seed, uint64_t step_idx,
                           uint64_t env_id_base) {
+    g_want_legal = flags != NULL;
     for (int64_t i = 0; i < n; ++i) {
         env_t e = {boards[i], aux ? aux[i] : AUX_INIT, score ? score[i] : 0};
         out_t o;
@@ -706,6 +708,7 @@ static void count_step(int64_t *c, const out_t *o) {
 ORC_API void orc_rollout_random(uint64_t *boards, uint64_t *aux, int32_t *score, int64_t n, int64_t k_steps,
                                 int flavour, uint64_t seed, uint64_t step_base, uint64_t env_id_base,
                                 int64_t *counters) {
+    g_want_legal = 0;
     for (int64_t i = 0; i < n; ++i) {
         env_t e = {boards[i], aux ? aux[i] : AUX_INIT, score ? score[i] : 0};
         uint64_t id = env_id_base + (uint64_t)i;
@@ -759,6 +762,7 @@ ORC_API void orc_rollout_qlearn_seq(uint64_t *boards, uint64_t *aux, int32_t *sc
                                     uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t *counters) {
     float *rows = (float *)t->rows;
     static const float zero[4] = {0, 0, 0, 0};
+    g_want_legal = 0;
     for (int64_t k = 0; k < k_steps; ++k) {
         uint64_t step = step_base + (uint64_t)k;
         for (int64_t i = 0; i < n; ++i) {
@@ -794,9 +798,10 @@ ORC_API void orc_rollout_qlearn_seq(uint64_t *boards, uint64_t *aux, int32_t *sc
 ORC_API void orc_qlearn_step_sync(uint64_t *boards, uint64_t *aux, int32_t *score, qtab_t *t, int64_t n,
                                   int flavour, float lr, float gamma, uint64_t eps_thresh, uint64_t seed,
                                   uint64_t step, uint64_t env_id_base, int64_t *counters,
-                                  uint64_t *rec_key, uint8_t *rec_action, float *rec_delta) {
+                                  uint64_t *rec_key, uint8_t *rec_action, float *rec_delta, int apply) {
     float *rows = (float *)t->rows;
     static const float zero[4] = {0, 0, 0, 0};
+    g_want_legal = 0;
     int64_t *slot = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
     uint8_t *act = (uint8_t *)malloc((size_t)(n ? n : 1));
     float *delta = (float *)malloc((size_t)(n ? n : 1) * sizeof(float));
@@ -823,8 +828,8 @@ ORC_API void orc_qlearn_step_sync(uint64_t *boards, uint64_t *aux, int32_t *scor
         if (aux) aux[i] = e.aux;
         if (score) score[i] = e.score;
     }
-    /* a new state inserted after the fresh env's board is looked up next step */
-    apply_deltas_sorted(rows, slot, act, delta, n);
+    /* apply = 0: emit the records only (the cross-rank exchange applies them) */
+    if (apply) apply_deltas_sorted(rows, slot, act, delta, n);
     free(delta); free(act); free(slot);
 }
 

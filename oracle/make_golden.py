@@ -16,6 +16,7 @@ Files
   env_nopenalty.npz  Deep_QLearning/environment/Game2048_nopenalty_env.py under the
                      caller protocol of mainDQL_CNN_step2.py:163-237 (caller commits the board)
   qlearn_ref.npz     QLearningBase/Agent/main.py QLearningAgent driven by the loop main.py:80-109
+  compat_seeded.npz  both envs and the full tabular loop under fixed np.random / random seeds
 """
 from __future__ import annotations
 
@@ -295,6 +296,61 @@ def record_qlearn(episodes: int = 150):
     }
 
 
+def record_seeded(steps: int = 400, episodes: int = 20):
+    """What a user of the reference sees under fixed seeds (for the drop-in adapters, rng="numpy"/"python"):
+    (a) both envs driven by a fixed action sequence under np.random.seed(4242);
+    (b) the full tabular loop main.py:80-109 under np.random.seed(1) / random.seed(1)."""
+    out = {}
+    for flavour in ("penalty", "nopenalty"):
+        mod = ref_shim.load_penalty_env() if flavour == "penalty" else ref_shim.load_nopenalty_env()
+        np.random.seed(4242)
+        actions = np.random.RandomState(7).randint(0, 4, size=steps)
+        env = mod.Game2048_env()
+        boards, rewards, dones, maxes, scores, first = [], [], [], [], [], pack_board(env.game.board)
+        for t in range(steps):
+            board, reward, done, max_number = env.step(int(actions[t]))
+            if flavour == "nopenalty":
+                env.game.board = board
+            boards.append(pack_board(board)); rewards.append(float(reward)); dones.append(int(bool(done)))
+            maxes.append(int(max_number)); scores.append(int(env.score))
+            if done:
+                env.reset()
+                boards[-1] = pack_board(env.game.board)  # what the next step starts from
+        out.update({f"{flavour}_actions": actions.astype(np.uint8), f"{flavour}_first": np.uint64(first),
+                    f"{flavour}_boards": np.array(boards, np.uint64), f"{flavour}_rewards": np.array(rewards),
+                    f"{flavour}_dones": np.array(dones, np.uint8), f"{flavour}_max": np.array(maxes, np.int64),
+                    f"{flavour}_scores": np.array(scores, np.int64)})
+    penv = ref_shim.load_penalty_env()
+    agent_mod = ref_shim.load_tabular_agent()
+    np.random.seed(1)
+    pyrandom.seed(1)
+    env = penv.Game2048_env()
+    agent = agent_mod.QLearningAgent(episodes, action_space=env.action_space.n, learning_rate=0.1,
+                                     discount_factor=0.99, exploration_rate=0.95)
+    A, R, B, totals = [], [], [], []
+    for episode in range(episodes):
+        state = tuple(map(tuple, env.reset()))
+        done, total = False, 0
+        while not done:
+            action = agent.choose_action(state)
+            next_state, reward, done, info = env.step(action)
+            next_state = tuple(map(tuple, next_state))
+            _ = agent.q_table[state]
+            agent.update_q_value(state, action, reward, next_state, done)
+            state = next_state
+            total += reward
+            A.append(int(action)); R.append(float(reward)); B.append(pack_board(next_state))
+        totals.append(total)
+        agent.decay_exploration(episode)
+    keys = np.array([pack_board(k) for k in agent.q_table.keys()], np.uint64)
+    rows = np.array([np.asarray(v, np.float64) for v in agent.q_table.values()]).reshape(-1, 4)
+    order = np.argsort(keys)
+    out.update({"loop_actions": np.array(A, np.uint8), "loop_rewards": np.array(R), "loop_boards": np.array(B, np.uint64),
+                "loop_totals": np.array(totals), "loop_q_keys": keys[order], "loop_q_rows": rows[order],
+                "loop_params": np.array([episodes, 0.1, 0.99, 0.95], np.float64), "loop_eps_final": np.float64(agent.epsilon)})
+    return out
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit(f"reference not found under {ref_shim.REF_ROOT}")
@@ -307,6 +363,10 @@ def main():
         print(f"{path}: {fl.size} steps, valid {np.mean(fl & 1):.3f}, game_over {int(np.sum((fl >> 1) & 1))}, "
               f"done {int(np.sum((fl >> 2) & 1))}, resets {len(g['reset_board'])}, max level {int(g['maxlvl'].max())}, "
               f"{os.path.getsize(path) / 1e3:.0f} kB")
+    sd = record_seeded()
+    path = os.path.join(OUT_DIR, "compat_seeded.npz")
+    np.savez_compressed(path, **sd)
+    print(f"{path}: {len(sd['loop_actions'])} loop steps, {os.path.getsize(path) / 1e3:.0f} kB")
     q = record_qlearn()
     path = os.path.join(OUT_DIR, "qlearn_ref.npz")
     np.savez_compressed(path, **q)

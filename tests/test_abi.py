@@ -1,0 +1,70 @@
+"""CPU-side checks of the boundary: the C-ABI library builds for sm_100a, loads, exports every symbol
+include/g2048.h declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import g2048
+from g2048 import _lib
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = g2048.build()
+    assert os.path.exists(path)
+    handle = ctypes.CDLL(path)
+    declared = g2048.declared_symbols()
+    assert len(declared) >= 40
+    missing = [s for s in declared if not hasattr(handle, s)]
+    assert not missing, missing
+    assert set(_lib._SIG) == set(declared), set(_lib._SIG) ^ set(declared)
+    assert handle.g2048_version() == 100
+
+
+def test_only_the_c_abi_is_exported():
+    out = subprocess.run(["nm", "-D", "--defined-only", g2048.build()], capture_output=True, text=True).stdout
+    syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert syms and all(s.startswith("g2048_") for s in syms), [s for s in syms if not s.startswith("g2048_")][:5]
+
+
+def test_sass_is_sm100a_with_bulk_copy_and_256bit_loads():
+    sass = subprocess.run(["cuobjdump", "-sass", g2048.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UBLKCP" in sass          # cp.async.bulk (TMA) staging of the row LUT
+    assert ".256" in sass            # one 32-byte load per Q-table slot
+    assert "REDG.E.ADD.F32" in sass  # float atomics on Q values without a return trip
+
+
+@pytest.mark.skipif(ctypes.CDLL(g2048.build()).g2048_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback():
+    with pytest.raises(g2048.G2048Error, match="no CPU fallback"):
+        g2048.Game2048_env()
+    with pytest.raises(g2048.G2048Error):
+        g2048.init(0)
+    L = g2048.lib()
+    b = np.zeros(4, np.uint64)
+    rc = L.g2048_legal_mask(b.ctypes.data, b.ctypes.data, 4, None)   # compute entry without init -> error code
+    assert rc != 0 and L.g2048_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "2048_q-learning_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "g2048_oracle" not in text, f
+
+
+def test_tile_packing_roundtrip():
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        lv = rng.randint(0, 16, size=16)
+        tiles = np.where(lv > 0, 1 << lv.astype(np.int64), 0).reshape(4, 4)
+        b = g2048.pack_tiles(tiles)
+        assert np.array_equal(g2048.unpack_tiles(b), tiles)
+    with pytest.raises(ValueError):
+        g2048.pack_tiles(np.full((4, 4), 3))

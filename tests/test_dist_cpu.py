@@ -1,0 +1,80 @@
+"""The N > 1 path on CPU: two gloo processes run the sharded synchronous Q-learning exchange
+(dist.ShardedQLearning) with an oracle-backed engine and must reproduce the single-process table and
+boards exactly -- sharding invariance through global env ids and rank-ordered record gathering."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N_TOTAL, STEPS, SEED = 1001, 12, 77   # odd size: unequal shards exercise the padding
+
+
+class OracleEngine:
+    def __init__(self, lo, hi):
+        import oracle
+        self.o, self.lo = oracle, lo
+        n = hi - lo
+        self.boards = np.zeros(n, np.uint64)
+        oracle.env_reset(self.boards, None, None, None, seed=SEED, episode_idx=0, env_id_base=lo)
+        self.aux = np.full(n, oracle.AUX_INIT, np.uint64)
+        self.score = np.zeros(n, np.int32)
+        self.tab = oracle.QTable(1 << 16, f32=True)
+        self.t = 0
+
+    def emit(self):
+        _, (k, a, d) = self.o.qlearn_step_sync(self.boards, self.aux, self.score, self.tab, 0.1, 0.99, 0.4, 0, SEED,
+                                               self.t, self.lo, records=True, apply=False)
+        self.t += 1
+        return torch.from_numpy(k.view(np.int64)), torch.from_numpy(a), torch.from_numpy(d)
+
+    def apply(self, keys, actions, deltas):
+        self.tab.apply_deltas_f32(keys.numpy().view(np.uint64).copy(), actions.numpy().copy(), deltas.numpy().copy())
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import g2048
+    from g2048 import dist as gdist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = gdist.shard_range(N_TOTAL, rank, world)
+    eng = OracleEngine(lo, hi)
+    sh = gdist.ShardedQLearning(eng, N_TOTAL)
+    for _ in range(STEPS):
+        sh.step()
+    keys, rows = eng.tab.export()
+    nz = np.abs(rows).sum(1) > 0
+    np.savez(os.path.join(out, f"rank{rank}.npz"), boards=eng.boards, keys=keys[nz], rows=rows[nz], lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions_exactly():
+    from g2048 import dist as gdist
+    for n, w in ((10, 3), (8, 8), (1 << 23, 8), (5, 8)):
+        r = [gdist.shard_range(n, i, w) for i in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_exchange_equals_single_process(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sys.path.insert(0, ROOT)
+    single = OracleEngine(0, N_TOTAL)
+    for t in range(STEPS):
+        single.o.qlearn_step_sync(single.boards, single.aux, single.score, single.tab, 0.1, 0.99, 0.4, 0, SEED, t, 0)
+    keys, rows = single.tab.export()
+    nz = np.abs(rows).sum(1) > 0
+    for rank in range(2):
+        d = np.load(tmp_path / f"rank{rank}.npz")
+        assert np.array_equal(d["boards"], single.boards[int(d["lo"]):int(d["hi"])])
+        assert np.array_equal(d["keys"], keys[nz])
+        assert np.array_equal(d["rows"], rows[nz])     # float32 sums in the same (global env id) order: bit-identical

@@ -1,0 +1,316 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  The CUDA path is driven through the C ABI
+(ctypes, include/g2048.h) and compared with the CPU oracle -- bit-exact for boards, flags, scores, aux
+state, the float64 shaped reward and (deterministic mode) the float32 Q-table; atomic-mode Q values
+within the float32 tolerance stated in the test.  Golden vectors recorded from the reference itself are
+replayed as well.  Nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from test_oracle_golden import replay_env
+
+pytestmark = pytest.mark.gpu
+
+Q_ATOL, Q_RTOL = 1e-5, 1e-5   # float32 atomic-sum-order tolerance (1e-6 is typical)
+
+
+def vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def L():
+    import g2048
+    g2048.init(0)
+    return g2048.lib()
+
+
+@pytest.fixture(scope="module")
+def ctx(L):
+    handle = L.g2048_ctx_create(0, 1 << 20, 1 << 22)
+    assert handle, L.g2048_last_error()
+    yield handle
+    L.g2048_ctx_destroy(handle)
+
+
+def ok(L, rc):
+    assert rc == 0, L.g2048_last_error().decode()
+
+
+def random_boards(rng, n, lmax=15, p_zero=0.3):
+    lv = rng.randint(1, lmax + 1, size=(n, 16))
+    lv = np.where(rng.random_sample((n, 16)) < p_zero, 0, lv).astype(np.uint64)
+    b = np.zeros(n, np.uint64)
+    for j in range(16):
+        b |= lv[:, j] << np.uint64(4 * j)
+    b[b == 0] = 1
+    return b
+
+
+def fresh_envs(n, seed=5, episode=0, base=0):
+    boards = np.zeros(n, np.uint64)
+    oracle.env_reset(boards, None, None, None, seed=seed, episode_idx=episode, env_id_base=base)
+    return boards, np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+
+
+# ------------------------------------------------------------------------------------------ moves
+def test_row_lut_all_65536_rows(L, ctx):
+    """Every row through move(0) on the GPU == the oracle's restatement of move_left."""
+    res, mg = oracle.row_table()
+    rows = np.arange(65536, dtype=np.uint64)
+    for shift in (0, 16, 32, 48):   # the row in each of the four board rows
+        boards = rows << np.uint64(shift)
+        boards[0] = 1
+        out, moved, sc = np.zeros_like(boards), np.zeros(65536, np.uint8), np.zeros(65536, np.int32)
+        ok(L, L.g2048_ctx_move_trial(ctx, vp(boards), vp(np.zeros(65536, np.uint8)), vp(out), vp(moved), vp(sc), 65536))
+        want = res.astype(np.uint64) << np.uint64(shift)
+        score = np.array([(1 << (m >> 4) if m >> 4 else 0) + (1 << (m & 15) if m & 15 else 0) for m in mg], np.int32)
+        assert np.array_equal(out[1:], want[1:]) and np.array_equal(sc[1:], score[1:])
+        assert np.array_equal(moved[1:] != 0, (want != boards)[1:])
+
+
+@pytest.mark.parametrize("lmax,p_zero", [(15, 0.3), (15, 0.0), (3, 0.1), (11, 0.6), (2, 0.0)])
+def test_moves_and_legal_mask_random_boards(L, ctx, lmax, p_zero):
+    rng = np.random.RandomState(lmax * 7 + int(p_zero * 10))
+    n = 200_000
+    boards = random_boards(rng, n, lmax, p_zero)
+    actions = rng.randint(0, 4, size=n).astype(np.uint8)
+    out, moved, sc = np.zeros_like(boards), np.zeros(n, np.uint8), np.zeros(n, np.int32)
+    ok(L, L.g2048_ctx_move_trial(ctx, vp(boards), vp(actions), vp(out), vp(moved), vp(sc), n))
+    wb, wm, ws = oracle.move(boards, actions)
+    assert np.array_equal(out, wb) and np.array_equal(moved, wm) and np.array_equal(sc, ws)
+    lm = np.zeros(n, np.uint8)
+    ok(L, L.g2048_ctx_legal_mask(ctx, vp(boards), vp(lm), n))
+    assert np.array_equal(lm, oracle.legal_mask(boards))
+    assert np.array_equal((lm == 0) & ((boards != 0)), oracle.dead(boards).astype(bool))
+
+
+# ------------------------------------------------------------------------------------------ golden replay
+def make_ctx_step(L, ctx):
+    def step(boards, aux, score, actions, draws, flavour):
+        n = len(boards)
+        r, f, m, ms = np.zeros(n), np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        ok(L, L.g2048_ctx_env_step(ctx, vp(boards), vp(aux), vp(score), vp(actions), vp(draws), vp(r), vp(f), vp(m),
+                                   vp(ms), n, flavour, 0, 0, 0))
+        return r, f, m, ms
+    return step
+
+
+@pytest.mark.parametrize("name,flavour", [("env_penalty", 0), ("env_nopenalty", 1)])
+def test_env_step_replays_reference_golden(L, ctx, golden, name, flavour):
+    """Bit-exact replay of action/spawn trajectories recorded from the reference (BASELINE config 2 form)."""
+    replay_env(golden(name), flavour, make_ctx_step(L, ctx))
+
+
+@pytest.mark.parametrize("name", ["env_penalty", "env_nopenalty"])
+def test_env_reset_replays_reference_golden(L, ctx, golden, name):
+    g = golden(name)
+    n = len(g["reset_board"])
+    boards, score = np.zeros(n, np.uint64), np.ones(n, np.int32)
+    ok(L, L.g2048_ctx_env_reset(ctx, vp(boards), vp(score), None, vp(np.ascontiguousarray(g["reset_draws"])), n, 0, 0, 0))
+    assert np.array_equal(boards, g["reset_board"]) and not score.any()
+
+
+@pytest.mark.parametrize("flavour", [0, 1])
+def test_env_step_philox_4096_envs_512_steps(L, ctx, flavour):
+    """BASELINE config 2 size: 4096 envs x 512 steps, every output of every step against the oracle."""
+    n, T, seed, base = 4096, 512, 0xABCDEF, 1 << 33
+    rng = np.random.RandomState(flavour)
+    gb, ga, gs = fresh_envs(n, seed, 0, base)
+    cb, ca, cs = gb.copy(), ga.copy(), gs.copy()
+    step = None
+    for t in range(T):
+        actions = rng.randint(0, 4, size=n).astype(np.uint8)
+        r, f, m, ms = np.zeros(n), np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        ok(L, L.g2048_ctx_env_step(ctx, vp(gb), vp(ga), vp(gs), vp(actions), None, vp(r), vp(f), vp(m), vp(ms), n,
+                                   flavour, seed, t, base))
+        wr, wf, wm, wms = oracle.env_step(cb, ca, cs, actions, None, flavour, seed, t, base)
+        assert np.array_equal(gb, cb), t
+        assert np.array_equal(f, wf) and np.array_equal(m, wm) and np.array_equal(ms, wms), t
+        assert np.array_equal(r.view(np.uint64), wr.view(np.uint64)), t
+        assert np.array_equal(gs, cs), t
+        if flavour == 0:
+            assert np.array_equal(ga, ca), t
+        done = ((f >> 2) & 1).astype(np.uint8)
+        if done.any():
+            ok(L, L.g2048_ctx_env_reset(ctx, vp(gb), vp(gs), vp(done), None, n, seed, t + 1, base))
+            oracle.env_reset(cb, cs, done, None, seed, t + 1, base)
+            assert np.array_equal(gb, cb)
+    assert step is None
+
+
+# ------------------------------------------------------------------------------------------ fused rollouts
+@pytest.mark.parametrize("flavour", [0, 1])
+@pytest.mark.parametrize("n,k", [(20000, 300), (1000, 700), (1, 2000)])
+def test_rollout_random_matches_oracle(L, ctx, flavour, n, k):
+    """Fused K-step rollout (boards in registers, smem LUT for n >= 16384) == oracle, bit for bit."""
+    seed, base, t0 = 99 + n, 12345, 7
+    gb, ga, gs = fresh_envs(n, seed, 0, base)
+    cb, ca, cs = gb.copy(), ga.copy(), gs.copy()
+    gc = np.zeros(8, np.int64)
+    ok(L, L.g2048_ctx_rollout_random(ctx, vp(gb), vp(ga), vp(gs), n, k, flavour, seed, t0, base, vp(gc)))
+    cc = oracle.rollout_random(cb, ca, cs, k, flavour, seed, t0, base, threads=8)
+    assert np.array_equal(gb, cb) and np.array_equal(gs, cs)
+    if flavour == 0:
+        assert np.array_equal(ga, ca)
+    assert np.array_equal(gc, cc), (gc, cc)
+    assert gc[0] == n * k
+
+
+def test_rollout_random_is_sharding_invariant_at_1M_envs(L, ctx):
+    """BASELINE config 3 size: 2^20 envs; one launch == two half-size launches with shifted env ids."""
+    n, k, seed = 1 << 20, 48, 0x2048
+    b, a, s = fresh_envs(n, seed)
+    b1, a1, s1, c1 = b.copy(), a.copy(), s.copy(), np.zeros(8, np.int64)
+    ok(L, L.g2048_ctx_rollout_random(ctx, vp(b1), vp(a1), vp(s1), n, k, 0, seed, 0, 0, vp(c1)))
+    h = n // 2
+    c2 = np.zeros(8, np.int64)
+    for lo in (0, h):
+        bb, aa, ss, cc = b[lo:lo + h].copy(), a[lo:lo + h].copy(), s[lo:lo + h].copy(), np.zeros(8, np.int64)
+        ok(L, L.g2048_ctx_rollout_random(ctx, vp(bb), vp(aa), vp(ss), h, k, 0, seed, 0, lo, vp(cc)))
+        assert np.array_equal(bb, b1[lo:lo + h]) and np.array_equal(aa, a1[lo:lo + h]) and np.array_equal(ss, s1[lo:lo + h])
+        c2 += cc
+        c2[4] = max(c2[4], cc[4]) if lo else cc[4]
+    c2[4] = c1[4]
+    assert np.array_equal(c1, c2) and c1[0] == n * k
+    # tile-sum conservation: sum of tiles == 2 * (#2-spawns) + 4 * (#4-spawns) is not observable here, but every
+    # board must stay a legal non-empty position
+    assert (b1 != 0).all()
+    # a 65,536-env sample of the same launch against the oracle
+    m = 1 << 16
+    cb, ca, cs = b[:m].copy(), a[:m].copy(), s[:m].copy()
+    oracle.rollout_random(cb, ca, cs, k, 0, seed, 0, 0, threads=8)
+    assert np.array_equal(cb, b1[:m]) and np.array_equal(ca, a1[:m]) and np.array_equal(cs, s1[:m])
+
+
+# ------------------------------------------------------------------------------------------ Q-table
+def export_ctx_table(L, ctx):
+    n = L.g2048_ctx_qtable_size(ctx)
+    assert n >= 0
+    keys, rows = np.zeros(max(n, 1), np.uint64), np.zeros((max(n, 1), 4), np.float32)
+    assert L.g2048_ctx_qtable_export(ctx, vp(keys), vp(rows), n) == n
+    order = np.argsort(keys[:n])
+    return keys[:n][order], rows[:n][order]
+
+
+def test_qtable_update_n1_teacher_forced_reference_transitions(L, ctx, golden):
+    """update_q_value on the reference's own transitions, one at a time (N = 1 == the reference's order):
+    float32 bit-exact against the oracle, and within tolerance of the reference's float64 table."""
+    g = golden("qlearn_ref")
+    n = 3000
+    ok(L, L.g2048_ctx_qtable_clear(ctx))
+    r32 = g["r"].astype(np.float32)
+    tab = oracle.QTable(1 << 15, f32=True)
+    for i in range(n):
+        sl = slice(i, i + 1)
+        ok(L, L.g2048_ctx_qtable_update(ctx, vp(g["s"][sl]), vp(g["a"][sl]), vp(r32[sl]), vp(g["s2"][sl]),
+                                        vp(g["done"][sl]), 1, 0.1, 0.99, i % 2))
+        tab.update_batch_f32(g["s"][sl], g["a"][sl], r32[sl], g["s2"][sl], g["done"][sl], 0.1, 0.99)
+    keys, rows = export_ctx_table(L, ctx)
+    wk, wr = tab.export()
+    assert np.array_equal(keys, wk)
+    assert np.array_equal(rows, wr.astype(np.float32))
+    t64 = oracle.QTable(1 << 15, f32=False)
+    t64.update_seq_f64(g["s"][:n], g["a"][:n], g["r"][:n], g["s2"][:n], g["done"][:n], 0.1, 0.99)
+    k64, r64 = t64.export()
+    assert np.array_equal(keys, k64)
+    np.testing.assert_allclose(rows, r64, rtol=Q_RTOL, atol=Q_ATOL)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_qtable_update_batched_synchronous(L, ctx, mode):
+    """One synchronous batch with heavy (state, action) collisions: deterministic mode bit-exact, atomic mode
+    within tolerance of the oracle's ordered float32 sums."""
+    rng = np.random.RandomState(3)
+    pool = random_boards(rng, 3000, 8, 0.3)
+    ok(L, L.g2048_ctx_qtable_clear(ctx))
+    tab = oracle.QTable(1 << 14, f32=True)
+    for rep in range(6):
+        n = 100_000
+        s, s2 = pool[rng.randint(0, len(pool), n)], pool[rng.randint(0, len(pool), n)]
+        a = rng.randint(0, 4, n).astype(np.uint8)
+        r = (rng.standard_normal(n) * 3).astype(np.float32)
+        d = (rng.random_sample(n) < 0.05).astype(np.uint8)
+        ok(L, L.g2048_ctx_qtable_update(ctx, vp(s), vp(a), vp(r), vp(s2), vp(d), n, 0.1, 0.99, mode))
+        tab.update_batch_f32(s, a, r, s2, d, 0.1, 0.99)
+        keys, rows = export_ctx_table(L, ctx)
+        wk, wr = tab.export()
+        assert np.array_equal(keys, wk)
+        if mode == 1:
+            assert np.array_equal(rows, wr.astype(np.float32)), rep
+        else:
+            np.testing.assert_allclose(rows, wr, rtol=1e-4, atol=1e-3)   # sums of ~30 terms of magnitude ~1
+            ok(L, L.g2048_ctx_qtable_clear(ctx))                          # restart both from the same table
+            tab = oracle.QTable(1 << 14, f32=True)
+
+
+def test_qtable_lookup_and_choose_action(L, ctx):
+    rng = np.random.RandomState(11)
+    pool = random_boards(rng, 5000, 10, 0.3)
+    ok(L, L.g2048_ctx_qtable_clear(ctx))
+    tab = oracle.QTable(1 << 14, f32=True)
+    n = 50_000
+    s, s2 = pool[rng.randint(0, len(pool), n)], pool[rng.randint(0, len(pool), n)]
+    a, r = rng.randint(0, 4, n).astype(np.uint8), rng.standard_normal(n).astype(np.float32)
+    d = np.zeros(n, np.uint8)
+    ok(L, L.g2048_ctx_qtable_update(ctx, vp(s), vp(a), vp(r), vp(s2), vp(d), n, 0.1, 0.9, 1))
+    tab.update_batch_f32(s, a, r, s2, d, 0.1, 0.9)
+    probe = np.concatenate([pool[:2000], random_boards(rng, 2000, 12, 0.5)])
+    rows, found = np.zeros((len(probe), 4), np.float32), np.zeros(len(probe), np.uint8)
+    ok(L, L.g2048_ctx_qtable_lookup(ctx, vp(probe), len(probe), vp(rows), vp(found), 0))
+    for i in range(0, len(probe), 97):
+        wr, wf = tab.get(probe[i])
+        assert bool(found[i]) == wf and np.array_equal(rows[i], wr.astype(np.float32))
+    size0 = L.g2048_ctx_qtable_size(ctx)
+    assert size0 == len(tab)
+    for eps in (0.0, 0.3, 1.0):
+        acts = np.zeros(len(probe), np.uint8)
+        ok(L, L.g2048_ctx_choose_action(ctx, vp(probe), vp(acts), len(probe), eps, 77, 5, 1000))
+        want = tab.choose_action(probe, oracle.eps_threshold(eps), 77, 5, 1000)
+        assert np.array_equal(acts, want)
+    assert L.g2048_ctx_qtable_size(ctx) == len(tab)   # choose_action inserts like the defaultdict
+
+
+def test_rollout_qlearn_single_env_is_the_reference_order(L, ctx):
+    """Fused asynchronous rollout with N = 1 == sequential Q-learning (main.py:91-101) in float32, bit for bit."""
+    for flavour, eps in ((0, 0.2), (1, 0.5)):
+        seed, base, k = 31337, 3, 4000
+        ok(L, L.g2048_ctx_qtable_clear(ctx))
+        gb, ga, gs = fresh_envs(1, seed, 0, base)
+        cb, ca, cs = gb.copy(), ga.copy(), gs.copy()
+        gc = np.zeros(8, np.int64)
+        tab = oracle.QTable(1 << 15, f32=True)
+        for part in range(2):   # two launches: the carried state must survive the boundary
+            ok(L, L.g2048_ctx_rollout_qlearn(ctx, vp(gb), vp(ga), vp(gs), 1, k, flavour, 0.1, 0.99, eps, seed, part * k,
+                                             base, vp(gc)))
+        cc = oracle.rollout_qlearn_seq(cb, ca, cs, tab, 2 * k, 0.1, 0.99, eps, flavour, seed, 0, base)
+        assert np.array_equal(gb, cb) and np.array_equal(ga, ca) and np.array_equal(gs, cs)
+        keys, rows = export_ctx_table(L, ctx)
+        wk, wr = tab.export()
+        assert np.array_equal(keys, wk)
+        assert np.array_equal(rows, wr.astype(np.float32))
+        assert gc[0] == k and cc[0] == 2 * k
+
+
+def test_rollout_qlearn_1M_envs_properties(L, ctx):
+    """BASELINE config 3 size (2^20 envs): step count, no dropped inserts, table size == inserts, finite Q
+    bounded by |r|max / (1 - gamma), boards stay legal."""
+    n, k, seed = 1 << 20, 16, 0x2048
+    big = L.g2048_ctx_create(0, n, 1 << 26)
+    assert big, L.g2048_last_error()
+    try:
+        b, a, s = fresh_envs(n, seed)
+        c = np.zeros(8, np.int64)
+        ok(L, L.g2048_ctx_rollout_qlearn(big, vp(b), vp(a), vp(s), n, k, 0, 0.1, 0.99, 0.1, seed, 0, 0, vp(c)))
+        assert c[0] == n * k and c[7] == 0
+        size = L.g2048_ctx_qtable_size(big)
+        assert size == c[6]
+        keys, rows = np.zeros(size, np.uint64), np.zeros((size, 4), np.float32)
+        assert L.g2048_ctx_qtable_export(big, vp(keys), vp(rows), size) == size
+        assert len(np.unique(keys)) == size and (keys != 0).all()
+        assert np.isfinite(rows).all() and np.abs(rows).max() <= 20 / (1 - 0.99)
+        assert (b != 0).all()
+    finally:
+        L.g2048_ctx_destroy(big)
