@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s and tabular Q-updates/s of the fused 2048 Q-learning hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], "C3"): 2^20 envs per GPU, penalty-flavour env, epsilon-greedy tabular
+Q-learning (alpha 0.1, gamma 0.99, epsilon 0.1, Philox seed 0x2048) on an open-addressing hash Q-table in
+HBM.  One bench "step" = one fused launch of k_rollout_qlearn advancing every env by ENV_STEPS_PER_LAUNCH
+steps (each env step = choose_action + env.step + update_q_value, i.e. one Q-update).  Multi-GPU = weak
+scaling: every rank runs its own env shard (global env ids) against its own table replica, no data-path
+collective (DESIGN.md "Multi-GPU").
+
+Prints ONE JSON line (rank 0).  `value`: device-resident throughput (CUDA events, max over ranks);
+`e2e`: the same metric through the host-buffer C-ABI call g2048_ctx_rollout_qlearn with pinned HOST buffers,
+host<->device copies inside the timed region; `roofline`: the fused kernel against the measured HBM peak
+(32 algorithmic bytes per env step); `cpu_baseline`: the C oracle port on the host cores (bounded sample).
+`--impl reference` times that CPU port as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ENVS_PER_GPU = 1 << 20
+ENV_STEPS_PER_LAUNCH = 16
+LR, GAMMA, EPS, SEED = 0.1, 0.99, 0.1, 0x2048
+ALGO_BYTES_PER_STEP = 32        # key(s') 8 + row(s') 16 + Q(s,a) 4 R + 4 W, slot of s carried
+ALGO_BYTES_PER_UPDATE = 40      # stand-alone update API: + key(s) 8
+ALGO_BYTES_SINGLE_STEP = 38     # single-step env API, penalty flavour
+METRIC = "env-steps/sec & tabular Q-updates/sec"
+UNIT = "env-steps/s (1 Q-update per env step)"
+
+
+def workload_name(n_envs, k):
+    return (f"C3: {n_envs} envs/GPU epsilon-greedy tabular Q-learning, penalty env, fused {k}-step rollouts, "
+            f"HBM hash Q-table")
+
+
+def vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the fused kernel from the committed ncu capture, if any."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.reasons.update(k for k, bit in names.items() if r & bit)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def fresh_host_envs(L, ctx, n, base, pinned):
+    """Pinned host buffers with freshly reset boards (reset itself runs on the GPU through the C ABI)."""
+    def alloc(dtype, count):
+        nbytes = np.dtype(dtype).itemsize * count
+        if pinned:
+            p = L.g2048_host_alloc(nbytes)
+            assert p, L.g2048_last_error()
+            return np.frombuffer((C.c_char * nbytes).from_address(p), dtype=dtype, count=count), p
+        return np.zeros(count, dtype), None
+    b, pb = alloc(np.uint64, n)
+    a, pa = alloc(np.uint64, n)
+    s, ps = alloc(np.int32, n)
+    a[:] = 0x000000000000FF01
+    s[:] = 0
+    rc = L.g2048_ctx_env_reset(ctx, vp(b), vp(s), None, None, n, SEED, 0, base)
+    assert rc == 0, L.g2048_last_error()
+    return (b, a, s), (pb, pa, ps)
+
+
+def cpu_baseline(n_threads, seconds=4.0, repeats=3):
+    """The C oracle's sequential-semantics Q-learning rollout, one env shard + one table per host thread."""
+    import oracle
+    oracle.load()
+    per_thread_envs = 2048
+
+    def run(k):
+        n = per_thread_envs * n_threads
+        b = np.zeros(n, np.uint64)
+        oracle.env_reset(b, None, None, None, seed=SEED)
+        a, s = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+        t0 = time.perf_counter()
+        c = oracle.rollout_qlearn_mt(b, a, s, k, LR, GAMMA, EPS, 1 << 23, n_threads, 0, SEED, 0, 0)
+        return int(c[0]), time.perf_counter() - t0
+
+    steps, dt = run(64)
+    k = int(max(64, min(2048, 64 * seconds / max(dt, 1e-3))))
+    best = 0.0
+    for _ in range(repeats):
+        steps, dt = run(k)
+        best = max(best, steps / dt)
+    return {"value": best, "unit": UNIT, "cores": n_threads, "kind": "port",
+            "sample": f"C oracle port (oracle/g2048_oracle.c), {per_thread_envs} envs x {k} steps per thread, "
+                      f"{n_threads} threads each with its own table, best of {repeats}",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU restatement of the reference path (the reference itself is pure Python and does
+    not exist on the GPU box), all host threads, one bounded sample of the C3 workload per step."""
+    if rank != 0:
+        return
+    import oracle
+    oracle.load()
+    threads = os.cpu_count() or 1
+    per_thread_envs = 8192
+    n = per_thread_envs * threads
+    b = np.zeros(n, np.uint64)
+    oracle.env_reset(b, None, None, None, seed=SEED)
+    a, s = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+    k = ENV_STEPS_PER_LAUNCH
+    for w in range(args.warmup):
+        oracle.rollout_qlearn_mt(b, a, s, k, LR, GAMMA, EPS, 1 << 20, threads, 0, SEED, w * k, 0)
+    t0 = time.perf_counter()
+    total = 0
+    for i in range(args.steps):
+        c = oracle.rollout_qlearn_mt(b, a, s, k, LR, GAMMA, EPS, 1 << 20, threads, 0, SEED, (args.warmup + i) * k, 0)
+        total += int(c[0])
+    dt = time.perf_counter() - t0
+    v = total / dt
+    sample = (f"C oracle port, {n} envs ({per_thread_envs}/thread) x {k} steps per bench step, {threads} threads, "
+              f"fresh per-thread tables each step")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 boards / f32 Q rows", "data": "synthetic",
+        "config": {"workload": workload_name(N_ENVS_PER_GPU, k), "cpu_sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU)
+    ap.add_argument("--no-extras", action="store_true", help="skip the explanatory side measurements")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import g2048
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the g2048 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    g2048.init(local_rank)
+    L = g2048.lib()
+    dev = torch.device("cuda", local_rank)
+    n, k = args.envs, ENV_STEPS_PER_LAUNCH
+    base = rank * n
+    launches = args.steps + args.warmup
+
+    # table: as many slots as keep the load factor under ~0.45 for one arm (<= 2^31 slots = 64 GiB)
+    expected_inserts = 0.8 * n * k * launches
+    free_bytes, _ = torch.cuda.mem_get_info()
+    cap = 1 << 22
+    while cap < (1 << 31) and cap * 0.45 < expected_inserts and cap * 2 * 32 < free_bytes * 0.6:
+        cap <<= 1
+    ctx = L.g2048_ctx_create(local_rank, n, cap)
+    assert ctx, L.g2048_last_error()
+    table = L.g2048_ctx_table(ctx)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_envs():
+        b = torch.zeros(n, dtype=torch.int64, device=dev)
+        a = torch.full((n,), 0x000000000000FF01, dtype=torch.int64, device=dev)
+        s = torch.zeros(n, dtype=torch.int32, device=dev)
+        assert L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, SEED, 0, base, stream) == 0
+        return b, a, s
+
+    counters = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    # ---- pre-warm: ramp clocks with random-policy rollouts (not counted) --------------------------------
+    b, a, s = device_envs()
+    t_end = time.perf_counter() + 0.3
+    while time.perf_counter() < t_end:
+        L.g2048_rollout_random(b.data_ptr(), a.data_ptr(), s.data_ptr(), n, 64, 0, SEED, 0, base, counters.data_ptr(), stream)
+        torch.cuda.synchronize()
+
+    # ---- arm 1: device-resident (value) -------------------------------------------------------------------
+    b, a, s = device_envs()
+    counters.zero_()
+
+    def launch(i):
+        rc = L.g2048_rollout_qlearn(b.data_ptr(), a.data_ptr(), s.data_ptr(), table, cap, n, k, 0, LR, GAMMA, EPS, SEED,
+                                    i * k, base, counters.data_ptr(), stream)
+        assert rc == 0, L.g2048_last_error()
+
+    for i in range(args.warmup):
+        launch(i)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record()
+        for i in range(args.steps):
+            launch(args.warmup + i)
+            ev[i + 1].record()
+        barrier()
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    elapsed_s = max_over_ranks(ev[0].elapsed_time(ev[-1]) / 1e3)
+    c = counters.cpu().numpy()
+    assert int(c[0]) == n * k * launches, (int(c[0]), n * k * launches)
+    value = world * n * k * args.steps / elapsed_s
+    kernel_ms = statistics.mean(per_launch_ms)
+    peak, peak_src = measured_peak()
+    achieved = n * k * ALGO_BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    table_stats = {"capacity_slots": cap, "table_GiB": cap * 32 / 2**30, "states": int(c[6]),
+                   "load_factor_end": int(c[6]) / cap, "dropped": int(c[7]),
+                   "new_state_fraction": int(c[6]) / max(int(c[0]), 1)}
+
+    # ---- arm 2: end to end through the host-buffer C-ABI call (pinned host memory) --------------------------
+    assert L.g2048_ctx_qtable_clear(ctx) == 0
+    (hb, ha, hs), pins = fresh_host_envs(L, ctx, n, base, pinned=True)
+    hc = np.zeros(8, np.int64)
+
+    def e2e_step(i):
+        rc = L.g2048_ctx_rollout_qlearn(ctx, vp(hb), vp(ha), vp(hs), n, k, 0, LR, GAMMA, EPS, SEED, i * k, base, vp(hc))
+        assert rc == 0, L.g2048_last_error()
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(args.warmup + i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert int(hc[0]) == n * k
+    e2e = {"value": world * n * k * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 20,
+           "d2h_bytes_per_step": n * 20 + 64, "ms_per_step": e2e_s / args.steps * 1e3,
+           "api": "g2048_ctx_rollout_qlearn (host boards/aux/score in, boards/aux/score/counters out, pinned)"}
+    for p in pins:
+        L.g2048_host_free(p)
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        extras = side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak)
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 boards / f64 reward / f32 Q rows", "data": "synthetic",
+            "config": {"workload": workload_name(n, k), "envs_per_gpu": n, "env_steps_per_launch": k, "alpha": LR,
+                       "gamma": GAMMA, "epsilon": EPS, "seed": SEED, "flavour": "penalty", "mode": "fused async atomic",
+                       "parallelism": f"env shards x{world}, table replica per GPU, no collective",
+                       "l2": f"Q-table {cap * 32 / 2**30:.0f} GiB >> 126 MB L2 (random 32 B sectors); boards live in registers"},
+            "q_updates_per_sec": value, "table": table_stats,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_rollout_qlearn<penalty>", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "peak_source": peak_src,
+                         "note": "fused kernel is integer-ALU / latency bound, not HBM bound (DESIGN.md); the "
+                                 "HBM-bound kernels are reported under extras"},
+            "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary(),
+            "cpu_baseline": cpu_baseline(os.cpu_count() or 1) if world == 1 else None,
+            "extras": extras,
+        }
+        print(json.dumps(out))
+    L.g2048_ctx_destroy(ctx)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
+    """Explanatory numbers beside the headline: random-policy rollout, single-step env API, stand-alone update."""
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    b = torch.zeros(n, dtype=torch.int64, device=dev)
+    a = torch.full((n,), 0x000000000000FF01, dtype=torch.int64, device=dev)
+    s = torch.zeros(n, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+    L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, SEED, 0, base, stream)
+    # (a) fused random-policy rollout, 64 steps per launch
+    for flavour, name in ((0, "penalty"), (1, "nopenalty")):
+        dt = timed(lambda: L.g2048_rollout_random(b.data_ptr(), a.data_ptr(), s.data_ptr(), n, 64, flavour, SEED, 0, base,
+                                                  cnt.data_ptr(), stream), 10)
+        out[f"random_policy_rollout_{name}"] = {"env_steps_per_sec": n * 64 / dt, "ms_per_launch": dt * 1e3}
+    # (b) single-step env API, state in HBM every call (HBM bound: 38 B/step)
+    act = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev)
+    r64 = torch.zeros(n, dtype=torch.float64, device=dev)
+    fl = torch.zeros(n, dtype=torch.uint8, device=dev)
+    ml = torch.zeros(n, dtype=torch.uint8, device=dev)
+    dt = timed(lambda: L.g2048_env_step(b.data_ptr(), a.data_ptr(), s.data_ptr(), act.data_ptr(), None, r64.data_ptr(),
+                                        None, fl.data_ptr(), ml.data_ptr(), None, n, 0, SEED, 1, base, stream), 50)
+    gbs = n * ALGO_BYTES_SINGLE_STEP / dt / 1e9
+    out["single_step_env_api"] = {"env_steps_per_sec": n / dt, "achieved_GBps_at_38B": gbs, "frac_of_hbm_peak": gbs / peak,
+                                  "note": f"{n} envs = {n * 38 / 1e6:.0f} MB per call, L2-resident"}
+    # (c) stand-alone batched update on random transitions over a pre-filled table (HBM bound: 40 B/update)
+    m = 1 << 22
+    L.g2048_ctx_qtable_clear(ctx)
+    pool = torch.randint(1, 1 << 62, (min(cap // 4, 1 << 27),), dtype=torch.int64, device=dev)
+    idx = torch.randint(0, pool.numel(), (m,), device=dev)
+    idx2 = torch.randint(0, pool.numel(), (m,), device=dev)
+    s1, s2 = pool[idx].contiguous(), pool[idx2].contiguous()
+    aa = torch.randint(0, 4, (m,), dtype=torch.uint8, device=dev)
+    rr = torch.randn(m, dtype=torch.float32, device=dev)
+    dd = torch.zeros(m, dtype=torch.uint8, device=dev)
+    need = int(L.g2048_qlearn_scratch_bytes(m))
+    scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    rows = torch.empty((1 << 22, 4), dtype=torch.float32, device=dev)
+    for lo in range(0, pool.numel(), 1 << 22):  # insert the whole pool
+        chunk = pool[lo:lo + (1 << 22)]
+        L.g2048_qtable_lookup(table, cap, chunk.data_ptr(), chunk.numel(), rows.data_ptr(), None, 1, stream)
+    for mode, name in ((0, "atomic"), (1, "deterministic")):
+        dt = timed(lambda: L.g2048_qtable_update(table, cap, s1.data_ptr(), aa.data_ptr(), rr.data_ptr(), s2.data_ptr(),
+                                                 dd.data_ptr(), m, LR, GAMMA, mode, scratch.data_ptr(), need, stream), 10)
+        gbs = m * ALGO_BYTES_PER_UPDATE / dt / 1e9
+        out[f"standalone_q_update_{name}"] = {"updates_per_sec": m / dt, "achieved_GBps_at_40B": gbs,
+                                              "frac_of_hbm_peak": gbs / peak, "batch": m, "table_states": pool.numel()}
+    L.g2048_ctx_qtable_clear(ctx)
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -782,7 +782,10 @@ ORC_API void orc_rollout_qlearn_seq(uint64_t *boards, uint64_t *aux, int32_t *sc
                 q = q + f32_delta(lr, gamma, (float)o.reward, best, (o.flags & FLAG_DONE) != 0, q);
                 rows[4 * h + a] = q;
             }
-            if (o.flags & FLAG_DONE) philox_reset(&e, seed, id, step, STREAM_AUTORESET);
+            if (o.flags & FLAG_DONE) {
+                philox_reset(&e, seed, id, step, STREAM_AUTORESET);
+                qtab_slot_counted(t, e.board, counters); /* state = env.reset() is read at once (main.py:81-82, :92) */
+            }
             boards[i] = e.board;
             if (aux) aux[i] = e.aux;
             if (score) score[i] = e.score;

@@ -66,7 +66,7 @@ def test_row_lut_all_65536_rows(L, ctx):
         out, moved, sc = np.zeros_like(boards), np.zeros(65536, np.uint8), np.zeros(65536, np.int32)
         ok(L, L.g2048_ctx_move_trial(ctx, vp(boards), vp(np.zeros(65536, np.uint8)), vp(out), vp(moved), vp(sc), 65536))
         want = res.astype(np.uint64) << np.uint64(shift)
-        score = np.array([(1 << (m >> 4) if m >> 4 else 0) + (1 << (m & 15) if m & 15 else 0) for m in mg], np.int32)
+        score = np.array([(1 << (m >> 4) if m >> 4 else 0) + (1 << (m & 15) if m & 15 else 0) for m in mg.tolist()], np.int32)
         assert np.array_equal(out[1:], want[1:]) and np.array_equal(sc[1:], score[1:])
         assert np.array_equal(moved[1:] != 0, (want != boards)[1:])
 
