@@ -74,7 +74,7 @@ _SIG = {
     "g2048_qtable_lookup": (i32, [vp, u64, vp, i64, vp, vp, i32, vp]),
     "g2048_choose_action": (i32, [vp, u64, vp, vp, i64, f64, u64, u64, u64, vp]),
     "g2048_qtable_update": (i32, [vp, u64, vp, vp, vp, vp, vp, i64, f32, f32, i32, vp, sz, vp]),
-    "g2048_qtable_apply_deltas": (i32, [vp, u64, vp, vp, vp, i64, i32, vp, sz, vp]),
+    "g2048_qtable_apply_targets": (i32, [vp, u64, vp, vp, vp, i64, f32, i32, vp, sz, vp]),
     "g2048_qtable_size": (i32, [vp, u64, vp, vp]),
     "g2048_qtable_export": (i32, [vp, u64, vp, vp, i64, vp, vp]),
     "g2048_ctx_create": (vp, [i32, i64, u64]),

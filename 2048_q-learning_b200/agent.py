@@ -65,13 +65,14 @@ class BatchedQLearningAgent:
                                                _ptr(next_state), _ptr(d), n, self.lr, self.gamma, MODES[mode], _ptr(sc),
                                                sc.numel(), _stream()), "g2048_qtable_update")
 
-    def apply_deltas(self, keys, actions, deltas, mode: str = "deterministic") -> None:
+    def apply_targets(self, keys, actions, targets, mode: str = "deterministic", lr: float | None = None) -> None:
+        """Q[key][a] <- Q + lr (target - Q) for (state, action, target) records, e.g. gathered from all ranks."""
         n = keys.numel()
         with torch.cuda.device(self.device):
             sc = self._scratch_for(n)
-            check(self.lib.g2048_qtable_apply_deltas(_ptr(self.table), self.capacity, _ptr(keys), _ptr(actions),
-                                                     _ptr(deltas), n, MODES[mode], _ptr(sc), sc.numel(), _stream()),
-                  "g2048_qtable_apply_deltas")
+            check(self.lib.g2048_qtable_apply_targets(_ptr(self.table), self.capacity, _ptr(keys), _ptr(actions),
+                                                      _ptr(targets), n, self.lr if lr is None else lr, MODES[mode],
+                                                      _ptr(sc), sc.numel(), _stream()), "g2048_qtable_apply_targets")
 
     def decay_exploration(self, current_epoch: int) -> float:
         return epsilon_schedule_step(self, current_epoch)
@@ -99,7 +100,7 @@ class BatchedQLearningAgent:
         return env.counters
 
     def step_sync(self, env: BatchedGame2048Env, mode: str = "deterministic", apply: bool = True, records: bool = False):
-        """One synchronous batched step; optionally returns the (key, action, delta) records."""
+        """One synchronous batched step; optionally returns the (key, action, target) records."""
         n = env.n
         with torch.cuda.device(self.device):
             rk = torch.empty(n, dtype=torch.int64, device=self.device) if records else None
@@ -158,6 +159,6 @@ class BatchedQLearningAgent:
         keys = blob["keys"].to(self.device)
         rows = blob["rows"].to(self.device)
         self.epsilon = blob["epsilon"]
-        for a in range(4):  # Q[key][a] += row[a] on an empty table
-            self.apply_deltas(keys, torch.full((keys.numel(),), a, dtype=torch.uint8, device=self.device),
-                              rows[:, a].contiguous(), mode="atomic")
+        for a in range(4):  # lr = 1 on an empty table: Q[key][a] <- row[a]
+            self.apply_targets(keys, torch.full((keys.numel(),), a, dtype=torch.uint8, device=self.device),
+                               rows[:, a].contiguous(), mode="atomic", lr=1.0)

@@ -44,7 +44,8 @@ int fail(int code, const char* what) {
 
 constexpr int kMaxDevices = 64;
 constexpr size_t kLutRowBytes = 65536 * sizeof(uint16_t);
-constexpr size_t kLutBytes = kLutRowBytes + 65536;  // row table followed by the merged-level table
+constexpr size_t kLutMergedBytes = 65536;
+constexpr size_t kLutBytes = kLutRowBytes + kLutMergedBytes + 256 * sizeof(uint32_t);  // row | merged | mscore
 constexpr int kRolloutThreads = 1024;
 
 struct DeviceState {
@@ -58,9 +59,14 @@ std::mutex g_mu;
 
 // ---- host-side table construction -------------------------------------------------------------------
 // Row table: move_left on one row (Game2048_env.py:25-41) for all 65,536 rows.
-void build_row_tables(std::vector<uint16_t>& row, std::vector<uint8_t>& merged) {
+void build_row_tables(std::vector<uint16_t>& row, std::vector<uint8_t>& merged, std::vector<uint32_t>& mscore) {
     row.resize(65536);
     merged.resize(65536);
+    mscore.resize(256);
+    for (unsigned m = 0; m < 256; ++m) {  // merged byte -> score (sum of 2^level over its two nibbles) | hi level << 24
+        unsigned hi = m >> 4, lo = m & 15;
+        mscore[m] = ((hi ? 1u << hi : 0u) + (lo ? 1u << lo : 0u)) | (hi << 24);
+    }
     for (unsigned r = 0; r < 65536; ++r) {
         int t[4] = {(int)(r & 15), (int)((r >> 4) & 15), (int)((r >> 8) & 15), (int)((r >> 12) & 15)};
         int packed[4], n = 0;
@@ -72,9 +78,10 @@ void build_row_tables(std::vector<uint16_t>& row, std::vector<uint8_t>& merged) 
             if (pair) { out[m++] = packed[i] + 1; mg[k++] = packed[i] + 1; ++i; }
             else out[m++] = packed[i];
         }
-        row[r] = (uint16_t)(out[0] | (out[1] << 4) | (out[2] << 8) | (out[3] << 12));
+        unsigned p = lut_index2(r) & 0xFFFFu;  // bank-swizzled position of row r
+        row[p] = (uint16_t)(out[0] | (out[1] << 4) | (out[2] << 8) | (out[3] << 12));
         int hi = mg[0] > mg[1] ? mg[0] : mg[1], lo = mg[0] > mg[1] ? mg[1] : mg[0];
-        merged[r] = (uint8_t)((hi << 4) | lo);
+        merged[p] = (uint8_t)((hi << 4) | lo);
     }
 }
 // update_and_normalize (Game2048_env.py:197-205), same libm calls as CPython's math.log2
@@ -147,7 +154,7 @@ inline bool pow2(uint64_t c) { return c && !(c & (c - 1)); }
 // ============================================================================================ kernels
 namespace {
 
-__device__ __forceinline__ Lut global_lut(const Tables& T) { return Lut{T.lut_row, T.lut_merged}; }
+__device__ __forceinline__ Lut global_lut(const Tables& T) { return Lut{T.lut_row, T.lut_merged, T.lut_mscore}; }
 
 // Stage the 192 KB row LUT into dynamic shared memory with one bulk-async copy (TMA, UBLKCP) completing
 // on an mbarrier; every thread then waits on phase 0.
@@ -174,7 +181,8 @@ __device__ __forceinline__ Lut stage_lut(const Tables& T, unsigned char* smem) {
             : "r"(bar)
             : "memory");
     }
-    return Lut{reinterpret_cast<const uint16_t*>(smem), smem + kLutRowBytes};
+    return Lut{reinterpret_cast<const uint16_t*>(smem), smem + kLutRowBytes,
+               reinterpret_cast<const uint32_t*>(smem + kLutRowBytes + kLutMergedBytes)};
 }
 
 template <bool REPLAY>
@@ -202,9 +210,7 @@ k_env_step(Tables T, u64* boards, u64* aux, int* score, const uint8_t* actions, 
     Lut L = global_lut(T);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         Env e;
-        e.board = boards[i];
-        env_from_aux(e, (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT);
-        e.score = score ? score[i] : 0;
+        env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
         int a = actions[i] & 3;
         StepOut o;
         if (REPLAY) {
@@ -237,9 +243,7 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
     Counters c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         Env e;
-        e.board = boards[i];
-        env_from_aux(e, (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT);
-        e.score = score ? score[i] : 0;
+        env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
         u64 id = id_base + (u64)i;
         for (long long k = 0; k < k_steps; ++k) {
             u64 t = step_base + (u64)k;
@@ -257,7 +261,8 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
 }
 
 // main.py:91-101 fused.  Per step: Philox -> epsilon-greedy from the carried row of s -> env step ->
-// find-or-insert s' (one 32-byte sector) -> RED.ADD on Q[s][a] -> carry (slot, row) of s' as the next s.
+// find-or-insert s' (one 32-byte sector) -> atomic q <- q + lr (target - q) on Q[s][a] -> carry (slot, row)
+// of s' as the next s.
 template <int FLAVOUR>
 __global__ void __launch_bounds__(kRolloutThreads, 1)
 k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mask, long long n, long long k_steps,
@@ -268,12 +273,10 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
     Counters c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         Env e;
-        e.board = boards[i];
-        env_from_aux(e, (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT);
-        e.score = score ? score[i] : 0;
+        env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
         u64 id = id_base + (u64)i;
         float4 row;
-        int ins = 0;
+        u32 ins = 0;
         u32 slot = table_find<true>(tab, mask, e.board, row, ins);
         c.dropped += (slot == kNoSlot);
         for (long long k = 0; k < k_steps; ++k) {
@@ -290,10 +293,9 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
                 c.dropped += (slot2 == kNoSlot);
             }
             if (slot != kNoSlot) {
-                float q_sa = q_at(row, a);
-                float delta = td_delta(lr, gamma, (float)o.reward, max4(row2), o.done, q_sa);
-                atomicAdd(&tab[slot].q[a], delta);
-                if (slot2 == slot) q_set(row2, a, __fadd_rn(q_sa, delta));
+                float target = td_target(gamma, (float)o.reward, max4(row2), o.done);
+                float nq = q_update_atomic(&tab[slot].q[a], q_at(row, a), lr, target);
+                if (slot2 == slot) q_set(row2, a, nq);
             }
             row = row2;
             slot = slot2;
@@ -312,22 +314,20 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
 }
 
 // Synchronous step, phase A: choose + env step + bootstrap on the snapshot; emits one record per env:
-// sort key = slot * 4 + action (all ones = no slot), delta, and optionally (state key, action).
+// sort key = slot * 4 + action (all ones = no slot), TD target, and optionally (state key, action).
 template <int FLAVOUR>
 __global__ void __launch_bounds__(256)
 k_qlearn_phase_a(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mask, long long n, float lr, float gamma,
-                 u64 eps_thresh, u64 seed, u64 t, u64 id_base, long long* counters, u64* sortkey, float* delta_out,
-                 u64* rec_key, uint8_t* rec_action, float* rec_delta) {
+                 u64 eps_thresh, u64 seed, u64 t, u64 id_base, long long* counters, u64* sortkey, float* target_out,
+                 u64* rec_key, uint8_t* rec_action, float* rec_target) {
     Lut L = global_lut(T);
     Counters c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         Env e;
-        e.board = boards[i];
-        env_from_aux(e, (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT);
-        e.score = score ? score[i] : 0;
+        env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
         u64 id = id_base + (u64)i;
         float4 row, row2;
-        int ins = 0;
+        u32 ins = 0;
         u64 s_key = e.board;
         u32 slot = table_find<true>(tab, mask, s_key, row, ins);
         c.dropped += (slot == kNoSlot);
@@ -338,12 +338,12 @@ k_qlearn_phase_a(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
         c.add(o);
         u32 slot2 = table_find<true>(tab, mask, e.board, row2, ins);
         c.dropped += (slot2 == kNoSlot);
-        float delta = td_delta(lr, gamma, (float)o.reward, max4(row2), o.done, q_at(row, a));
+        float target = td_target(gamma, (float)o.reward, max4(row2), o.done);
         if (sortkey) sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)a);
-        if (delta_out) delta_out[i] = delta;
+        if (target_out) target_out[i] = target;
         if (rec_key) rec_key[i] = s_key;
         if (rec_action) rec_action[i] = (uint8_t)a;
-        if (rec_delta) rec_delta[i] = delta;
+        if (rec_target) rec_target[i] = target;
         if (o.done) philox_autoreset(e, seed, id, t);
         boards[i] = e.board;
         if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
@@ -353,45 +353,49 @@ k_qlearn_phase_a(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
     flush_counters(c, counters);
 }
 
-// update_q_value phase A on given transitions (teacher-forced): reads only, emits sort key + delta
+// update_q_value phase A on given transitions (teacher-forced): reads only, emits sort key + TD target
 __global__ void __launch_bounds__(256)
 k_q_update_phase_a(Slot* tab, u64 mask, const u64* s, const uint8_t* a, const float* r, const u64* s2,
-                   const uint8_t* done, long long n, float lr, float gamma, u64* sortkey, float* delta_out) {
+                   const uint8_t* done, long long n, float gamma, u64* sortkey, float* target_out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float4 row, row2;
-        int ins = 0;
+        u32 ins = 0;
         table_find<true>(tab, mask, s2[i], row2, ins);
         u32 slot = table_find<true>(tab, mask, s[i], row, ins);
         int act = a[i] & 3;
         sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)act);
-        delta_out[i] = td_delta(lr, gamma, r[i], max4(row2), done[i] != 0, q_at(row, act));
+        target_out[i] = td_target(gamma, r[i], max4(row2), done[i] != 0);
     }
 }
-// (key, action, delta) records -> sort key (find-or-insert the key)
+// (key, action, target) records -> sort key (find-or-insert the key)
 __global__ void __launch_bounds__(256)
 k_keys_to_records(Slot* tab, u64 mask, const u64* keys, const uint8_t* a, long long n, u64* sortkey) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float4 row;
-        int ins = 0;
+        u32 ins = 0;
         u32 slot = table_find<true>(tab, mask, keys[i], row, ins);
         sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)(a[i] & 3));
     }
 }
-__global__ void __launch_bounds__(256) k_apply_atomic(Slot* tab, const u64* sortkey, const float* delta, long long n) {
+__global__ void __launch_bounds__(256)
+k_apply_atomic(Slot* tab, const u64* sortkey, const float* target, float lr, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         u64 k = sortkey[i];
-        if (k != ~0ull) atomicAdd(&tab[k >> 2].q[k & 3], delta[i]);
+        if (k == ~0ull) continue;
+        float* q = &tab[k >> 2].q[k & 3];
+        q_update_atomic(q, __ldcg(q), lr, target[i]);
     }
 }
-// sorted (stable) records: the head of every run sums its run in order and adds it to Q once
-__global__ void __launch_bounds__(256) k_segment_apply(Slot* tab, const u64* sortkey, const float* delta, long long n) {
+// sorted (stable) records: the head of every run applies its run in order, q <- q + lr (target - q)
+__global__ void __launch_bounds__(256)
+k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         u64 k = sortkey[i];
         if (k == ~0ull || (i > 0 && sortkey[i - 1] == k)) continue;
-        float acc = delta[i];
-        for (long long j = i + 1; j < n && sortkey[j] == k; ++j) acc = __fadd_rn(acc, delta[j]);
-        float* q = &tab[k >> 2].q[k & 3];
-        *q = __fadd_rn(*q, acc);
+        float* qp = &tab[k >> 2].q[k & 3];
+        float q = td_apply(*qp, lr, target[i]);
+        for (long long j = i + 1; j < n && sortkey[j] == k; ++j) q = td_apply(q, lr, target[j]);
+        *qp = q;
     }
 }
 
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(256)
 k_q_lookup(Slot* tab, u64 mask, const u64* keys, long long n, float4* rows, uint8_t* found) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float4 row;
-        int ins = 0;
+        u32 ins = 0;
         u32 slot = table_find<INSERT>(tab, mask, keys[i], row, ins);
         rows[i] = row;
         if (found) found[i] = (slot != kNoSlot) && !ins;
@@ -411,7 +415,7 @@ k_choose_action(Slot* tab, u64 mask, const u64* boards, uint8_t* actions, long l
                 u64 id_base) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float4 row;
-        int ins = 0;
+        u32 ins = 0;
         table_find<true>(tab, mask, boards[i], row, ins);
         Draw4 x = philox(seed, id_base + (u64)i, t, G2048_STREAM_STEP);
         actions[i] = (uint8_t)choose_action(row, x, eps_thresh);
@@ -441,12 +445,10 @@ __global__ void __launch_bounds__(256)
 k_move_trial(Tables T, const u64* in, const uint8_t* actions, u64* out, uint8_t* moved, int* move_score, long long n) {
     Lut L = global_lut(T);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        u64 r;
-        u32 mm;
-        bool mv = do_move(in[i], actions[i] & 3, L, r, mm);
-        if (out) out[i] = r;
-        if (moved) moved[i] = mv;
-        if (move_score) move_score[i] = merge_score(mm);
+        Moved m = do_move(in[i], actions[i] & 3, L);
+        if (out) out[i] = m.board;
+        if (moved) moved[i] = m.moved;
+        if (move_score) move_score[i] = m.score;
     }
 }
 __global__ void __launch_bounds__(256) k_legal_mask(const u64* boards, uint8_t* out, long long n) {
@@ -555,8 +557,9 @@ G2048_API int g2048_init(int device) {
     if (d.ready) return 0;
     std::vector<uint16_t> row;
     std::vector<uint8_t> merged;
+    std::vector<uint32_t> mscore;
     std::vector<double> valid, invalid, pen;
-    build_row_tables(row, merged);
+    build_row_tables(row, merged, mscore);
     build_reward_tables(valid, invalid, pen);
     void *lut = nullptr, *rv = nullptr, *ri = nullptr, *pn = nullptr;
     CK(cudaMalloc(&lut, kLutBytes));
@@ -564,13 +567,15 @@ G2048_API int g2048_init(int device) {
     CK(cudaMalloc(&ri, invalid.size() * sizeof(double)));
     CK(cudaMalloc(&pn, pen.size() * sizeof(double)));
     CK(cudaMemcpy(lut, row.data(), kLutRowBytes, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy((char*)lut + kLutRowBytes, merged.data(), 65536, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((char*)lut + kLutRowBytes, merged.data(), kLutMergedBytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((char*)lut + kLutRowBytes + kLutMergedBytes, mscore.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(rv, valid.data(), valid.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ri, invalid.data(), invalid.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pn, pen.data(), pen.size() * sizeof(double), cudaMemcpyHostToDevice));
     d.lut = lut;
-    d.tables = Tables{(const uint16_t*)lut, (const uint8_t*)lut + kLutRowBytes, (const double*)rv, (const double*)ri,
-                      (const double*)pn};
+    d.tables = Tables{(const uint16_t*)lut, (const uint8_t*)lut + kLutRowBytes,
+                      (const uint32_t*)((const char*)lut + kLutRowBytes + kLutMergedBytes), (const double*)rv,
+                      (const double*)ri, (const double*)pn};
     CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaFuncSetAttribute(k_rollout_random<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_rollout_random<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
@@ -777,10 +782,10 @@ int carve(void* scratch, size_t bytes, int64_t n, Scratch& s) {
     return 0;
 }
 // apply the records in s.key_in / s.val_in
-int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, int mode, cudaStream_t st) {
+int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, float lr, int mode, cudaStream_t st) {
     int g = grid_for(n, 256, D->sm_count);
     if (mode == G2048_MODE_ATOMIC) {
-        k_apply_atomic<<<g, 256, 0, st>>>(tab, s.key_in, s.val_in, n);
+        k_apply_atomic<<<g, 256, 0, st>>>(tab, s.key_in, s.val_in, lr, n);
         LAUNCH_CHECK("k_apply_atomic");
         return 0;
     }
@@ -789,7 +794,7 @@ int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int6
     // equal keys keep ascending record (= env) order
     CK(cub::DeviceRadixSort::SortPairs(s.cub_temp, s.cub_bytes, (const u64*)s.key_in, s.key_out, (const float*)s.val_in,
                                        s.val_out, (int64_t)n, 0, 64, st));
-    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, n);
+    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n);
     LAUNCH_CHECK("k_segment_apply");
     return 0;
 }
@@ -800,7 +805,7 @@ G2048_API size_t g2048_qlearn_scratch_bytes(int64_t n) { return scratch_bytes(n)
 G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
                                 int64_t n, int flavour, float lr, float gamma, double eps, int mode, int apply,
                                 uint64_t seed, uint64_t step_idx, uint64_t env_id_base, int64_t* counters,
-                                uint64_t* rec_key, uint8_t* rec_action, float* rec_delta, void* scratch,
+                                uint64_t* rec_key, uint8_t* rec_action, float* rec_target, void* scratch,
                                 size_t scratch_bytes_, void* stream) {
     DEVSTATE();
     if (n < 0 || (n && !boards) || !table || !pow2(capacity) || capacity > (1ull << 32) ||
@@ -817,11 +822,11 @@ G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score,
     k_qlearn_phase_a<F><<<g, 256, 0, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table, capacity - 1, \
                                                   n, lr, gamma, eps_threshold(eps), seed, step_idx, env_id_base,      \
                                                   (long long*)counters, s.key_in, s.val_in, (u64*)rec_key, rec_action, \
-                                                  rec_delta)
+                                                  rec_target)
     if (flavour == 0) PHASE_A(0); else PHASE_A(1);
 #undef PHASE_A
     LAUNCH_CHECK("k_qlearn_phase_a");
-    if (apply) return apply_records(D, (Slot*)table, capacity, s, n, mode, S(stream));
+    if (apply) return apply_records(D, (Slot*)table, capacity, s, n, lr, mode, S(stream));
     return 0;
 }
 
@@ -865,18 +870,18 @@ G2048_API int g2048_qtable_update(void* table, uint64_t capacity, const uint64_t
     int rc = carve(scratch, scratch_bytes_, n, sc);
     if (rc) return rc;
     k_q_update_phase_a<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((Slot*)table, capacity - 1, (const u64*)s, a, r,
-                                                                              (const u64*)s2, done, n, lr, gamma,
-                                                                              sc.key_in, sc.val_in);
+                                                                              (const u64*)s2, done, n, gamma, sc.key_in,
+                                                                              sc.val_in);
     LAUNCH_CHECK("k_q_update_phase_a");
-    return apply_records(D, (Slot*)table, capacity, sc, n, mode, S(stream));
+    return apply_records(D, (Slot*)table, capacity, sc, n, lr, mode, S(stream));
 }
-G2048_API int g2048_qtable_apply_deltas(void* table, uint64_t capacity, const uint64_t* keys, const uint8_t* a,
-                                        const float* delta, int64_t n, int mode, void* scratch, size_t scratch_bytes_,
-                                        void* stream) {
+G2048_API int g2048_qtable_apply_targets(void* table, uint64_t capacity, const uint64_t* keys, const uint8_t* a,
+                                         const float* target, int64_t n, float lr, int mode, void* scratch,
+                                         size_t scratch_bytes_, void* stream) {
     DEVSTATE();
-    if (n < 0 || !table || !pow2(capacity) || capacity > (1ull << 32) || (n && (!keys || !a || !delta)) ||
+    if (n < 0 || !table || !pow2(capacity) || capacity > (1ull << 32) || (n && (!keys || !a || !target)) ||
         (mode != 0 && mode != 1))
-        return fail(G2048_ERR_ARG, "g2048_qtable_apply_deltas: bad arguments");
+        return fail(G2048_ERR_ARG, "g2048_qtable_apply_targets: bad arguments");
     if (n == 0) return 0;
     Scratch sc{};
     int rc = carve(scratch, scratch_bytes_, n, sc);
@@ -884,8 +889,8 @@ G2048_API int g2048_qtable_apply_deltas(void* table, uint64_t capacity, const ui
     k_keys_to_records<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((Slot*)table, capacity - 1, (const u64*)keys, a,
                                                                              n, sc.key_in);
     LAUNCH_CHECK("k_keys_to_records");
-    CK(cudaMemcpyAsync(sc.val_in, delta, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, S(stream)));
-    return apply_records(D, (Slot*)table, capacity, sc, n, mode, S(stream));
+    CK(cudaMemcpyAsync(sc.val_in, target, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, S(stream)));
+    return apply_records(D, (Slot*)table, capacity, sc, n, lr, mode, S(stream));
 }
 G2048_API int g2048_qtable_size(const void* table, uint64_t capacity, int64_t* count, void* stream) {
     DEVSTATE();

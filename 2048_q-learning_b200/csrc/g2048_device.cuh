@@ -27,8 +27,9 @@ constexpr int kMaxProbe = 256;
 
 // Host-built tables resident in HBM/L2 (built once per device by g2048_init).
 struct Tables {
-    const uint16_t* lut_row;      // [65536] row moved left
-    const uint8_t* lut_merged;    // [65536] the (at most two) merged levels, hi nibble >= lo nibble
+    const uint16_t* lut_row;      // [65536] row moved left, stored at the swizzled index lut_index(row)
+    const uint8_t* lut_merged;    // [65536] the (at most two) merged levels, hi nibble >= lo nibble (same index)
+    const uint32_t* lut_mscore;   // [256] merged byte -> move score (bits 0-23) | hi level << 24
     const double* rew_valid;      // [16 lvl][16 d][256 score/4] normalised reward of a valid move
     const double* rew_invalid;    // [2 game_over][16 lvl][16 d]
     const double* pen;            // [32] stall penalty sequence, pen[0] = -1
@@ -38,7 +39,15 @@ struct Tables {
 struct Lut {
     const uint16_t* row;
     const uint8_t* merged;
+    const uint32_t* mscore;
 };
+// Bank swizzle of the LUT index, applied to two packed rows at once.  Real boards hold small levels, so the
+// plain index puts most lanes of a warp into ~8 of the 32 banks (measured 6.9 wavefronts per LDS); XOR-folding
+// bits 7-13 into bits 1-6 spreads them (2.7 wavefronts on rollout boards) and stays a bijection per row.
+constexpr u32 kSwzMask = 0x007E007Eu;
+__host__ __device__ __forceinline__ u32 lut_index2(u32 two_rows) {
+    return two_rows ^ (((two_rows >> 6) ^ (two_rows >> 7)) & kSwzMask);
+}
 
 // ------------------------------------------------------------------ Philox4x32-10
 // counter = (env id lo, env id hi, step lo, stream<<24 | step hi), key = seed
@@ -69,22 +78,35 @@ __device__ __forceinline__ u64 is15mask(u64 b) {  // bit 4i set iff nibble i == 
     t &= t >> 2;
     return t & kNib1;
 }
-__device__ __forceinline__ u32 rev_rows32(u32 x) {  // reverse the 4 nibbles of each 16-bit row
-    x = __byte_perm(x, 0, 0x2301);
-    return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+// Direction handling on the two 32-bit halves (lo = rows 0,1; hi = rows 2,3).  Both stages are involutions
+// and are made conditional through their PRMT selectors / delta-swap masks, so a warp whose lanes move in four
+// different directions runs one instruction stream:
+//   T (transpose)    byte permute [r0.lo r2.lo r1.lo r3.lo | r0.hi r2.hi r1.hi r3.hi], then swap the high nibble
+//                    of bytes 0,1 with the low nibble of bytes 2,3 (delta swap, shift 12)
+//   R (reverse rows) swap the bytes of each row, then the nibbles of each byte (delta swap, shift 4)
+struct MoveCtl { u32 selTlo, selThi, maskT, selR, maskR; };
+__device__ __forceinline__ MoveCtl move_ctl(int a) {  // 0 left | 1 up = T | 2 right = R | 3 down = T then R
+    MoveCtl c;
+    bool t = a & 1, r = a & 2;
+    c.selTlo = t ? 0x6240u : 0x3210u;
+    c.selThi = t ? 0x7351u : 0x7654u;
+    c.maskT = t ? 0x0000F0F0u : 0u;
+    c.selR = r ? 0x2301u : 0x3210u;
+    c.maskR = r ? 0x0F0F0F0Fu : 0u;
+    return c;
 }
-__device__ __forceinline__ u64 reverse_rows(u64 b) {
-    return ((u64)rev_rows32((u32)(b >> 32)) << 32) | rev_rows32((u32)b);
+__device__ __forceinline__ u32 delta_swap(u32 x, u32 mask, int shift) {
+    u32 t = ((x >> shift) ^ x) & mask;
+    return x ^ t ^ (t << shift);
 }
-__device__ __forceinline__ u64 transpose(u64 x) {  // 4x4 nibble matrix transpose
-    u64 a1 = x & 0xF0F00F0FF0F00F0Full;
-    u64 a2 = x & 0x0000F0F00000F0F0ull;
-    u64 a3 = x & 0x0F0F00000F0F0000ull;
-    u64 a = a1 | (a2 << 12) | (a3 >> 12);
-    u64 b1 = a & 0xFF00FF0000FF00FFull;
-    u64 b2 = a & 0x00FF00FF00000000ull;
-    u64 b3 = a & 0x00000000FF00FF00ull;
-    return b1 | (b2 >> 24) | (b3 << 24);
+__device__ __forceinline__ void stage_T(u32& lo, u32& hi, const MoveCtl& c) {
+    u32 l = __byte_perm(lo, hi, c.selTlo), h = __byte_perm(lo, hi, c.selThi);
+    lo = delta_swap(l, c.maskT, 12);
+    hi = delta_swap(h, c.maskT, 12);
+}
+__device__ __forceinline__ void stage_R(u32& lo, u32& hi, const MoveCtl& c) {
+    lo = delta_swap(__byte_perm(lo, 0, c.selR), c.maskR, 4);
+    hi = delta_swap(__byte_perm(hi, 0, c.selR), c.maskR, 4);
 }
 __device__ __forceinline__ int max_level(u64 b) {  // largest nibble
     u32 lo = (u32)b, hi = (u32)(b >> 32);
@@ -101,33 +123,33 @@ __device__ __forceinline__ int max_level(u64 b) {  // largest nibble
     return (int)(m & 0xFFu);
 }
 
-// move towards nibble 0 of every row through the row LUT (move_left, Game2048_env.py:22-46).
-// mm receives the four rows' merged-level bytes.
-__device__ __forceinline__ u64 move_left_lut(u64 t, const Lut& L, u32& mm) {
-    u32 lo = (u32)t, hi = (u32)(t >> 32);
-    u32 i0 = lo & 0xFFFFu, i1 = lo >> 16, i2 = hi & 0xFFFFu, i3 = hi >> 16;
+// Result of one move: the moved board, whether anything moved, the move score and the largest merged level.
+struct Moved {
+    u64 board;
+    int score;     // score += merged value (Game2048_env.py:35)
+    int hi_level;  // largest level created by a merge (0 = none)
+    bool moved;
+};
+// Game2048.move without the spawn (Game2048_env.py:51-60): canonicalise the direction (T, R), move towards
+// nibble 0 of every row through the row LUT (move_left, :22-46), undo (R, T).
+__device__ __forceinline__ Moved do_move(u64 b, int a, const Lut& L) {
+    MoveCtl c = move_ctl(a);
+    u32 lo = (u32)b, hi = (u32)(b >> 32);
+    stage_T(lo, hi, c);
+    stage_R(lo, hi, c);
+    u32 plo = lut_index2(lo), phi = lut_index2(hi);
+    u32 i0 = plo & 0xFFFFu, i1 = plo >> 16, i2 = phi & 0xFFFFu, i3 = phi >> 16;
     u32 r0 = L.row[i0], r1 = L.row[i1], r2 = L.row[i2], r3 = L.row[i3];
-    u32 m0 = L.merged[i0], m1 = L.merged[i1], m2 = L.merged[i2], m3 = L.merged[i3];
-    mm = m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
-    return ((u64)(r2 | (r3 << 16)) << 32) | (u64)(r0 | (r1 << 16));
-}
-// sum over the 8 merged-level nibbles of 2^level (level 0 = no merge) (score += merged value, :35)
-__device__ __forceinline__ int merge_score(u32 mm) {
-    int s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += (int)((1u << ((mm >> (4 * i)) & 0xFu)) & ~1u);
-    return s;
-}
-// Game2048.move without the spawn (Game2048_env.py:51-60), branch-free in the action:
-// 0 left | 1 up = transpose,left,transpose | 2 right = reverse,left,reverse | 3 down = both.
-__device__ __forceinline__ bool do_move(u64 b, int a, const Lut& L, u64& out, u32& mm) {
-    u64 t = (a & 1) ? transpose(b) : b;
-    t = (a & 2) ? reverse_rows(t) : t;
-    u64 r = move_left_lut(t, L, mm);
-    bool moved = (r != t);
-    r = (a & 2) ? reverse_rows(r) : r;
-    out = (a & 1) ? transpose(r) : r;
-    return moved;
+    u32 e0 = L.mscore[L.merged[i0]], e1 = L.mscore[L.merged[i1]], e2 = L.mscore[L.merged[i2]], e3 = L.mscore[L.merged[i3]];
+    u32 nlo = r0 | (r1 << 16), nhi = r2 | (r3 << 16);
+    Moved m;
+    m.moved = (nlo != lo) | (nhi != hi);
+    m.score = (int)((e0 + e1 + e2 + e3) & 0x00FFFFFFu);
+    m.hi_level = (int)(max(max(e0, e1), max(e2, e3)) >> 24);
+    stage_R(nlo, nhi, c);
+    stage_T(nlo, nhi, c);
+    m.board = ((u64)nhi << 32) | nlo;
+    return m;
 }
 
 // position (bit offset, multiple of 4) of the k-th set bit of E (bits only at nibble LSBs),
@@ -145,15 +167,17 @@ __device__ __forceinline__ int kth_empty_pos(u64 E, int k) {
 }
 // add_number (Game2048_env.py:16-20).  REPLAY: d0 = recorded cell index k, d1 = recorded is-4 flag;
 // otherwise d0/d1 are 32-bit uniform draws: k = floor(d0 * n_empty / 2^32), 4 iff d1 >= 0.9 * 2^32.
+// lvl_max is raised to the spawned level (1 or 2) when it is larger.
 template <bool REPLAY>
-__device__ __forceinline__ u64 spawn(u64 b, u32 d0, u32 d1) {
+__device__ __forceinline__ u64 spawn(u64 b, u32 d0, u32 d1, int& lvl_max) {
     u64 E = ~nzmask(b) & kNib1;
     int ne = __popcll(E);
     if (ne == 0) return b;
     int k = REPLAY ? (int)d0 : (int)__umulhi(d0, (u32)ne);
     if (k >= ne) k = ne - 1;  // malformed replay input: stay in range
-    bool is4 = REPLAY ? (d1 != 0) : (d1 >= kIs4Thresh);
-    return b | ((u64)(is4 ? 2 : 1) << kth_empty_pos(E, k));
+    int lvl = (REPLAY ? (d1 != 0) : (d1 >= kIs4Thresh)) ? 2 : 1;
+    lvl_max = max(lvl_max, lvl);
+    return b | ((u64)lvl << kth_empty_pos(E, k));
 }
 // Game2048.__init__ (Game2048_env.py:11-14): empty board + two spawns
 template <bool REPLAY>
@@ -198,8 +222,12 @@ struct Env {
     u32 cons_count;   // consecutive_count (saturating)
     u32 small;        // prev_level | cons_action << 8 | pen_idx << 16   (aux low word)
     int score;        // env.score
+    int maxlvl;       // largest level on `board`, carried across steps (tiles only grow within an episode)
 };
-__device__ __forceinline__ void env_from_aux(Env& e, u64 aux) { e.small = (u32)aux; e.cons_count = (u32)(aux >> 32); }
+__device__ __forceinline__ void env_load(Env& e, u64 board, u64 aux, int score) {
+    e.board = board; e.small = (u32)aux; e.cons_count = (u32)(aux >> 32); e.score = score;
+    e.maxlvl = max_level(board);
+}
 __device__ __forceinline__ u64 env_to_aux(const Env& e) { return ((u64)e.cons_count << 32) | e.small; }
 
 struct StepOut {
@@ -226,15 +254,15 @@ __device__ __forceinline__ double shaped_reward(int score, bool valid, bool game
 // Game2048_env.step, penalty flavour (Game2048_env.py:97-129).  d0,d1: spawn draws of the move.
 template <bool REPLAY>
 __device__ __forceinline__ void penalty_step(Env& e, int a, u32 d0, u32 d1, const Lut& L, const Tables& T, StepOut& o) {
-    u64 b1;
-    u32 mm;
-    bool valid = do_move(e.board, a, L, b1, mm);                 // :98
-    int ms = merge_score(mm);
-    if (valid) b1 = spawn<REPLAY>(b1, d0, d1);                   // :61-62
+    Moved m = do_move(e.board, a, L);                            // :98
+    bool valid = m.moved;
+    int ms = m.score, lvl = max(e.maxlvl, m.hi_level);           // np.max(board) :100, incrementally
+    u64 b1 = m.board;
+    if (valid) b1 = spawn<REPLAY>(b1, d0, d1, lvl);              // :61-62
     bool game_over = is_dead(b1);                                // :99
-    int lvl = max_level(b1);                                     // :100
     if (lvl < 1) lvl = 1;                                        // max(2, max_number) :141
     e.board = b1;
+    e.maxlvl = lvl;
     e.score += ms;                                               // :104
     int prev_level = (int)(e.small & 0xFFu), cons_action = (int)((e.small >> 8) & 0xFFu);
     int pen_idx = (int)((e.small >> 16) & 0xFFu);
@@ -264,25 +292,27 @@ __device__ __forceinline__ void penalty_step(Env& e, int a, u32 d0, u32 d1, cons
 // agent's action (full-board quirk).
 template <bool REPLAY>
 __device__ __forceinline__ void nopenalty_step(Env& e, int a, u32 d0, u32 d1, u32 q0, u32 q1, const Lut& L, StepOut& o) {
-    u64 S = e.board, M;
-    u32 mm;
-    bool valid = do_move(S, a, L, M, mm);                        // :53-66
-    int ms = merge_score(mm);
-    if (valid) M = spawn<REPLAY>(M, d0, d1);
+    u64 S = e.board;
+    Moved m = do_move(S, a, L);                                  // :53-66
+    bool valid = m.moved;
+    int ms = m.score, lvl = max(e.maxlvl, m.hi_level);
+    u64 M = m.board;
+    if (valid) M = spawn<REPLAY>(M, d0, d1, lvl);
     bool game_over = false;
     if (nzmask(S) == kNib1) {                                    // :68-78, evaluated on S
         u32 lm = legal_mask(S);
+        lvl = e.maxlvl;
         if (lm == 0) {
             game_over = true;
             M = S;
         } else {
-            u32 mm2;
-            do_move(S, __ffs((int)lm) - 1, L, M, mm2);
-            M = spawn<REPLAY>(M, q0, q1);
+            Moved m2 = do_move(S, __ffs((int)lm) - 1, L);
+            lvl = max(lvl, m2.hi_level);
+            M = spawn<REPLAY>(m2.board, q0, q1, lvl);
         }
     }
-    int lvl = max_level(M);                                      // :108
-    e.board = M;
+    e.board = M;                                                 // np.max(moved_board) :108
+    e.maxlvl = lvl;
     e.score += ms;                                               // :111
     o.reward = (!valid && !game_over) ? -10.0 : (double)ms;      // :122-128
     o.move_score = ms; o.maxlvl = lvl;
@@ -307,6 +337,7 @@ __device__ __forceinline__ void philox_step(Env& e, int a, const Draw4& x, u64 s
 __device__ __forceinline__ void philox_autoreset(Env& e, u64 seed, u64 env_id, u64 t) {
     Draw4 y = philox(seed, env_id, t, G2048_STREAM_AUTORESET);
     e.board = fresh_board<false>(y.x0, y.x1, y.x2, y.x3);
+    e.maxlvl = ((y.x1 >= kIs4Thresh) || (y.x3 >= kIs4Thresh)) ? 2 : 1;
     e.score = 0;   // reset() zeroes env.score only (Game2048_env.py:187-191); aux state survives
 }
 
@@ -337,7 +368,7 @@ __device__ __forceinline__ void load_slot(const Slot* s, u64& key, float4& q) {
 // defaultdict semantics (main.py:16): reading a state creates its zero row.  Returns the slot index
 // (kNoSlot if the probe limit is hit: the state is then treated as a zero row and not updated).
 template <bool INSERT>
-__device__ __forceinline__ u32 table_find(Slot* tab, u64 mask, u64 key, float4& q, int& inserted) {
+__device__ __forceinline__ u32 table_find(Slot* tab, u64 mask, u64 key, float4& q, u32& inserted) {
     u64 h = mix64(key) & mask;
     for (int p = 0; p < kMaxProbe; ++p, h = (h + 1) & mask) {
         u64 k;
@@ -371,20 +402,38 @@ __device__ __forceinline__ int choose_action(const float4& q, const Draw4& x, u6
     return ((u64)x.x2 < eps_thresh) ? (int)(x.x3 >> 30) : argmax4(q);
 }
 // update_q_value (main.py:40-43) in float32, every operation rounded on its own (-fmad=false):
-// delta = lr * ((r + (done ? 0 : gamma * best_next)) - q_sa)
-__device__ __forceinline__ float td_delta(float lr, float gamma, float r, float best_next, bool done, float q_sa) {
+//   target = r + (done ? 0 : gamma * best_next)     q = q + lr * (target - q)
+__device__ __forceinline__ float td_target(float gamma, float r, float best_next, bool done) {
     float g = __fmul_rn(gamma, best_next);
-    float target = __fadd_rn(r, done ? 0.0f : g);
-    return __fmul_rn(lr, __fsub_rn(target, q_sa));
+    return __fadd_rn(r, done ? 0.0f : g);
+}
+__device__ __forceinline__ float td_apply(float q, float lr, float target) {
+    return __fadd_rn(q, __fmul_rn(lr, __fsub_rn(target, q)));
+}
+// Atomic read-modify-write of one Q value: q <- q + lr * (target - q) as a CAS loop, so concurrent
+// updates of the same (state, action) compose like the reference's sequential loop (a contraction
+// towards the targets) instead of summing stale deltas, which diverges once the number of
+// simultaneous updaters exceeds 2 / lr.  `guess` is the caller's last view of the value.
+__device__ __forceinline__ float q_update_atomic(float* addr, float guess, float lr, float target) {
+    u32 assumed = __float_as_uint(guess);
+    while (true) {
+        float nq = td_apply(__uint_as_float(assumed), lr, target);
+        u32 old = atomicCAS(reinterpret_cast<u32*>(addr), assumed, __float_as_uint(nq));
+        if (old == assumed) return nq;
+        assumed = old;
+    }
 }
 
 // ------------------------------------------------------------------ counters
+// Per-thread partial sums (32-bit where a launch cannot overflow them), reduced per warp and added to the
+// caller's int64 counters with one atomic per warp and counter.
 struct Counters {
-    long long steps = 0, valid = 0, episodes = 0, score = 0, reward_fx = 0, inserts = 0, dropped = 0;
+    u32 steps = 0, valid = 0, episodes = 0, inserts = 0, dropped = 0;
     int maxlvl = 0;
+    long long score = 0, reward_fx = 0;
     __device__ __forceinline__ void add(const StepOut& o) {
         steps += 1; valid += o.valid; episodes += o.done; score += o.move_score;
-        maxlvl = o.maxlvl > maxlvl ? o.maxlvl : maxlvl;
+        maxlvl = max(o.maxlvl, maxlvl);
         reward_fx += (long long)(o.reward * 1048576.0);
     }
 };

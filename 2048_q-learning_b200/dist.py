@@ -1,8 +1,8 @@
-"""Env shards over the GPUs of one box + the Q-delta exchange (one process per GPU, torch.distributed).
+"""Env shards over the GPUs of one box + the Q-target exchange (one process per GPU, torch.distributed).
 
 Envs are independent (the reference has exactly one, main.py:66), so rank r owns the contiguous global env
 ids [lo, hi) and its Philox draws are keyed by the GLOBAL env id: results do not depend on the sharding.
-The Q-table is replicated; the only exchange step is the list of (state key, action, delta) records of one
+The Q-table is replicated; the only exchange step is the list of (state key, action, target) records of one
 synchronous step (16 B per transition, fixed size per rank): `all_gather` in rank order = ascending global
 env id, then every replica applies the whole list with the same deterministic kernel (sort by
 (state, action) + segmented sum), so all replicas stay identical and equal to the 1-GPU result.
@@ -34,8 +34,8 @@ class TorchEngine:
     def emit(self):
         return self.agent.step_sync(self.env, mode="deterministic", apply=False, records=True)
 
-    def apply(self, keys, actions, deltas):
-        self.agent.apply_deltas(keys, actions, deltas, mode="deterministic")
+    def apply(self, keys, actions, targets):
+        self.agent.apply_targets(keys, actions, targets, mode="deterministic")
 
 
 class ShardedQLearning:
@@ -59,5 +59,5 @@ class ShardedQLearning:
         return torch.cat([o[:n] for o, n in zip(out, self.sizes)])
 
     def step(self):
-        keys, actions, deltas = self.engine.emit()
-        self.engine.apply(self._gather(keys), self._gather(actions), self._gather(deltas))
+        keys, actions, targets = self.engine.emit()
+        self.engine.apply(self._gather(keys), self._gather(actions), self._gather(targets))

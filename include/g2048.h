@@ -76,8 +76,8 @@
 #define G2048_N_COUNTERS 8
 
 /* Q-learning modes */
-#define G2048_MODE_ATOMIC 0         /* deltas applied with float atomics (sum order unspecified) */
-#define G2048_MODE_DETERMINISTIC 1  /* sort by (state, action) + segmented sum in ascending env order */
+#define G2048_MODE_ATOMIC 0         /* q <- q + lr (target - q) as an atomic CAS loop (order among duplicates unspecified) */
+#define G2048_MODE_DETERMINISTIC 1  /* sort by (state, action), duplicates applied one after another in ascending env order */
 
 #define G2048_QTABLE_SLOT_BYTES 32  /* key u64 | meta u64 | float q[4] */
 
@@ -145,21 +145,24 @@ G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* sco
 
 /* The loop of main.py:91-101 for n envs and k_steps steps each, fused: epsilon-greedy choose_action
  * (main.py:34-38) -> env step -> update_q_value (main.py:40-43) on the HBM hash table, asynchronously
- * (each env applies its update at once with a float atomic; N = 1 is the reference's sequential order). */
+ * (each env applies q <- q + lr (target - q) at once as an atomic read-modify-write; N = 1 is the reference's
+ * sequential order). */
 G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
                                    int64_t n, int64_t k_steps, int flavour, float lr, float gamma, double eps,
                                    uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t* counters,
                                    void* stream);
 
 /* One synchronous batched Q-learning step: every env chooses from and bootstraps
- * on the table as it is at step start; the deltas are applied afterwards (mode ATOMIC or DETERMINISTIC).
- * rec_key/rec_action/rec_delta (each may be NULL) export the (state, action, delta) records, e.g. for the
+ * on the table as it is at step start (target_i = r_i + gamma max Q[s'_i] (1 - done_i)); afterwards every
+ * (state, action) receives its targets one after another, q <- q + lr (target_i - q) -- the reference's own
+ * update applied in sequence -- in ascending env order (DETERMINISTIC) or in unspecified order (ATOMIC).
+ * rec_key/rec_action/rec_target (each may be NULL) export the (state, action, target) records, e.g. for the
  * cross-GPU exchange; apply = 0 only emits them and leaves the Q values untouched. */
 G2048_API size_t g2048_qlearn_scratch_bytes(int64_t n);
 G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
                                 int64_t n, int flavour, float lr, float gamma, double eps, int mode, int apply,
                                 uint64_t seed, uint64_t step_idx, uint64_t env_id_base, int64_t* counters,
-                                uint64_t* rec_key, uint8_t* rec_action, float* rec_delta, void* scratch,
+                                uint64_t* rec_key, uint8_t* rec_action, float* rec_target, void* scratch,
                                 size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------ Q-table (device pointers) */
@@ -177,10 +180,10 @@ G2048_API int g2048_choose_action(void* table, uint64_t capacity, const uint64_t
 G2048_API int g2048_qtable_update(void* table, uint64_t capacity, const uint64_t* s, const uint8_t* a, const float* r,
                                   const uint64_t* s2, const uint8_t* done, int64_t n, float lr, float gamma, int mode,
                                   void* scratch, size_t scratch_bytes, void* stream);
-/* Q[key][a] += delta for n records (e.g. all-gathered from the other ranks), same modes. */
-G2048_API int g2048_qtable_apply_deltas(void* table, uint64_t capacity, const uint64_t* keys, const uint8_t* a,
-                                        const float* delta, int64_t n, int mode, void* scratch, size_t scratch_bytes,
-                                        void* stream);
+/* Q[key][a] <- Q + lr (target - Q) for n records (e.g. all-gathered from the other ranks), same modes. */
+G2048_API int g2048_qtable_apply_targets(void* table, uint64_t capacity, const uint64_t* keys, const uint8_t* a,
+                                         const float* target, int64_t n, float lr, int mode, void* scratch,
+                                         size_t scratch_bytes, void* stream);
 /* number of states -> *count (device int64) */
 G2048_API int g2048_qtable_size(const void* table, uint64_t capacity, int64_t* count, void* stream);
 /* compact (key, row) pairs into keys[max_out], rows[max_out][4]; *count (device int64, zeroed by the caller)

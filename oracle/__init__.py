@@ -66,7 +66,7 @@ def load():
             "orc_q_update_seq_f64": (None, [vp] * 6 + [i64, f64, f64]),
             "orc_q_replay_agent_f64": (None, [vp] * 8 + [i64, f64, f64]),
             "orc_q_update_batch_f32": (None, [vp] * 6 + [i64, f32, f32]),
-            "orc_q_apply_deltas_f32": (None, [vp] * 4 + [i64]),
+            "orc_q_apply_targets_f32": (None, [vp] * 4 + [f32, i64]),
             "orc_rollout_random": (None, [vp, vp, vp, i64, i64, i32, u64, u64, u64, vp]),
             "orc_choose_action": (None, [vp, vp, i64, u64, u64, u64, u64, vp]),
             "orc_rollout_qlearn_seq": (None, [vp, vp, vp, vp, i64, i64, i32, f32, f32, u64, u64, u64, u64, vp]),
@@ -195,9 +195,10 @@ class QTable:
         load().orc_q_update_batch_f32(self.h, _p(s, np.uint64), _p(a, np.uint8), _p(r, np.float32), _p(s2, np.uint64),
                                       _p(done, np.uint8), len(s), lr, gamma)
 
-    def apply_deltas_f32(self, keys, a, delta):
+    def apply_targets_f32(self, keys, a, target, lr):
         assert self.f32
-        load().orc_q_apply_deltas_f32(self.h, _p(keys, np.uint64), _p(a, np.uint8), _p(delta, np.float32), len(keys))
+        load().orc_q_apply_targets_f32(self.h, _p(keys, np.uint64), _p(a, np.uint8), _p(target, np.float32), lr,
+                                       len(keys))
 
     def choose_action(self, boards, eps_thresh, seed, step_idx, env_id_base=0):
         assert self.f32

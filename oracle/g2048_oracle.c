@@ -617,14 +617,21 @@ ORC_API void orc_q_replay_agent_f64(qtab_t *t, const uint64_t *s, const uint8_t 
 
 /* float32 arithmetic helpers: every operation rounds to float32 on its own
  * (no FMA contraction, no excess precision) -- the CUDA side is compiled with
- * -fmad=false and must produce the same bits. */
-static float f32_delta(float lr, float gamma, float r, float best_next, int done, float q_sa) {
+ * -fmad=false and must produce the same bits.
+ * update_q_value (main.py:40-43) split in two:
+ *   target = r + (done ? 0 : gamma * best_next)           (:41-42)
+ *   q      = q + lr * (target - q)                         (:43) */
+static float f32_target(float gamma, float r, float best_next, int done) {
     volatile float g = gamma * best_next;
     volatile float gn = done ? 0.0f : g;
     volatile float target = r + gn;
-    volatile float diff = target - q_sa;
+    return target;
+}
+static float f32_apply(float q, float lr, float target) {
+    volatile float diff = target - q;
     volatile float d = lr * diff;
-    return d;
+    volatile float nq = q + d;
+    return nq;
 }
 typedef struct { uint64_t key; int64_t idx; } sortrec_t;
 static int sortrec_cmp(const void *pa, const void *pb) {
@@ -632,36 +639,32 @@ static int sortrec_cmp(const void *pa, const void *pb) {
     if (a->key != b->key) return a->key < b->key ? -1 : 1;
     return a->idx < b->idx ? -1 : (a->idx > b->idx);
 }
-/* Q[slot][a] = Q[slot][a] + (delta_i1 + delta_i2 + ...), each (slot, a)
- * segment accumulated in ascending i. */
-static void apply_deltas_sorted(float *rows, const int64_t *slot, const uint8_t *a, const float *delta, int64_t n) {
+/* Transitions that hit the same (state, action) in one batch are applied one after
+ * another in ascending i -- q = q + lr * (target_i - q) -- exactly what the
+ * reference's sequential loop does to Q[s][a]; only the bootstrap values inside
+ * target_i come from the snapshot.  (Summing the deltas instead would multiply the
+ * step size by the number of duplicates and diverge once that exceeds 2 / lr.) */
+static void apply_targets_sorted(float *rows, const int64_t *slot, const uint8_t *a, const float *target, float lr,
+                                 int64_t n) {
     sortrec_t *rec = (sortrec_t *)malloc((size_t)(n ? n : 1) * sizeof *rec);
     int64_t m = 0;
     for (int64_t i = 0; i < n; ++i)
         if (slot[i] >= 0) { rec[m].key = (uint64_t)slot[i] * 4 + a[i]; rec[m].idx = i; ++m; }
     qsort(rec, (size_t)m, sizeof *rec, sortrec_cmp);
-    for (int64_t i = 0; i < m;) {
-        volatile float acc = delta[rec[i].idx];
-        int64_t j = i + 1;
-        for (; j < m && rec[j].key == rec[i].key; ++j) acc = acc + delta[rec[j].idx];
-        volatile float q = rows[rec[i].key];
-        q = q + acc;
-        rows[rec[i].key] = q;
-        i = j;
-    }
+    for (int64_t i = 0; i < m; ++i) rows[rec[i].key] = f32_apply(rows[rec[i].key], lr, target[rec[i].idx]);
     free(rec);
 }
 
 /* Batched synchronous update, float32 rows:
- * every transition reads Q from the snapshot at batch start,
- *   delta_i = lr * ((r_i + (done_i ? 0 : gamma * max_a Q[s2_i][a])) - Q[s_i][a_i])
- * then Q[s][a] = Q[s][a] + (sum of its delta_i accumulated in ascending i).
+ * every transition bootstraps on the snapshot at batch start,
+ *   target_i = r_i + (done_i ? 0 : gamma * max_a Q_snap[s2_i][a])
+ * then each (s, a) receives its targets in ascending i: q = q + lr * (target_i - q).
  * N = 1 is exactly update_q_value (main.py:40-43) in float32. */
 ORC_API void orc_q_update_batch_f32(qtab_t *t, const uint64_t *s, const uint8_t *a, const float *r,
                                     const uint64_t *s2, const uint8_t *done, int64_t n, float lr, float gamma) {
     float *rows = (float *)t->rows;
     int64_t *slot = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
-    float *delta = (float *)malloc((size_t)(n ? n : 1) * sizeof(float));
+    float *target = (float *)malloc((size_t)(n ? n : 1) * sizeof(float));
     for (int64_t i = 0; i < n; ++i) { /* inserts create zero rows only: they change no value */
         qtab_slot(t, s2[i], 1);
         slot[i] = qtab_slot(t, s[i], 1);
@@ -669,19 +672,19 @@ ORC_API void orc_q_update_batch_f32(qtab_t *t, const uint64_t *s, const uint8_t 
     for (int64_t i = 0; i < n; ++i) {
         int64_t h2 = qtab_slot(t, s2[i], 0);
         float best = h2 < 0 ? 0.0f : rows[4 * h2 + argmax4f(&rows[4 * h2])];
-        float q_sa = slot[i] < 0 ? 0.0f : rows[4 * slot[i] + a[i]];
-        delta[i] = f32_delta(lr, gamma, r[i], best, done[i] != 0, q_sa);
+        target[i] = f32_target(gamma, r[i], best, done[i] != 0);
     }
-    apply_deltas_sorted(rows, slot, a, delta, n);
-    free(delta); free(slot);
+    apply_targets_sorted(rows, slot, a, target, lr, n);
+    free(target); free(slot);
 }
 
-/* (key, action, delta) lists, e.g. received from other ranks: look the key up
- * (insert if absent) and accumulate as above. */
-ORC_API void orc_q_apply_deltas_f32(qtab_t *t, const uint64_t *keys, const uint8_t *a, const float *delta, int64_t n) {
+/* (key, action, target) records, e.g. received from other ranks: look the key up
+ * (insert if absent) and apply as above. */
+ORC_API void orc_q_apply_targets_f32(qtab_t *t, const uint64_t *keys, const uint8_t *a, const float *target, float lr,
+                                     int64_t n) {
     int64_t *slot = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
     for (int64_t i = 0; i < n; ++i) slot[i] = qtab_slot(t, keys[i], 1);
-    apply_deltas_sorted((float *)t->rows, slot, a, delta, n);
+    apply_targets_sorted((float *)t->rows, slot, a, target, lr, n);
     free(slot);
 }
 
@@ -777,11 +780,9 @@ ORC_API void orc_rollout_qlearn_seq(uint64_t *boards, uint64_t *aux, int32_t *sc
             count_step(counters, &o);
             int64_t h2 = qtab_slot_counted(t, e.board, counters);
             float best = h2 < 0 ? 0.0f : rows[4 * h2 + argmax4f(rows + 4 * h2)];
-            if (h >= 0) {
-                volatile float q = rows[4 * h + a];
-                q = q + f32_delta(lr, gamma, (float)o.reward, best, (o.flags & FLAG_DONE) != 0, q);
-                rows[4 * h + a] = q;
-            }
+            if (h >= 0)
+                rows[4 * h + a] = f32_apply(rows[4 * h + a], lr,
+                                            f32_target(gamma, (float)o.reward, best, (o.flags & FLAG_DONE) != 0));
             if (o.flags & FLAG_DONE) {
                 philox_reset(&e, seed, id, step, STREAM_AUTORESET);
                 qtab_slot_counted(t, e.board, counters); /* state = env.reset() is read at once (main.py:81-82, :92) */
@@ -795,19 +796,19 @@ ORC_API void orc_rollout_qlearn_seq(uint64_t *boards, uint64_t *aux, int32_t *sc
 
 /* One synchronous batched Q-learning step over n envs:
  * all envs choose from and bootstrap on the table snapshot at step start;
- * deltas are applied afterwards, each (state, action) segment summed in
- * ascending env order.  Bit-comparable with the GPU's deterministic mode for
+ * the targets are applied afterwards, each (state, action) receiving its
+ * targets in ascending env order.  Bit-comparable with the GPU's deterministic mode for
  * any n and any sharding.  Optionally exports the transition records. */
 ORC_API void orc_qlearn_step_sync(uint64_t *boards, uint64_t *aux, int32_t *score, qtab_t *t, int64_t n,
                                   int flavour, float lr, float gamma, uint64_t eps_thresh, uint64_t seed,
                                   uint64_t step, uint64_t env_id_base, int64_t *counters,
-                                  uint64_t *rec_key, uint8_t *rec_action, float *rec_delta, int apply) {
+                                  uint64_t *rec_key, uint8_t *rec_action, float *rec_target, int apply) {
     float *rows = (float *)t->rows;
     static const float zero[4] = {0, 0, 0, 0};
     g_want_legal = 0;
     int64_t *slot = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
     uint8_t *act = (uint8_t *)malloc((size_t)(n ? n : 1));
-    float *delta = (float *)malloc((size_t)(n ? n : 1) * sizeof(float));
+    float *target = (float *)malloc((size_t)(n ? n : 1) * sizeof(float));
     for (int64_t i = 0; i < n; ++i) {
         env_t e = {boards[i], aux ? aux[i] : AUX_INIT, score ? score[i] : 0};
         uint64_t id = env_id_base + (uint64_t)i;
@@ -822,18 +823,17 @@ ORC_API void orc_qlearn_step_sync(uint64_t *boards, uint64_t *aux, int32_t *scor
         int64_t h2 = qtab_slot_counted(t, e.board, counters);
         float best = h2 < 0 ? 0.0f : rows[4 * h2 + argmax4f(rows + 4 * h2)];
         slot[i] = h; act[i] = (uint8_t)a;
-        delta[i] = f32_delta(lr, gamma, (float)o.reward, best, (o.flags & FLAG_DONE) != 0,
-                             h < 0 ? 0.0f : rows[4 * h + a]);
+        target[i] = f32_target(gamma, (float)o.reward, best, (o.flags & FLAG_DONE) != 0);
         if (rec_action) rec_action[i] = (uint8_t)a;
-        if (rec_delta) rec_delta[i] = delta[i];
+        if (rec_target) rec_target[i] = target[i];
         if (o.flags & FLAG_DONE) philox_reset(&e, seed, id, step, STREAM_AUTORESET);
         boards[i] = e.board;
         if (aux) aux[i] = e.aux;
         if (score) score[i] = e.score;
     }
     /* apply = 0: emit the records only (the cross-rank exchange applies them) */
-    if (apply) apply_deltas_sorted(rows, slot, act, delta, n);
-    free(delta); free(act); free(slot);
+    if (apply) apply_targets_sorted(rows, slot, act, target, lr, n);
+    free(target); free(act); free(slot);
 }
 
 /* ------------------------------------------------------------------------- */

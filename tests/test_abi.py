@@ -35,7 +35,7 @@ def test_sass_is_sm100a_with_bulk_copy_and_256bit_loads():
     assert "sm_100a" in sass
     assert "UBLKCP" in sass          # cp.async.bulk (TMA) staging of the row LUT
     assert ".256" in sass            # one 32-byte load per Q-table slot
-    assert "REDG.E.ADD.F32" in sass  # float atomics on Q values without a return trip
+    assert "ATOMG.E.CAS" in sass     # key insertion and the atomic q <- q + lr (target - q)
 
 
 @pytest.mark.skipif(ctypes.CDLL(g2048.build()).g2048_device_count() > 0, reason="a GPU is present")

@@ -34,7 +34,7 @@ class OracleEngine:
         return torch.from_numpy(k.view(np.int64)), torch.from_numpy(a), torch.from_numpy(d)
 
     def apply(self, keys, actions, deltas):
-        self.tab.apply_deltas_f32(keys.numpy().view(np.uint64).copy(), actions.numpy().copy(), deltas.numpy().copy())
+        self.tab.apply_targets_f32(keys.numpy().view(np.uint64).copy(), actions.numpy().copy(), deltas.numpy().copy(), 0.1)
 
 
 def _worker(rank, world, port, out):

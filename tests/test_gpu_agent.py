@@ -75,7 +75,7 @@ def test_sharded_delta_exchange_equals_single_gpu(g):
         recs = [replicas[r].step_sync(shard_envs[r], mode="deterministic", apply=False, records=True) for r in range(G)]
         keys = torch.cat([x[0] for x in recs]); acts = torch.cat([x[1] for x in recs]); dl = torch.cat([x[2] for x in recs])
         for r in range(G):
-            replicas[r].apply_deltas(keys, acts, dl, mode="deterministic")
+            replicas[r].apply_targets(keys, acts, dl, mode="deterministic")
     k1, r1 = one.export()
     for r in range(G):
         assert np.array_equal(np_boards(shard_envs[r].boards), np_boards(one_env.boards)[r * h:(r + 1) * h])
