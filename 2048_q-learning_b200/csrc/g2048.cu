@@ -6,7 +6,8 @@
 //   k_rollout_random  K steps per env with the board in registers, row LUT staged in shared memory by
 //                     one bulk-async (TMA) copy, Philox spawn, in-kernel reset
 //   k_rollout_qlearn  the same loop with epsilon-greedy choose_action and the TD update on the HBM hash
-//                     table fused in (one 32-byte sector read + one float RED per step)
+//                     table fused in (probe loads are the only dependent memory chain; insert and update are
+//                     speculative atomicCAS checked one step later)
 //   k_qlearn_phase_a / k_q_update_phase_a / k_keys_to_records + k_apply_atomic / CUB radix sort +
 //   k_segment_apply   synchronous batched update, atomic and deterministic modes
 //   k_q_lookup, k_choose_action, k_q_size, k_q_export, k_legal_mask, k_pack, k_unpack, k_onehot,
@@ -261,8 +262,20 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
 }
 
 // main.py:91-101 fused.  Per step: Philox -> epsilon-greedy from the carried row of s -> env step ->
-// find-or-insert s' (one 32-byte sector) -> atomic q <- q + lr (target - q) on Q[s][a] -> carry (slot, row)
-// of s' as the next s.
+// find-or-insert s' -> q <- q + lr (target - q) on Q[s][a] -> carry (slot, row) of s' as the next s.
+//
+// Measured on B200 (tools/membench.cu): random 32-byte sector LOADS that miss L2 saturate at ~36 G/s and
+// atomicCAS that misses L2 at ~20 G/s, both already at 256 threads/SM -- that, not the 6.5 TB/s streaming
+// peak, is what bounds a hash table in HBM.  So the kernel keeps the dependent chain per step at the probe
+// loads only:
+//   * lookup = plain 256-bit load(s); an empty slot is claimed with atomicCAS (an L2 hit by then) WITHOUT
+//     waiting for its result: the lane goes on as if the insert succeeded (a new state has a zero row
+//     wherever it lands) and checks the CAS result one step later, re-probing only if another state won the slot;
+//   * the update is ONE atomicCAS from the value this lane read (again an L2 hit, again checked a step later):
+//     it applies q <- q + lr (target - q) atomically, and is skipped (counted in LOST) if another env changed
+//     the same Q value in between -- stale deltas are never summed, so heavily shared early-game states cannot
+//     diverge, and no lane spins on a contended address.  With one env nothing is ever lost: N = 1 is the
+//     reference's sequential order exactly.
 template <int FLAVOUR>
 __global__ void __launch_bounds__(kRolloutThreads, 1)
 k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mask, long long n, long long k_steps,
@@ -276,39 +289,71 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
         env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
         u64 id = id_base + (u64)i;
         float4 row;
-        u32 ins = 0;
-        u32 slot = table_find<true>(tab, mask, e.board, row, ins);
+        u32 slot = table_find<true>(tab, mask, e.board, row, c.inserts);
         c.dropped += (slot == kNoSlot);
+        bool ins_pending = false, upd_pending = false, upd_patch = false;
+        u64 ins_old = 0;
+        u32 upd_old = 0, upd_assumed = 0;
+        int upd_a = 0;
         for (long long k = 0; k < k_steps; ++k) {
             u64 t = step_base + (u64)k;
             Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
+            // results of the speculative operations of the previous step
+            if (ins_pending) {
+                ins_pending = false;
+                if (ins_old == 0) c.inserts += 1;
+                else if (ins_old != e.board) {   // another state won the slot: find a place for ours now
+                    float4 r2;
+                    slot = table_find<true>(tab, mask, e.board, r2, c.inserts);
+                    c.dropped += (slot == kNoSlot);
+                }
+            }
+            if (upd_pending) {
+                upd_pending = false;
+                if (upd_old != upd_assumed) {
+                    c.lost += 1;
+                    if (upd_patch) q_set(row, upd_a, __uint_as_float(upd_old));   // s' == s: see the winner's value
+                }
+            }
             int a = choose_action(row, x, eps_thresh);
+            u64 s_board = e.board;
             StepOut o;
             philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
             c.add(o);
             float4 row2 = row;
             u32 slot2 = slot;
-            if (o.valid || FLAVOUR == G2048_FLAVOUR_NOPENALTY) {  // an invalid ENV-P move leaves s' == s
-                slot2 = table_find<true>(tab, mask, e.board, row2, ins);
-                c.dropped += (slot2 == kNoSlot);
-            }
+            const bool same = (e.board == s_board);   // an invalid move leaves s' == s
+            if (!same) slot2 = table_find_spec(tab, mask, e.board, row2, ins_pending, ins_old, c.dropped);
             if (slot != kNoSlot) {
-                float target = td_target(gamma, (float)o.reward, max4(row2), o.done);
-                float nq = q_update_atomic(&tab[slot].q[a], q_at(row, a), lr, target);
-                if (slot2 == slot) q_set(row2, a, nq);
+                float q = q_at(row, a);
+                float nq = td_apply(q, lr, td_target(gamma, (float)o.reward, max4(row2), o.done));
+                upd_assumed = __float_as_uint(q);
+                upd_old = atomicCAS(reinterpret_cast<u32*>(&tab[slot].q[a]), upd_assumed, __float_as_uint(nq));
+                upd_pending = true; upd_patch = same; upd_a = a;
+                if (same) q_set(row2, a, nq);
             }
             row = row2;
             slot = slot2;
             if (o.done) {
+                if (ins_pending) {   // the terminal state's insert must land before the env moves on
+                    ins_pending = false;
+                    if (ins_old == 0) c.inserts += 1;
+                    else if (ins_old != e.board) { float4 r2; table_find<true>(tab, mask, e.board, r2, c.inserts); }
+                }
                 philox_autoreset(e, seed, id, t);
-                slot = table_find<true>(tab, mask, e.board, row, ins);
+                slot = table_find<true>(tab, mask, e.board, row, c.inserts);
                 c.dropped += (slot == kNoSlot);
+                if (upd_pending) upd_patch = false;
             }
         }
+        if (ins_pending) {
+            if (ins_old == 0) c.inserts += 1;
+            else if (ins_old != e.board) { float4 r2; table_find<true>(tab, mask, e.board, r2, c.inserts); }
+        }
+        if (upd_pending && upd_old != upd_assumed) c.lost += 1;
         boards[i] = e.board;
         if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
         if (score) score[i] = e.score;
-        c.inserts += ins;
     }
     flush_counters(c, counters);
 }
@@ -327,16 +372,15 @@ k_qlearn_phase_a(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
         env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
         u64 id = id_base + (u64)i;
         float4 row, row2;
-        u32 ins = 0;
         u64 s_key = e.board;
-        u32 slot = table_find<true>(tab, mask, s_key, row, ins);
+        u32 slot = table_find<true>(tab, mask, s_key, row, c.inserts);
         c.dropped += (slot == kNoSlot);
         Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
         int a = choose_action(row, x, eps_thresh);
         StepOut o;
         philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
         c.add(o);
-        u32 slot2 = table_find<true>(tab, mask, e.board, row2, ins);
+        u32 slot2 = table_find<true>(tab, mask, e.board, row2, c.inserts);
         c.dropped += (slot2 == kNoSlot);
         float target = td_target(gamma, (float)o.reward, max4(row2), o.done);
         if (sortkey) sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)a);
@@ -348,7 +392,6 @@ k_qlearn_phase_a(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
         boards[i] = e.board;
         if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
         if (score) score[i] = e.score;
-        c.inserts += ins;
     }
     flush_counters(c, counters);
 }

@@ -384,6 +384,27 @@ __device__ __forceinline__ u32 table_find(Slot* tab, u64 mask, u64 key, float4& 
     q = make_float4(0.f, 0.f, 0.f, 0.f);
     return kNoSlot;
 }
+// Speculative find-or-insert for the fused rollout: probe with plain loads; an empty slot is claimed with an
+// atomicCAS whose result (ins_old) the caller inspects one step later -- the row of a new state is zero wherever
+// it finally lands, only the slot index may need a re-probe (ins_old neither 0 nor key).
+__device__ __forceinline__ u32 table_find_spec(Slot* tab, u64 mask, u64 key, float4& q, bool& ins_pending, u64& ins_old,
+                                               u32& dropped) {
+    u64 h = mix64(key) & mask;
+    for (int p = 0; p < kMaxProbe; ++p, h = (h + 1) & mask) {
+        u64 k;
+        load_slot(tab + h, k, q);
+        if (k == key) return (u32)h;
+        if (k == 0) {
+            ins_old = atomicCAS(&tab[h].key, 0ull, key);
+            ins_pending = true;
+            q = make_float4(0.f, 0.f, 0.f, 0.f);
+            return (u32)h;
+        }
+    }
+    dropped += 1;
+    q = make_float4(0.f, 0.f, 0.f, 0.f);
+    return kNoSlot;
+}
 __device__ __forceinline__ float q_at(const float4& q, int a) { return a == 0 ? q.x : a == 1 ? q.y : a == 2 ? q.z : q.w; }
 __device__ __forceinline__ void q_set(float4& q, int a, float v) {
     if (a == 0) q.x = v; else if (a == 1) q.y = v; else if (a == 2) q.z = v; else q.w = v;
@@ -428,7 +449,7 @@ __device__ __forceinline__ float q_update_atomic(float* addr, float guess, float
 // Per-thread partial sums (32-bit where a launch cannot overflow them), reduced per warp and added to the
 // caller's int64 counters with one atomic per warp and counter.
 struct Counters {
-    u32 steps = 0, valid = 0, episodes = 0, inserts = 0, dropped = 0;
+    u32 steps = 0, valid = 0, episodes = 0, inserts = 0, dropped = 0, lost = 0;
     int maxlvl = 0;
     long long score = 0, reward_fx = 0;
     __device__ __forceinline__ void add(const StepOut& o) {
@@ -444,14 +465,14 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 }
 __device__ __forceinline__ void flush_counters(const Counters& c, long long* out) {
     if (!out) return;
-    long long v[7] = {c.steps, c.valid, c.episodes, c.score, c.reward_fx, c.inserts, c.dropped};
-    const int idx[7] = {G2048_C_STEPS, G2048_C_VALID, G2048_C_EPISODES, G2048_C_SCORE, G2048_C_REWARD_FX,
-                        G2048_C_INSERTS, G2048_C_DROPPED};
+    long long v[8] = {c.steps, c.valid, c.episodes, c.score, c.reward_fx, c.inserts, c.dropped, c.lost};
+    const int idx[8] = {G2048_C_STEPS, G2048_C_VALID, G2048_C_EPISODES, G2048_C_SCORE, G2048_C_REWARD_FX,
+                        G2048_C_INSERTS, G2048_C_DROPPED, G2048_C_LOST};
     int mx = c.maxlvl;
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, s));
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < 8; ++i) {
         long long s = warp_sum(v[i]);
         if ((threadIdx.x & 31) == 0 && s) atomicAdd((unsigned long long*)(out + idx[i]), (unsigned long long)s);
     }

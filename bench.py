@@ -258,7 +258,7 @@ def main():
         assert L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, SEED, 0, base, stream) == 0
         return b, a, s
 
-    counters = torch.zeros(8, dtype=torch.int64, device=dev)
+    counters = torch.zeros(9, dtype=torch.int64, device=dev)
 
     # ---- pre-warm: ramp clocks with random-policy rollouts (not counted) --------------------------------
     b, a, s = device_envs()
@@ -296,13 +296,14 @@ def main():
     achieved = n * k * ALGO_BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     table_stats = {"capacity_slots": cap, "table_GiB": cap * 32 / 2**30, "states": int(c[6]),
-                   "load_factor_end": int(c[6]) / cap, "dropped": int(c[7]),
+                   "load_factor_end": int(c[6]) / cap, "dropped": int(c[7]), "lost_updates": int(c[8]),
+                   "lost_update_fraction": int(c[8]) / max(int(c[0]), 1),
                    "new_state_fraction": int(c[6]) / max(int(c[0]), 1)}
 
     # ---- arm 2: end to end through the host-buffer C-ABI call (pinned host memory) --------------------------
     assert L.g2048_ctx_qtable_clear(ctx) == 0
     (hb, ha, hs), pins = fresh_host_envs(L, ctx, n, base, pinned=True)
-    hc = np.zeros(8, np.int64)
+    hc = np.zeros(9, np.int64)
 
     def e2e_step(i):
         rc = L.g2048_ctx_rollout_qlearn(ctx, vp(hb), vp(ha), vp(hs), n, k, 0, LR, GAMMA, EPS, SEED, i * k, base, vp(hc))
@@ -372,7 +373,7 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
     b = torch.zeros(n, dtype=torch.int64, device=dev)
     a = torch.full((n,), 0x000000000000FF01, dtype=torch.int64, device=dev)
     s = torch.zeros(n, dtype=torch.int32, device=dev)
-    cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(9, dtype=torch.int64, device=dev)
     L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, SEED, 0, base, stream)
     # (a) fused random-policy rollout, 64 steps per launch
     for flavour, name in ((0, "penalty"), (1, "nopenalty")):

@@ -73,7 +73,8 @@
 #define G2048_C_REWARD_FX 5  /* sum of trunc(reward * 2^20): order-independent checksum of the rewards */
 #define G2048_C_INSERTS 6    /* new Q-table states */
 #define G2048_C_DROPPED 7    /* lookups that hit the probe limit (table too full) */
-#define G2048_N_COUNTERS 8
+#define G2048_C_LOST 8       /* fused rollout: updates skipped because another env changed the same Q value first */
+#define G2048_N_COUNTERS 9
 
 /* Q-learning modes */
 #define G2048_MODE_ATOMIC 0         /* q <- q + lr (target - q) as an atomic CAS loop (order among duplicates unspecified) */

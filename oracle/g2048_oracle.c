@@ -695,8 +695,9 @@ ORC_API void orc_q_apply_targets_f32(qtab_t *t, const uint64_t *keys, const uint
 /* counters: [0] env steps, [1] valid moves, [2] finished episodes, [3] sum of
  * move scores, [4] max level seen, [5] sum of trunc(reward * 2^20) (an
  * order-independent integer checksum of the float64 rewards), [6] table
- * inserts, [7] dropped inserts (table full). */
-enum { C_STEPS, C_VALID, C_EPISODES, C_SCORE, C_MAXLVL, C_REWARD_FX, C_INSERTS, C_DROPPED, C_N };
+ * inserts, [7] dropped inserts (table full), [8] lost updates (always 0 here:
+ * the sequential oracle never races). */
+enum { C_STEPS, C_VALID, C_EPISODES, C_SCORE, C_MAXLVL, C_REWARD_FX, C_INSERTS, C_DROPPED, C_LOST, C_N };
 static void count_step(int64_t *c, const out_t *o) {
     c[C_STEPS] += 1;
     c[C_VALID] += (o->flags & FLAG_VALID) != 0;

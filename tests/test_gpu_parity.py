@@ -149,7 +149,7 @@ def test_rollout_random_matches_oracle(L, ctx, flavour, n, k):
     seed, base, t0 = 99 + n, 12345, 7
     gb, ga, gs = fresh_envs(n, seed, 0, base)
     cb, ca, cs = gb.copy(), ga.copy(), gs.copy()
-    gc = np.zeros(8, np.int64)
+    gc = np.zeros(9, np.int64)
     ok(L, L.g2048_ctx_rollout_random(ctx, vp(gb), vp(ga), vp(gs), n, k, flavour, seed, t0, base, vp(gc)))
     cc = oracle.rollout_random(cb, ca, cs, k, flavour, seed, t0, base, threads=8)
     assert np.array_equal(gb, cb) and np.array_equal(gs, cs)
@@ -163,12 +163,12 @@ def test_rollout_random_is_sharding_invariant_at_1M_envs(L, ctx):
     """BASELINE config 3 size: 2^20 envs; one launch == two half-size launches with shifted env ids."""
     n, k, seed = 1 << 20, 48, 0x2048
     b, a, s = fresh_envs(n, seed)
-    b1, a1, s1, c1 = b.copy(), a.copy(), s.copy(), np.zeros(8, np.int64)
+    b1, a1, s1, c1 = b.copy(), a.copy(), s.copy(), np.zeros(9, np.int64)
     ok(L, L.g2048_ctx_rollout_random(ctx, vp(b1), vp(a1), vp(s1), n, k, 0, seed, 0, 0, vp(c1)))
     h = n // 2
-    c2 = np.zeros(8, np.int64)
+    c2 = np.zeros(9, np.int64)
     for lo in (0, h):
-        bb, aa, ss, cc = b[lo:lo + h].copy(), a[lo:lo + h].copy(), s[lo:lo + h].copy(), np.zeros(8, np.int64)
+        bb, aa, ss, cc = b[lo:lo + h].copy(), a[lo:lo + h].copy(), s[lo:lo + h].copy(), np.zeros(9, np.int64)
         ok(L, L.g2048_ctx_rollout_random(ctx, vp(bb), vp(aa), vp(ss), h, k, 0, seed, 0, lo, vp(cc)))
         assert np.array_equal(bb, b1[lo:lo + h]) and np.array_equal(aa, a1[lo:lo + h]) and np.array_equal(ss, s1[lo:lo + h])
         c2 += cc
@@ -309,7 +309,7 @@ def test_rollout_qlearn_single_env_is_the_reference_order(L, ctx):
         ok(L, L.g2048_ctx_qtable_clear(ctx))
         gb, ga, gs = fresh_envs(1, seed, 0, base)
         cb, ca, cs = gb.copy(), ga.copy(), gs.copy()
-        gc = np.zeros(8, np.int64)
+        gc = np.zeros(9, np.int64)
         tab = oracle.QTable(1 << 15, f32=True)
         for part in range(2):   # two launches: the carried state must survive the boundary
             ok(L, L.g2048_ctx_rollout_qlearn(ctx, vp(gb), vp(ga), vp(gs), 1, k, flavour, 0.1, 0.99, eps, seed, part * k,
@@ -332,7 +332,7 @@ def test_rollout_qlearn_1M_envs_properties(L, ctx):
     assert big, L.g2048_last_error()
     try:
         b, a, s = fresh_envs(n, seed)
-        c = np.zeros(8, np.int64)
+        c = np.zeros(9, np.int64)
         ok(L, L.g2048_ctx_rollout_qlearn(big, vp(b), vp(a), vp(s), n, k, 0, 0.1, 0.99, 0.1, seed, 0, 0, vp(c)))
         assert c[0] == n * k and c[7] == 0
         size = L.g2048_ctx_qtable_size(big)
