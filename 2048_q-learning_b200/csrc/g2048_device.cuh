@@ -365,6 +365,9 @@ __device__ __forceinline__ void load_slot(const Slot* s, u64& key, float4& q) {
     q.x = __uint_as_float((u32)q01); q.y = __uint_as_float((u32)(q01 >> 32));
     q.z = __uint_as_float((u32)q23); q.w = __uint_as_float((u32)(q23 >> 32));
 }
+// Linear probing by single 32-byte slots.  (A two-slot 64-byte bucket loaded as a pair was measured SLOWER --
+// 10.7 vs 14.2 G steps/s: what saturates is the number of L2-miss sector requests, ~36 G/s on B200 whatever the
+// fetch granularity, tools/membench.cu -- so every extra sector costs, even an adjacent one.)
 // defaultdict semantics (main.py:16): reading a state creates its zero row.  Returns the slot index
 // (kNoSlot if the probe limit is hit: the state is then treated as a zero row and not updated).
 template <bool INSERT>
@@ -384,26 +387,24 @@ __device__ __forceinline__ u32 table_find(Slot* tab, u64 mask, u64 key, float4& 
     q = make_float4(0.f, 0.f, 0.f, 0.f);
     return kNoSlot;
 }
-// Speculative find-or-insert for the fused rollout: probe with plain loads; an empty slot is claimed with an
-// atomicCAS whose result (ins_old) the caller inspects one step later -- the row of a new state is zero wherever
-// it finally lands, only the slot index may need a re-probe (ins_old neither 0 nor key).
+// Speculative find-or-insert for the fused rollout: probe with plain loads; an empty slot is claimed with ONE
+// atomicCAS (issued after the probe loop, so its destination register is not touched again) whose result
+// (ins_old) the caller inspects one step later -- the row of a new state is zero wherever it finally lands, only
+// the slot index may need a re-probe (ins_old neither 0 nor key).
 __device__ __forceinline__ u32 table_find_spec(Slot* tab, u64 mask, u64 key, float4& q, bool& ins_pending, u64& ins_old,
                                                u32& dropped) {
-    u64 h = mix64(key) & mask;
-    for (int p = 0; p < kMaxProbe; ++p, h = (h + 1) & mask) {
-        u64 k;
+    u64 h = mix64(key) & mask, k = 1;
+    int p = 0;
+    for (; p < kMaxProbe; ++p, h = (h + 1) & mask) {
         load_slot(tab + h, k, q);
-        if (k == key) return (u32)h;
-        if (k == 0) {
-            ins_old = atomicCAS(&tab[h].key, 0ull, key);
-            ins_pending = true;
-            q = make_float4(0.f, 0.f, 0.f, 0.f);
-            return (u32)h;
-        }
+        if (k == key || k == 0) break;
     }
-    dropped += 1;
+    if (k == key) return (u32)h;
     q = make_float4(0.f, 0.f, 0.f, 0.f);
-    return kNoSlot;
+    if (p == kMaxProbe) { dropped += 1; return kNoSlot; }
+    ins_old = atomicCAS(&tab[h].key, 0ull, key);
+    ins_pending = true;
+    return (u32)h;
 }
 __device__ __forceinline__ float q_at(const float4& q, int a) { return a == 0 ? q.x : a == 1 ? q.y : a == 2 ? q.z : q.w; }
 __device__ __forceinline__ void q_set(float4& q, int a, float v) {

@@ -31,6 +31,7 @@ template<int ILP> __global__ void k(u64* buf, u64 nslots, int iters, int mode, u
 }
 int main(int argc,char**argv){
   double gib = argc>1? atof(argv[1]) : 8.0;
+  if(argc>2){ size_t g=atoi(argv[2]); cudaError_t e=cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity,g); size_t got=0; cudaDeviceGetLimit(&got,cudaLimitMaxL2FetchGranularity); printf("set L2 fetch granularity %zu -> %s, now %zu\n",g,cudaGetErrorString(e),got);} else { size_t got=0; cudaDeviceGetLimit(&got,cudaLimitMaxL2FetchGranularity); printf("default L2 fetch granularity %zu\n",got);}
   u64 nslots = 1; while((nslots*2)*32 <= (u64)(gib*(1ull<<30))) nslots*=2;
   u64* buf; cudaMalloc(&buf, nslots*32); u64* out; cudaMalloc(&out,8);
   cudaEvent_t e0,e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
