@@ -217,8 +217,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU)
+    ap.add_argument("--eps", type=float, default=EPS, help="fixed exploration rate (BASELINE config 3 quotes 0.1 and 0.95)")
     ap.add_argument("--no-extras", action="store_true", help="skip the explanatory side measurements")
     args = ap.parse_args()
+    global EPS
+    EPS = args.eps
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

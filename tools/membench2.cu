@@ -14,12 +14,14 @@ template<int V> __device__ __forceinline__ u64 ld32(const u64* p){
   if(V==4){ asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];":"=l"(a),"=l"(b):"l"(p)); asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];":"=l"(c),"=l"(d):"l"(p+2)); }
   if(V==5){ asm volatile("ld.global.cv.v2.u64 {%0,%1}, [%2];":"=l"(a),"=l"(b):"l"(p)); asm volatile("ld.global.cv.v2.u64 {%0,%1}, [%2];":"=l"(c),"=l"(d):"l"(p+2)); }
   if(V==6){ asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];":"=l"(a),"=l"(b):"l"(p)); }
+  if(V==8){ asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];":"=l"(a),"=l"(b),"=l"(c),"=l"(d):"l"(p)); u64 off = 4 + 2*((a^b^c^d)&3); u64 e,f; asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];":"=l"(e),"=l"(f):"l"(p+off)); a^=e; b^=f; }
+  if(V==9){ asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];":"=l"(a),"=l"(b),"=l"(c),"=l"(d):"l"(p)); u64 e,f; asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];":"=l"(e),"=l"(f):"l"(p+4)); a^=e; b^=f; }
   if(V==7){ asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];":"=l"(a),"=l"(b):"l"(p)); asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];":"=l"(c),"=l"(d):"l"(p+2)); }
   return a^b^c^d;
 }
 template<int V> __global__ void k(const u64* buf, u64 nslots, int iters, u64* out){
   u64 tid = blockIdx.x*(u64)blockDim.x+threadIdx.x, acc = tid*0x9E3779B97F4A7C15ull+1, sum=0;
-  for(int it=0; it<iters; ++it){ u64 s = mix(acc) & (nslots-1); u64 v = ld32<V>(buf+4*s); acc = acc*6364136223846793005ull + v + 1442695040888963407ull; sum+=v; }
+  for(int it=0; it<iters; ++it){ u64 s = mix(acc) & (nslots-1); if(V>=8) s &= ~3ull; u64 v = ld32<V>(buf+4*s); acc = acc*6364136223846793005ull + v + 1442695040888963407ull; sum+=v; }
   if(sum==0x123456789ull) out[0]=sum;
 }
 template<int V> void run(const u64* buf,u64 nslots,u64* out,int sms,const char* name){
@@ -42,5 +44,7 @@ int main(int argc,char**argv){
   run<5>(buf,nslots,out,sms,"2 x ld.global.cv.v2.u64");
   run<6>(buf,nslots,out,sms,"ld.global.cg.v2.u64 (16 B)");
   run<7>(buf,nslots,out,sms,"2 x ld.relaxed.gpu.global.v2.u64");
+  run<8>(buf,nslots,out,sms,"keys sector, then DEPENDENT 16 B from sector 1-3 of the same line");
+  run<9>(buf,nslots,out,sms,"keys sector + independent 16 B from sector 1 of the same line");
   return 0;
 }
