@@ -211,6 +211,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    global EPS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
@@ -219,8 +220,9 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU)
     ap.add_argument("--eps", type=float, default=EPS, help="fixed exploration rate (BASELINE config 3 quotes 0.1 and 0.95)")
     ap.add_argument("--no-extras", action="store_true", help="skip the explanatory side measurements")
+    ap.add_argument("--exchange", action="store_true",
+                    help="also time the synchronous mode with the cross-GPU record exchange (dist.ShardedQLearning)")
     args = ap.parse_args()
-    global EPS
     EPS = args.eps
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -343,6 +345,10 @@ def main():
         L.g2048_host_free(p)
 
     extras = {}
+    if args.exchange:
+        sync = sync_exchange_measurement(torch, dist, g2048, dev, rank, world, min(n, 1 << 20), max_over_ranks, barrier)
+        if rank == 0:
+            extras["synchronous_exchange"] = sync
     if not args.no_extras and rank == 0:
         extras = side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak)
         rnd = random_access_peak()
@@ -383,6 +389,37 @@ def main():
     L.g2048_ctx_destroy(ctx)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_ranks, barrier, steps=24):
+    """Synchronous data-parallel Q-learning: every step all ranks all_gather their (state, action, target) records
+    over NCCL and apply the whole list deterministically, so the replicas stay identical."""
+    from g2048 import dist as gdist
+    env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
+    agent = g2048.BatchedQLearningAgent(1000, 4, LR, GAMMA, EPS, capacity=1 << 28, device=dev.index, seed=SEED)
+    env.reset()
+    sh = gdist.ShardedQLearning(gdist.TorchEngine(env, agent), n * world)
+    for _ in range(3):
+        sh.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sh.step()
+    e1.record()
+    barrier()
+    dt = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+    keys, rows = agent.export()
+    digest = float(np.abs(rows).sum())
+    digests = [digest]
+    if world > 1:
+        t = torch.tensor([digest, float(len(keys))], dtype=torch.float64, device=dev)
+        all_t = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(all_t, t)
+        digests = [x.tolist() for x in all_t]
+    return {"env_steps_per_sec": world * n * steps / dt, "ms_per_step": dt / steps * 1e3, "envs_per_gpu": n,
+            "records_gathered_per_step": world * n, "bytes_received_per_rank_per_step": world * n * 13,
+            "replica_digests": digests, "mode": "deterministic apply of all ranks' records on every replica"}
 
 
 def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
@@ -443,6 +480,34 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
         out[f"standalone_q_update_{name}"] = {"updates_per_sec": m / dt, "achieved_GBps_at_40B": gbs,
                                               "frac_of_hbm_peak": gbs / peak, "batch": m, "table_states": pool.numel()}
     L.g2048_ctx_qtable_clear(ctx)
+    # (d) BASELINE config 5, env side only: 65,536 nopenalty envs feeding a DQN -- per step: select_action on
+    # (placeholder) network outputs with the legal mask, env step, one-hot encode of the new boards
+    m5 = 65536
+    b5 = torch.zeros(m5, dtype=torch.int64, device=dev)
+    s5 = torch.zeros(m5, dtype=torch.int32, device=dev)
+    L.g2048_env_reset(b5.data_ptr(), s5.data_ptr(), None, None, m5, SEED, 0, base, stream)
+    qv = torch.randn((m5, 4), dtype=torch.float32, device=dev)
+    a5 = torch.zeros(m5, dtype=torch.uint8, device=dev)
+    f5 = torch.zeros(m5, dtype=torch.uint8, device=dev)
+    lm5 = torch.full((m5,), 15, dtype=torch.uint8, device=dev)
+    r5 = torch.zeros(m5, dtype=torch.float32, device=dev)
+    step_no = [0]
+    for dt_name, code, width in (("f32", 0, 4), ("bf16", 1, 2)):
+        enc = torch.empty((m5, 16, 4, 4), dtype=torch.float32 if code == 0 else torch.bfloat16, device=dev)
+
+        def feed():
+            t = step_no[0]
+            L.g2048_select_action(qv.data_ptr(), lm5.data_ptr(), a5.data_ptr(), m5, 0.1, SEED, t, base, stream)
+            L.g2048_env_step(b5.data_ptr(), None, s5.data_ptr(), a5.data_ptr(), None, None, r5.data_ptr(), f5.data_ptr(),
+                             None, None, m5, 1, SEED, t, base, stream)
+            torch.bitwise_right_shift(f5, 4, out=lm5)
+            L.g2048_env_reset(b5.data_ptr(), s5.data_ptr(), f5.data_ptr(), None, m5, SEED, t + 1, base, stream) if False else None
+            L.g2048_encode_onehot(b5.data_ptr(), enc.data_ptr(), m5, code, stream)
+            step_no[0] += 1
+        dt = timed(feed, 50)
+        out[f"dqn_feed_65536_envs_{dt_name}"] = {"env_steps_per_sec": m5 / dt, "us_per_step": dt * 1e6,
+                                                "onehot_GBps": m5 * 256 * width / dt / 1e9,
+                                                "kernels_per_step": "select_action + env_step(nopenalty) + encode_onehot"}
     return out
 
 
