@@ -15,6 +15,9 @@ def __getattr__(name):  # the batched classes need torch: import lazily
     if name == "BatchedQLearningAgent":
         from . import agent
         return agent.BatchedQLearningAgent
+    if name in ("BatchedDQNAgent", "DQNModel", "dqn_step", "terminal_bonus"):
+        from . import dqn
+        return getattr(dqn, name)
     if name in ("ShardedQLearning", "shard_range"):
         from . import dist
         return getattr(dist, name)

@@ -1,0 +1,217 @@
+"""DQN agent fed by the batched GPU env (SURVEY.md section 8f "next" #1, BASELINE config 5).
+
+PyTorch restatement of Deep_QLearning/main_dir/Dqn8TestNOPERCNN.py: the network stays on PyTorch/cuBLAS/cuDNN
+(north_star); what is B200-native here is everything around it -- boards stay packed (8 bytes) in the replay
+memory and are one-hot encoded on the fly by `k_onehot_*`, actions for all envs come from `k_select_action`
+(act / act_ripetitive with the legal-move mask the env step already produced), and transitions never leave HBM.
+
+Reference pieces mirrored
+  DQNModel            :202-246  three blocks of four parallel Conv2D(512, k in 1..4, 'same') + concat + ReLU,
+                                Flatten, Dense 1024 ReLU, Dropout 0.5, Dense 4; Adam 5e-5; 197,204,996 parameters.
+                                Keras reads Input(16,4,4) channels-last: H = level, W = row, C = col.
+  DQNAgent            :248-400  same constructor arguments; encode_state :271-277, act :312-324,
+                                act_ripetitive :326-336, update_epsilon :341-343, remember, replay :351-390
+                                (loss = mean over B x 4 of (target - q)^2 with target == q except at the taken
+                                action; terminal target = reward), update_target_model :338-339.
+Deliberate differences (documented, batched form): the replay memory stores next_state explicitly instead of
+keras-rl's "next stored observation"; the consecutive-duplicate filter of `remember` (:283-297) is a
+single-stream heuristic and is not applied to the batch; prioritisation is alpha = 0 (uniform) as in the reference.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check
+from .env import BatchedGame2048Env, _ptr, _stream
+
+
+class ConvBlock(nn.Module):
+    """conv_block (:231-246): four parallel 'same' convolutions with kernel sizes 1..4, concatenated, ReLU."""
+
+    def __init__(self, c_in: int, c_out: int):
+        super().__init__()
+        d = c_out // 4
+        self.convs = nn.ModuleList([nn.Conv2d(c_in, d, kernel_size=k, padding="same") for k in (1, 2, 3, 4)])
+
+    def forward(self, x):
+        return F.relu(torch.cat([c(x) for c in self.convs], dim=1))
+
+
+class DQNModel(nn.Module):
+    """_build_model (:209-229).  Input: (N, 16, 4, 4) one-hot [batch, level, row, col] as produced by encode_state."""
+
+    def __init__(self, action_space: int = 4, width: int = 2048, hidden: int = 1024):
+        super().__init__()
+        self.blocks = nn.Sequential(ConvBlock(4, width), ConvBlock(width, width), ConvBlock(width, width))
+        self.fc1 = nn.Linear(16 * 4 * width, hidden)
+        self.drop = nn.Dropout(0.5)
+        self.fc2 = nn.Linear(hidden, action_space)
+
+    def forward(self, x):
+        # Keras channels-last reading of (16,4,4): H = level, W = row, C = col  ->  torch (N, C=col, H=level, W=row)
+        x = x.permute(0, 3, 1, 2)
+        x = self.blocks(x)
+        x = x.permute(0, 2, 3, 1).flatten(1)          # Keras Flatten order (h, w, c)
+        return self.fc2(self.drop(F.relu(self.fc1(x))))
+
+
+class BatchedDQNAgent:
+    """DQNAgent (:248-400) for N envs at once."""
+
+    def __init__(self, state_shape=(16, 4, 4), action_space=4, gamma=0.99, decay_episodes=200, epsilon=0.9,
+                 epsilon_min=0.001, epsilon_decay=0.9999, batch_size=64, memory_size=50000, alpha=0.0, beta=1.0,
+                 beta_increment=1e-5, *, device=0, width=2048, hidden=1024, dtype=torch.float32, seed=0x2048,
+                 learning_rate=5e-5):
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.G2048Error("BatchedDQNAgent needs a CUDA device (no CPU fallback)")
+        _lib.init(dev.index or 0)
+        self.lib, self.device, self.dtype, self.seed = _lib.lib(), dev, dtype, int(seed)
+        self.state_shape, self.action_space, self.gamma = state_shape, action_space, gamma
+        self.epsilon = self.epsilon_start = epsilon
+        self.epsilon_min, self.epsilon_decay, self.decay_episodes = epsilon_min, epsilon_decay, decay_episodes
+        self.batch_size, self.memory_size, self.alpha, self.beta, self.beta_increment = (batch_size, memory_size, alpha,
+                                                                                         beta, beta_increment)
+        self.model = DQNModel(action_space, width, hidden).to(dev, dtype)
+        self.target_model = DQNModel(action_space, width, hidden).to(dev, dtype)
+        self.update_target_model()
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=learning_rate)
+        self.step_counter = 0
+        self.loss_history: list[float] = []
+        # replay memory: packed boards, never one-hot (16 B per transition instead of 2 KB)
+        m = memory_size
+        self.mem_state = torch.zeros(m, dtype=torch.int64, device=dev)
+        self.mem_next = torch.zeros(m, dtype=torch.int64, device=dev)
+        self.mem_action = torch.zeros(m, dtype=torch.int64, device=dev)
+        self.mem_reward = torch.zeros(m, dtype=torch.float32, device=dev)
+        self.mem_done = torch.zeros(m, dtype=torch.bool, device=dev)
+        self.nb_entries, self._head = 0, 0
+        self._gen = torch.Generator(device=dev)
+        self._gen.manual_seed(self.seed)
+
+    # ---- reference API ---------------------------------------------------------------------------------------
+    def encode_state(self, boards: torch.Tensor) -> torch.Tensor:
+        """encode_state (:271-277) on packed boards: (N, 16, 4, 4) one-hot in the model's dtype."""
+        code = {torch.float32: 0, torch.bfloat16: 1}[self.dtype]
+        n = boards.numel()
+        out = torch.empty((n, 16, 4, 4), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_encode_onehot(_ptr(boards), _ptr(out), n, code, _stream()), "g2048_encode_onehot")
+        return out
+
+    def update_epsilon(self):
+        self.epsilon = max(self.epsilon_min, self.epsilon_start * (self.epsilon_decay ** self.step_counter))
+
+    @torch.no_grad()
+    def q_values(self, boards: torch.Tensor) -> torch.Tensor:
+        self.model.eval()
+        return self.model(self.encode_state(boards)).float().contiguous()
+
+    def _select(self, boards, legal_mask, env_id_base):
+        self.update_epsilon()
+        self.step_counter += 1
+        q = self.q_values(boards)
+        n = boards.numel()
+        actions = torch.empty(n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_select_action(_ptr(q), _ptr(legal_mask), _ptr(actions), n, float(self.epsilon),
+                                               self.seed, self.step_counter, env_id_base, _stream()),
+                  "g2048_select_action")
+        return actions
+
+    def act(self, boards: torch.Tensor, env_id_base: int = 0) -> torch.Tensor:
+        """act (:312-324): epsilon-greedy over the four actions."""
+        return self._select(boards, None, env_id_base)
+
+    def act_ripetitive(self, boards: torch.Tensor, legal_mask: torch.Tensor, env_id_base: int = 0) -> torch.Tensor:
+        """act_ripetitive (:326-336): epsilon-greedy restricted to the legal moves (4-bit mask per env)."""
+        return self._select(boards, legal_mask.to(torch.uint8).contiguous(), env_id_base)
+
+    def remember(self, state, action, reward, done, next_state) -> bool:
+        """remember (:279-297) for a batch of transitions (packed boards), ring-buffer append."""
+        n = state.numel()
+        idx = (torch.arange(n, device=self.device) + self._head) % self.memory_size
+        self.mem_state[idx] = state
+        self.mem_next[idx] = next_state
+        self.mem_action[idx] = action.to(torch.int64)
+        self.mem_reward[idx] = reward.to(torch.float32)
+        self.mem_done[idx] = done.to(torch.bool)
+        self._head = (self._head + n) % self.memory_size
+        self.nb_entries = min(self.nb_entries + n, self.memory_size)
+        return True
+
+    def replay(self, episode=None):
+        """replay (:351-390): one Adam step on a uniformly sampled minibatch."""
+        if self.nb_entries < self.batch_size or self.epsilon >= 1:
+            return None
+        idx = torch.randint(0, self.nb_entries, (self.batch_size,), device=self.device, generator=self._gen)
+        actions, rewards, done = self.mem_action[idx], self.mem_reward[idx], self.mem_done[idx]
+        self.model.train()
+        self.target_model.eval()
+        q = self.model(self.encode_state(self.mem_state[idx])).float()
+        with torch.no_grad():
+            next_q = self.target_model(self.encode_state(self.mem_next[idx])).float()
+            target_a = torch.where(done, rewards, rewards + self.gamma * next_q.max(dim=1).values)   # :368-372
+            targets = q.detach().clone()
+            targets.scatter_(1, actions.unsqueeze(1), target_a.unsqueeze(1))
+        loss = torch.mean((targets - q) ** 2)                                                         # :376
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        self.optimizer.step()
+        self.loss_history.append(float(loss.detach()))
+        return self.loss_history[-1]
+
+    def update_target_model(self):
+        self.target_model.load_state_dict(self.model.state_dict())
+
+    def change_lr_function(self, reached_1024: bool = False):
+        """:299-310: lr <- max(lr * 0.98, 1e-6) whenever an episode ended with a 1024 tile."""
+        lr = self.optimizer.param_groups[0]["lr"]
+        if reached_1024:
+            lr = max(lr * 0.98, 1e-6)
+            for g in self.optimizer.param_groups:
+                g["lr"] = lr
+        return lr
+
+    def save_agent_state(self, path: str):
+        torch.save({"model": self.model.state_dict(), "target": self.target_model.state_dict(),
+                    "opt": self.optimizer.state_dict(), "step_counter": self.step_counter, "epsilon": self.epsilon,
+                    "memory": (self.mem_state, self.mem_next, self.mem_action, self.mem_reward, self.mem_done,
+                               self.nb_entries, self._head), "loss_history": self.loss_history}, path)
+
+    def load_agent_state(self, path: str):
+        blob = torch.load(path, map_location=self.device)
+        self.model.load_state_dict(blob["model"])
+        self.target_model.load_state_dict(blob["target"])
+        self.optimizer.load_state_dict(blob["opt"])
+        self.step_counter, self.epsilon, self.loss_history = blob["step_counter"], blob["epsilon"], blob["loss_history"]
+        (self.mem_state, self.mem_next, self.mem_action, self.mem_reward, self.mem_done, self.nb_entries,
+         self._head) = blob["memory"]
+
+
+def terminal_bonus(boards: torch.Tensor, done: torch.Tensor) -> torch.Tensor:
+    """The driver's terminal bonus (mainDQL_CNN_step2.py:202-213): +100 if the final board holds a 2048 tile or
+    more, +50 if it holds two tiles >= 1024, on packed boards."""
+    lv = torch.stack([(boards >> (4 * j)) & 15 for j in range(16)], dim=1)
+    top2 = lv.topk(2, dim=1).values
+    bonus = torch.where(top2[:, 0] >= 11, 100.0, torch.where((top2[:, 0] >= 10) & (top2[:, 1] >= 10), 50.0, 0.0))
+    return torch.where(done, bonus, torch.zeros_like(bonus))
+
+
+def dqn_step(env: BatchedGame2048Env, agent: BatchedDQNAgent, train: bool = True):
+    """One step of the driver loop mainDQL_CNN_step2.py:163-237 for all envs: legal-move mask, act_ripetitive,
+    env.step (nopenalty flavour; the commit of :237 is folded into the batched env), terminal bonus, remember,
+    and a reset of the finished games."""
+    state = env.boards.clone()
+    legal = env.legal_mask()
+    actions = agent.act_ripetitive(state, legal, env.env_id_base)
+    next_state, reward, done, _ = env.step(actions)
+    reward = reward.to(torch.float32) + terminal_bonus(next_state, done)
+    if train:
+        agent.remember(state, actions, reward, done, next_state.clone())
+    if bool(done.any()):
+        env.reset(mask=done)
+    return reward, done

@@ -69,6 +69,13 @@ def ncu_traffic():
         return None
 
 
+def ncu_dram_ops_per_step():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_random_ops_per_env_step"])
+    except Exception:
+        return None
+
+
 def random_access_peak():
     """Live measurement of what HBM gives random slot reads (tools/membench: dependent random 32-byte loads over
     8 GiB at 1024 threads/SM).  Every such miss moves a 128-byte line (profiles/r01_membench.txt)."""
@@ -353,14 +360,15 @@ def main():
         extras = side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak)
         rnd = random_access_peak()
         if rnd:
-            # line operations the fused kernel needs: ~1 line read per lookup that misses L2 + the write-back of the
-            # dirtied line; from the committed ncu capture: DRAM bytes per env step / 128
-            per_step = (traffic / (n * k) / 128.0) if traffic else None
+            # random DRAM operations the fused kernel needs per env step (committed ncu capture): line fills
+            # (read sectors / 4) + sector write-backs
+            per_step = ncu_dram_ops_per_step()
             extras["hbm_random_access"] = {
                 "measured_line_fetches_per_sec": rnd, "bytes_moved_per_random_access": 128,
                 "equivalent_GBps": rnd * 128 / 1e9, "frac_of_streaming_peak": rnd * 128 / 1e9 / peak,
-                "fused_kernel_dram_lines_per_env_step_ncu": per_step,
-                "fused_kernel_frac_of_random_access_peak": (value / world * per_step / rnd) if per_step else None,
+                "fused_kernel_dram_ops_per_env_step_ncu": per_step,
+                "fused_kernel_bound_env_steps_per_sec": (rnd / per_step) if per_step else None,
+                "fused_kernel_frac_of_random_access_bound": (value / world * per_step / rnd) if per_step else None,
                 "note": "a hash table in HBM is bounded by random line fetches, not by its algorithmic bytes"}
     if world > 1:
         dist.barrier()
@@ -491,6 +499,7 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
     f5 = torch.zeros(m5, dtype=torch.uint8, device=dev)
     lm5 = torch.full((m5,), 15, dtype=torch.uint8, device=dev)
     r5 = torch.zeros(m5, dtype=torch.float32, device=dev)
+    dm5 = torch.zeros(m5, dtype=torch.uint8, device=dev)
     step_no = [0]
     for dt_name, code, width in (("f32", 0, 4), ("bf16", 1, 2)):
         enc = torch.empty((m5, 16, 4, 4), dtype=torch.float32 if code == 0 else torch.bfloat16, device=dev)
@@ -501,13 +510,14 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
             L.g2048_env_step(b5.data_ptr(), None, s5.data_ptr(), a5.data_ptr(), None, None, r5.data_ptr(), f5.data_ptr(),
                              None, None, m5, 1, SEED, t, base, stream)
             torch.bitwise_right_shift(f5, 4, out=lm5)
-            L.g2048_env_reset(b5.data_ptr(), s5.data_ptr(), f5.data_ptr(), None, m5, SEED, t + 1, base, stream) if False else None
+            torch.bitwise_and(f5, 4, out=dm5)   # done envs start a new game
+            L.g2048_env_reset(b5.data_ptr(), s5.data_ptr(), dm5.data_ptr(), None, m5, SEED, t + 1, base, stream)
             L.g2048_encode_onehot(b5.data_ptr(), enc.data_ptr(), m5, code, stream)
             step_no[0] += 1
         dt = timed(feed, 50)
         out[f"dqn_feed_65536_envs_{dt_name}"] = {"env_steps_per_sec": m5 / dt, "us_per_step": dt * 1e6,
                                                 "onehot_GBps": m5 * 256 * width / dt / 1e9,
-                                                "kernels_per_step": "select_action + env_step(nopenalty) + encode_onehot"}
+                                                "kernels_per_step": "select_action + env_step(nopenalty) + masked reset + encode_onehot"}
     return out
 
 
