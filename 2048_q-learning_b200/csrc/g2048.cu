@@ -962,6 +962,8 @@ struct g2048_ctx {
     int64_t max_envs = 0;
     uint64_t capacity = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // chunked rollouts: copies of one chunk overlap the kernel of another
+    cudaEvent_t ev_start = nullptr, ev_done[3] = {nullptr, nullptr, nullptr};
     void* table = nullptr;
     // device staging, sized for max_envs
     u64 *boards = nullptr, *aux = nullptr, *keys2 = nullptr;
@@ -982,6 +984,11 @@ G2048_API g2048_ctx* g2048_ctx_create(int device, int64_t max_envs, uint64_t tab
     size_t m = (size_t)max_envs;
     c->scratch_bytes = scratch_bytes(max_envs);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int j = 0; ok && j < 3; ++j)
+        ok = cudaStreamCreateWithFlags(&c->pipe[j], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_done[j], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok &&
               cudaMalloc(&c->boards, m * 8) == cudaSuccess && cudaMalloc(&c->aux, m * 8) == cudaSuccess &&
               cudaMalloc(&c->keys2, m * 8) == cudaSuccess && cudaMalloc(&c->score, m * 4) == cudaSuccess &&
               cudaMalloc(&c->move_score, m * 4) == cudaSuccess && cudaMalloc(&c->bytes_a, m) == cudaSuccess &&
@@ -1011,6 +1018,11 @@ G2048_API void g2048_ctx_destroy(g2048_ctx* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (int j = 0; j < 3; ++j) {
+        if (c->pipe[j]) cudaStreamDestroy(c->pipe[j]);
+        if (c->ev_done[j]) cudaEventDestroy(c->ev_done[j]);
+    }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
     delete c;
 }
 G2048_API void* g2048_ctx_table(g2048_ctx* c) { return c ? c->table : nullptr; }
@@ -1100,20 +1112,37 @@ static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* s
                        uint64_t env_id_base, int64_t* counters, bool qlearn) {
     CTX_ENTER(qlearn);
     if (!boards) return fail(G2048_ERR_ARG, "rollout: boards is null");
-    H2D(c->boards, boards, n * 8);
-    H2D(c->aux, aux, n * 8);
-    H2D(c->score, score, n * 4);
     CK(cudaMemsetAsync(c->counters, 0, G2048_N_COUNTERS * sizeof(long long), st));
-    if (qlearn)
-        RC(g2048_rollout_qlearn((uint64_t*)c->boards, aux ? (uint64_t*)c->aux : nullptr, score ? c->score : nullptr,
-                                c->table, c->capacity, n, k_steps, flavour, lr, gamma, eps, seed, step_base, env_id_base,
-                                (int64_t*)c->counters, st));
-    else
-        RC(g2048_rollout_random((uint64_t*)c->boards, aux ? (uint64_t*)c->aux : nullptr, score ? c->score : nullptr, n,
-                                k_steps, flavour, seed, step_base, env_id_base, (int64_t*)c->counters, st));
-    D2H(boards, c->boards, n * 8);
-    D2H(aux, c->aux, n * 8);
-    D2H(score, c->score, n * 4);
+    // Large batches go through in chunks on three streams, so that the host<->device copies of one chunk overlap
+    // the kernel of another (PCIe is full duplex: H2D, D2H and compute all run at once).  Env ids are global, so
+    // the result does not depend on the chunking.
+    const int chunks = n >= (1 << 18) ? 4 : 1;
+    CK(cudaEventRecord(c->ev_start, st));
+    for (int j = 0; j < chunks; ++j) {
+        cudaStream_t ps = chunks == 1 ? st : c->pipe[j % 3];
+        int64_t lo = n * j / chunks, m = n * (j + 1) / chunks - lo;
+        if (chunks > 1) CK(cudaStreamWaitEvent(ps, c->ev_start, 0));
+        CK(cudaMemcpyAsync(c->boards + lo, boards + lo, (size_t)m * 8, cudaMemcpyHostToDevice, ps));
+        if (aux) CK(cudaMemcpyAsync(c->aux + lo, aux + lo, (size_t)m * 8, cudaMemcpyHostToDevice, ps));
+        if (score) CK(cudaMemcpyAsync(c->score + lo, score + lo, (size_t)m * 4, cudaMemcpyHostToDevice, ps));
+        uint64_t* db = (uint64_t*)c->boards + lo;
+        uint64_t* da = aux ? (uint64_t*)c->aux + lo : nullptr;
+        int32_t* ds = score ? c->score + lo : nullptr;
+        if (qlearn)
+            RC(g2048_rollout_qlearn(db, da, ds, c->table, c->capacity, m, k_steps, flavour, lr, gamma, eps, seed, step_base,
+                                    env_id_base + (uint64_t)lo, (int64_t*)c->counters, ps));
+        else
+            RC(g2048_rollout_random(db, da, ds, m, k_steps, flavour, seed, step_base, env_id_base + (uint64_t)lo,
+                                    (int64_t*)c->counters, ps));
+        CK(cudaMemcpyAsync(boards + lo, c->boards + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, ps));
+        if (aux) CK(cudaMemcpyAsync(aux + lo, c->aux + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, ps));
+        if (score) CK(cudaMemcpyAsync(score + lo, c->score + lo, (size_t)m * 4, cudaMemcpyDeviceToHost, ps));
+    }
+    if (chunks > 1)
+        for (int j = 0; j < 3; ++j) {
+            CK(cudaEventRecord(c->ev_done[j], c->pipe[j]));
+            CK(cudaStreamWaitEvent(st, c->ev_done[j], 0));
+        }
     D2H(counters, c->counters, G2048_N_COUNTERS * sizeof(long long));
     CK(cudaStreamSynchronize(st));
     return 0;

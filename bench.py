@@ -253,6 +253,8 @@ def main():
     n, k = args.envs, ENV_STEPS_PER_LAUNCH
     base = rank * n
     launches = args.steps + args.warmup
+    # the table must stay under ~0.45 load for the whole run (<= 2^31 slots): long runs take fewer steps per launch
+    k = int(max(1, min(k, 0.45 * (1 << 31) / (0.8 * n * launches))))
 
     # table: as many slots as keep the load factor under ~0.45 for one arm (<= 2^31 slots = 64 GiB)
     expected_inserts = 0.8 * n * k * launches
