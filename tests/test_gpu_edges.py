@@ -1,0 +1,146 @@
+"""Edge cases of the C ABI on the GPU: empty and ragged batches, optional (NULL) outputs, argument errors,
+huge env ids / step indices, a table that runs full, malformed replay input."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def L():
+    import g2048
+    g2048.init(0)
+    return g2048.lib()
+
+
+@pytest.fixture(scope="module")
+def ctx(L):
+    h = L.g2048_ctx_create(0, 1 << 16, 1 << 12)
+    assert h
+    yield h
+    L.g2048_ctx_destroy(h)
+
+
+def envs(n, seed=3, base=0):
+    b = np.zeros(n, np.uint64)
+    oracle.env_reset(b, None, None, None, seed=seed, env_id_base=base)
+    return b, np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+
+
+def test_empty_batches_are_no_ops(L, ctx):
+    z8, z4, z1 = np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.uint8)
+    c = np.zeros(9, np.int64)
+    assert L.g2048_ctx_env_step(ctx, vp(z8), vp(z8), vp(z4), vp(z1), None, None, None, None, None, 0, 0, 1, 2, 3) == 0
+    assert L.g2048_ctx_env_reset(ctx, vp(z8), None, None, None, 0, 1, 2, 3) == 0
+    assert L.g2048_ctx_rollout_random(ctx, vp(z8), vp(z8), vp(z4), 0, 10, 0, 1, 2, 3, vp(c)) == 0
+    assert L.g2048_ctx_rollout_qlearn(ctx, vp(z8), vp(z8), vp(z4), 0, 10, 0, 0.1, 0.9, 0.1, 1, 2, 3, vp(c)) == 0
+    assert L.g2048_ctx_qtable_update(ctx, vp(z8), vp(z1), vp(np.zeros(0, np.float32)), vp(z8), vp(z1), 0, 0.1, 0.9, 1) == 0
+    assert not c.any()
+    b, a, s = envs(5)
+    b0 = b.copy()
+    assert L.g2048_ctx_rollout_random(ctx, vp(b), vp(a), vp(s), 5, 0, 0, 1, 2, 3, vp(c)) == 0   # zero steps
+    assert np.array_equal(b, b0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 255, 1025, 16385, 40001])
+@pytest.mark.parametrize("flavour", [0, 1])
+def test_ragged_batch_sizes(L, ctx, n, flavour):
+    """Sizes that are not multiples of the warp / block / grid, on both LUT paths (global below 16,384 envs,
+    shared memory above), with huge env ids and step indices (Philox counter words 1 and 3)."""
+    seed, base, t0, k = 5, (1 << 40) + 12345, (1 << 33) + 7, 37
+    b, a, s = envs(n, seed, base)
+    cb, ca, cs = b.copy(), a.copy(), s.copy()
+    c = np.zeros(9, np.int64)
+    assert L.g2048_ctx_rollout_random(ctx, vp(b), vp(a), vp(s), n, k, flavour, seed, t0, base, vp(c)) == 0
+    cc = oracle.rollout_random(cb, ca, cs, k, flavour, seed, t0, base, threads=4)
+    assert np.array_equal(b, cb) and np.array_equal(s, cs) and np.array_equal(c, cc)
+    # one single step, every output
+    actions = (np.arange(n) % 4).astype(np.uint8)
+    r, f, m, ms = np.zeros(n), np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int32)
+    assert L.g2048_ctx_env_step(ctx, vp(b), vp(a), vp(s), vp(actions), None, vp(r), vp(f), vp(m), vp(ms), n, flavour,
+                                seed, t0 + k, base) == 0
+    wr, wf, wm, wms = oracle.env_step(cb, ca, cs, actions, None, flavour, seed, t0 + k, base)
+    assert np.array_equal(b, cb) and np.array_equal(f, wf) and np.array_equal(m, wm) and np.array_equal(ms, wms)
+    assert np.array_equal(r.view(np.uint64), wr.view(np.uint64))
+
+
+def test_optional_outputs_may_be_null(L, ctx):
+    n = 1000
+    b, a, s = envs(n)
+    cb, ca, cs = b.copy(), a.copy(), s.copy()
+    actions = np.full(n, 2, np.uint8)
+    assert L.g2048_ctx_env_step(ctx, vp(b), None, None, vp(actions), None, None, None, None, None, n, 1, 9, 0, 0) == 0
+    oracle.env_step(cb, None, None, actions, None, 1, 9, 0, 0)
+    assert np.array_equal(b, cb)
+    assert L.g2048_ctx_rollout_random(ctx, vp(b), None, None, n, 5, 1, 9, 1, 0, None) == 0
+    oracle.rollout_random(cb, None, None, 5, 1, 9, 1, 0)
+    assert np.array_equal(b, cb)
+
+
+def test_argument_errors_are_reported_not_crashed(L, ctx):
+    b, a, s = envs(8)
+    act = np.zeros(8, np.uint8)
+    assert L.g2048_ctx_env_step(ctx, None, vp(a), vp(s), vp(act), None, None, None, None, None, 8, 0, 0, 0, 0) != 0
+    assert b"null" in L.g2048_last_error()
+    assert L.g2048_ctx_env_step(ctx, vp(b), vp(a), vp(s), vp(act), None, None, None, None, None, 8, 7, 0, 0, 0) != 0   # flavour
+    assert L.g2048_ctx_env_step(ctx, vp(b), vp(a), vp(s), vp(act), None, None, None, None, None, 1 << 20, 0, 0, 0, 0) != 0  # > max_envs
+    assert L.g2048_ctx_env_step(None, vp(b), vp(a), vp(s), vp(act), None, None, None, None, None, 8, 0, 0, 0, 0) != 0
+    assert not L.g2048_ctx_create(0, 16, 1000)            # capacity not a power of two
+    assert not L.g2048_ctx_create(0, 0, 0)
+    no_table = L.g2048_ctx_create(0, 16, 0)
+    assert no_table
+    assert L.g2048_ctx_rollout_qlearn(no_table, vp(b), vp(a), vp(s), 8, 1, 0, 0.1, 0.9, 0.1, 0, 0, 0, None) != 0
+    assert L.g2048_ctx_qtable_size(no_table) == -1
+    L.g2048_ctx_destroy(no_table)
+    import torch
+    t = torch.zeros(64, dtype=torch.int64, device="cuda")
+    assert L.g2048_qtable_lookup(t.data_ptr(), 3, t.data_ptr(), 1, t.data_ptr(), None, 0, None) != 0   # capacity 3
+
+
+def test_malformed_replay_draws_stay_in_range(L, ctx):
+    """Replay draws are untrusted input: a cell index beyond the number of empty cells must not corrupt the board."""
+    n = 4096
+    rng = np.random.RandomState(0)
+    b, a, s = envs(n)
+    draws = rng.randint(0, 256, size=(n, 4)).astype(np.uint8)
+    actions = rng.randint(0, 4, n).astype(np.uint8)
+    before = b.copy()
+    assert L.g2048_ctx_env_step(ctx, vp(b), vp(a), vp(s), vp(actions), vp(draws), None, None, None, None, n, 0, 0, 0, 0) == 0
+    tiles_before, tiles_after = oracle.unpack_i64(before).sum((1, 2)), oracle.unpack_i64(b).sum((1, 2))
+    grew = tiles_after - tiles_before
+    assert set(np.unique(grew)).issubset({0, 2, 4})       # exactly one spawned 2/4 or nothing
+    assert L.g2048_ctx_env_reset(ctx, vp(b), None, None, vp(draws), n, 0, 0, 0) == 0
+    cells = oracle.unpack_i64(b)
+    assert ((cells != 0).sum((1, 2)) == 2).all() and np.isin(cells, (0, 2, 4)).all()
+
+
+def test_table_that_runs_full_drops_and_survives(L):
+    """Capacity 4,096 slots against ~100k distinct states: lookups that hit the probe limit are counted as dropped,
+    the rollout still finishes, the table never reports more states than slots, keys stay unique."""
+    small = L.g2048_ctx_create(0, 1 << 15, 1 << 12)
+    try:
+        n = 20000
+        b, a, s = envs(n)
+        c = np.zeros(9, np.int64)
+        assert L.g2048_ctx_rollout_qlearn(small, vp(b), vp(a), vp(s), n, 40, 0, 0.1, 0.99, 0.5, 1, 0, 0, vp(c)) == 0
+        assert c[0] == n * 40 and c[7] > 0
+        size = L.g2048_ctx_qtable_size(small)
+        assert 0 < size <= 1 << 12 and size == c[6]
+        keys, rows = np.zeros(size, np.uint64), np.zeros((size, 4), np.float32)
+        assert L.g2048_ctx_qtable_export(small, vp(keys), vp(rows), size) == size
+        assert len(np.unique(keys)) == size and np.isfinite(rows).all()
+        # the synchronous path on the same full table
+        sc = b.copy()
+        act = np.zeros(n, np.uint8); r = np.ones(n, np.float32); d = np.zeros(n, np.uint8)
+        assert L.g2048_ctx_qtable_update(small, vp(sc), vp(act), vp(r), vp(b), vp(d), n, 0.1, 0.9, 1) == 0
+        assert L.g2048_ctx_qtable_size(small) <= 1 << 12
+    finally:
+        L.g2048_ctx_destroy(small)
