@@ -209,3 +209,37 @@ def test_reference_training_loop_runs_unchanged_on_the_adapters(g, golden):
     np.testing.assert_allclose(rows, gd["loop_q_rows"], rtol=1e-5, atol=1e-5)
     some = agent.to_dict()
     assert len(some) == len(keys) and all(len(k) == 4 for k in list(some)[:5])
+
+
+def test_drivers_and_checkpoint(g, golden, tmp_path):
+    """train_tabular == the reference loop (same seeded trajectory as the golden run, CSV in the reference's format);
+    train_tabular_batched learns something; Q-table checkpoint round trip."""
+    import csv
+    gd = golden("compat_seeded")
+    episodes = int(gd["loop_params"][0])
+    np.random.seed(1)
+    random.seed(1)
+    env = g.Game2048_env()
+    agent = g.QLearningAgent(episodes, action_space=4, learning_rate=0.1, discount_factor=0.99, exploration_rate=0.95)
+    log = tmp_path / "debug_log.csv"
+    hist = g.train_tabular(env, agent, episodes, log_file=str(log))
+    assert [h[0] for h in hist] == gd["loop_totals"].tolist()
+    rows = list(csv.reader(open(log)))
+    assert rows[0] == ["Episode", "Action", "Q-Values", "Reward", "Total-Reward", "Max Value"] and len(rows) == episodes + 1
+
+    benv = g.BatchedGame2048Env(1 << 12, "penalty", seed=5)
+    bagent = g.BatchedQLearningAgent(12, 4, 0.1, 0.99, 0.9, capacity=1 << 22, seed=5)
+    hist = g.train_tabular_batched(benv, bagent, 12, steps_per_epoch=16, log_file=str(tmp_path / "batched.csv"))
+    assert len(hist) == 12 and hist[-1][1] < hist[0][1]            # epsilon decayed
+    assert hist[-1][7] > hist[0][7] > 0                           # table grows
+    assert bagent.epsilon == pytest.approx(0.01)
+    keys, rows_ = bagent.export()
+    path = tmp_path / "q.pt"
+    bagent.save(str(path))
+    other = g.BatchedQLearningAgent(12, 4, capacity=1 << 22)
+    other.load(str(path))
+    k2, r2 = other.export()
+    assert np.array_equal(keys, k2) and np.array_equal(rows_, r2) and other.epsilon == bagent.epsilon
+    d = bagent.to_dict()
+    k0 = next(iter(d))
+    assert len(d) == len(keys) and len(k0) == 4 and len(k0[0]) == 4
