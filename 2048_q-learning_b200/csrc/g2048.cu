@@ -48,6 +48,7 @@ constexpr size_t kLutRowBytes = 65536 * sizeof(uint16_t);
 constexpr size_t kLutMergedBytes = 65536;
 constexpr size_t kLutBytes = kLutRowBytes + kLutMergedBytes + 256 * sizeof(uint32_t);  // row | merged | mscore
 constexpr int kRolloutThreads = 1024;
+constexpr int kSmallRolloutThreads = 128;   // small batches: LUT through L1, more registers per thread
 
 struct DeviceState {
     bool ready = false;
@@ -235,12 +236,14 @@ k_env_step(Tables T, u64* boards, u64* aux, int* score, const uint8_t* actions, 
     }
 }
 
-template <int FLAVOUR>
-__global__ void __launch_bounds__(kRolloutThreads, 1)
+// SMEM_LUT is a template parameter, not a run-time flag: with the address space of the LUT known the lookups are
+// LDS with 32-bit addresses (a run-time choice made them generic LD.E with 64-bit address arithmetic).
+template <int FLAVOUR, bool SMEM_LUT>
+__global__ void __launch_bounds__(SMEM_LUT ? kRolloutThreads : kSmallRolloutThreads, 1)
 k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long long k_steps, u64 seed, u64 step_base,
-                 u64 id_base, long long* counters, int smem_lut) {
+                 u64 id_base, long long* counters) {
     extern __shared__ __align__(128) unsigned char smem[];
-    Lut L = smem_lut ? stage_lut(T, smem) : global_lut(T);
+    Lut L = SMEM_LUT ? stage_lut(T, smem) : global_lut(T);
     Counters c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         Env e;
@@ -276,13 +279,12 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
 //     the same Q value in between -- stale deltas are never summed, so heavily shared early-game states cannot
 //     diverge, and no lane spins on a contended address.  With one env nothing is ever lost: N = 1 is the
 //     reference's sequential order exactly.
-template <int FLAVOUR>
-__global__ void __launch_bounds__(kRolloutThreads, 1)
+template <int FLAVOUR, bool SMEM_LUT>
+__global__ void __launch_bounds__(SMEM_LUT ? kRolloutThreads : kSmallRolloutThreads, 1)
 k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mask, long long n, long long k_steps,
-                 float lr, float gamma, u64 eps_thresh, u64 seed, u64 step_base, u64 id_base, long long* counters,
-                 int smem_lut) {
+                 float lr, float gamma, u64 eps_thresh, u64 seed, u64 step_base, u64 id_base, long long* counters) {
     extern __shared__ __align__(128) unsigned char smem[];
-    Lut L = smem_lut ? stage_lut(T, smem) : global_lut(T);
+    Lut L = SMEM_LUT ? stage_lut(T, smem) : global_lut(T);
     Counters c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         Env e;
@@ -620,10 +622,10 @@ G2048_API int g2048_init(int device) {
                       (const uint32_t*)((const char*)lut + kLutRowBytes + kLutMergedBytes), (const double*)rv,
                       (const double*)ri, (const double*)pn};
     CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
-    CK(cudaFuncSetAttribute(k_rollout_random<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
-    CK(cudaFuncSetAttribute(k_rollout_random<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
-    CK(cudaFuncSetAttribute(k_rollout_qlearn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
-    CK(cudaFuncSetAttribute(k_rollout_qlearn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_random<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_random<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_qlearn<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_qlearn<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     d.ready = true;
     return 0;
 }
@@ -741,7 +743,7 @@ static inline void rollout_geometry(const DeviceState* D, int64_t n, int& grid, 
         smem_lut = 1;
         smem = kLutBytes;
     } else {
-        block = 128;
+        block = kSmallRolloutThreads;
         grid = (int)((n + block - 1) / block);
         if (grid < 1) grid = 1;
         smem_lut = 0;
@@ -759,12 +761,12 @@ G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* sco
     int grid, block, smem_lut;
     size_t smem;
     rollout_geometry(D, n, grid, block, smem_lut, smem);
-    if (flavour == 0)
-        k_rollout_random<0><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, n, k_steps, seed,
-                                                              step_base, env_id_base, (long long*)counters, smem_lut);
-    else
-        k_rollout_random<1><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, n, k_steps, seed,
-                                                              step_base, env_id_base, (long long*)counters, smem_lut);
+#define LAUNCH_RR(F, SM)                                                                                                \
+    k_rollout_random<F, SM><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, n, k_steps, seed, \
+                                                              step_base, env_id_base, (long long*)counters)
+    if (flavour == 0) { if (smem_lut) LAUNCH_RR(0, true); else LAUNCH_RR(0, false); }
+    else { if (smem_lut) LAUNCH_RR(1, true); else LAUNCH_RR(1, false); }
+#undef LAUNCH_RR
     LAUNCH_CHECK("k_rollout_random");
     return 0;
 }
@@ -781,14 +783,13 @@ G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* sco
     int grid, block, smem_lut;
     size_t smem;
     rollout_geometry(D, n, grid, block, smem_lut, smem);
-    if (flavour == 0)
-        k_rollout_qlearn<0><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table,
-                                                              capacity - 1, n, k_steps, lr, gamma, eps_threshold(eps),
-                                                              seed, step_base, env_id_base, (long long*)counters, smem_lut);
-    else
-        k_rollout_qlearn<1><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table,
-                                                              capacity - 1, n, k_steps, lr, gamma, eps_threshold(eps),
-                                                              seed, step_base, env_id_base, (long long*)counters, smem_lut);
+#define LAUNCH_RQ(F, SM)                                                                                                  \
+    k_rollout_qlearn<F, SM><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table,      \
+                                                              capacity - 1, n, k_steps, lr, gamma, eps_threshold(eps), seed, \
+                                                              step_base, env_id_base, (long long*)counters)
+    if (flavour == 0) { if (smem_lut) LAUNCH_RQ(0, true); else LAUNCH_RQ(0, false); }
+    else { if (smem_lut) LAUNCH_RQ(1, true); else LAUNCH_RQ(1, false); }
+#undef LAUNCH_RQ
     LAUNCH_CHECK("k_rollout_qlearn");
     return 0;
 }
