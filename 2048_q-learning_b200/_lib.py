@@ -54,6 +54,7 @@ _SIG = {
     "g2048_last_error": (C.c_char_p, []),
     "g2048_init": (i32, [i32]),
     "g2048_device_count": (i32, []),
+    "g2048_host_tables": (None, [vp] * 6),
     "g2048_host_alloc": (vp, [sz]),
     "g2048_host_free": (None, [vp]),
     "g2048_env_reset": (i32, [vp, vp, vp, vp, i64, u64, u64, u64, vp]),

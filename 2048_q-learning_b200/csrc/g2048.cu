@@ -594,6 +594,25 @@ G2048_API void* g2048_host_alloc(size_t bytes) {
 }
 G2048_API void g2048_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+G2048_API void g2048_host_tables(uint16_t* row, uint8_t* merged, uint32_t* mscore, double* reward_valid,
+                                 double* reward_invalid, double* pen) {
+    std::vector<uint16_t> r;
+    std::vector<uint8_t> m;
+    std::vector<uint32_t> ms;
+    std::vector<double> v, iv, p;
+    build_row_tables(r, m, ms);
+    build_reward_tables(v, iv, p);
+    for (unsigned i = 0; i < 65536; ++i) {   // undo the bank swizzle
+        unsigned s = lut_index2(i) & 0xFFFFu;
+        if (row) row[i] = r[s];
+        if (merged) merged[i] = m[s];
+    }
+    if (mscore) memcpy(mscore, ms.data(), ms.size() * sizeof(uint32_t));
+    if (reward_valid) memcpy(reward_valid, v.data(), v.size() * sizeof(double));
+    if (reward_invalid) memcpy(reward_invalid, iv.data(), iv.size() * sizeof(double));
+    if (pen) memcpy(pen, p.data(), p.size() * sizeof(double));
+}
+
 G2048_API int g2048_init(int device) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (device < 0 || device >= kMaxDevices) return fail(G2048_ERR_ARG, "g2048_init: bad device index");

@@ -92,6 +92,12 @@ G2048_API const char* g2048_last_error(void);
 /* Builds the 64K-entry row LUT and the reward tables and uploads them to `device`; idempotent. */
 G2048_API int g2048_init(int device);
 G2048_API int g2048_device_count(void);
+/* Host-only: the tables g2048_init uploads, for inspection and CPU-side tests (no GPU needed).  row[65536] and
+ * merged[65536] are returned in PLAIN row order (the device copy is bank-swizzled), mscore[256],
+ * reward_valid[16*16*256] indexed (level*16 + d)*256 + score/4, reward_invalid[2*16*16] indexed
+ * game_over*256 + level*16 + d, pen[32].  Any pointer may be NULL. */
+G2048_API void g2048_host_tables(uint16_t* row, uint8_t* merged, uint32_t* mscore, double* reward_valid,
+                                 double* reward_invalid, double* pen);
 /* pinned host memory for the ctx API (cudaHostAlloc / cudaFreeHost) */
 G2048_API void* g2048_host_alloc(size_t bytes);
 G2048_API void g2048_host_free(void* p);
