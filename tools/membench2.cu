@@ -16,6 +16,12 @@ template<int V> __device__ __forceinline__ u64 ld32(const u64* p){
   if(V==6){ asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];":"=l"(a),"=l"(b):"l"(p)); }
   if(V==8){ asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];":"=l"(a),"=l"(b),"=l"(c),"=l"(d):"l"(p)); u64 off = 4 + 2*((a^b^c^d)&3); u64 e,f; asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];":"=l"(e),"=l"(f):"l"(p+off)); a^=e; b^=f; }
   if(V==9){ asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];":"=l"(a),"=l"(b),"=l"(c),"=l"(d):"l"(p)); u64 e,f; asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];":"=l"(e),"=l"(f):"l"(p+4)); a^=e; b^=f; }
+  if(V==10) asm volatile("ld.global.cg.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];":"=l"(a),"=l"(b),"=l"(c),"=l"(d):"l"(p));
+  if(V==11) asm volatile("atom.global.cas.b64 %0, [%1], %2, %3;":"=l"(a):"l"(p),"l"(0ull),"l"(0ull));
+  if(V==12) asm volatile("atom.global.or.b64 %0, [%1], %2;":"=l"(a):"l"(p),"l"(0ull));
+  if(V==13) asm volatile("ld.global.cg.L2::128B.v4.u64 {%0,%1,%2,%3}, [%4];":"=l"(a),"=l"(b),"=l"(c),"=l"(d):"l"(p));
+  if(V==14) asm volatile("ld.global.lu.v4.u64 {%0,%1,%2,%3}, [%4];":"=l"(a),"=l"(b),"=l"(c),"=l"(d):"l"(p));
+  if(V==15) asm volatile("ld.global.cs.v4.u64 {%0,%1,%2,%3}, [%4];":"=l"(a),"=l"(b),"=l"(c),"=l"(d):"l"(p));
   if(V==7){ asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];":"=l"(a),"=l"(b):"l"(p)); asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];":"=l"(c),"=l"(d):"l"(p+2)); }
   return a^b^c^d;
 }
@@ -44,6 +50,12 @@ int main(int argc,char**argv){
   run<5>(buf,nslots,out,sms,"2 x ld.global.cv.v2.u64");
   run<6>(buf,nslots,out,sms,"ld.global.cg.v2.u64 (16 B)");
   run<7>(buf,nslots,out,sms,"2 x ld.relaxed.gpu.global.v2.u64");
+  run<10>(buf,nslots,out,sms,"ld.global.cg.L2::64B.v4.u64");
+  run<11>(buf,nslots,out,sms,"atom.global.cas.b64 (fails, acts as a load)");
+  run<12>(buf,nslots,out,sms,"atom.global.or.b64 with 0 (acts as a load)");
+  run<13>(buf,nslots,out,sms,"ld.global.cg.L2::128B.v4.u64");
+  run<14>(buf,nslots,out,sms,"ld.global.lu.v4.u64");
+  run<15>(buf,nslots,out,sms,"ld.global.cs.v4.u64");
   run<8>(buf,nslots,out,sms,"keys sector, then DEPENDENT 16 B from sector 1-3 of the same line");
   run<9>(buf,nslots,out,sms,"keys sector + independent 16 B from sector 1 of the same line");
   return 0;
