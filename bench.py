@@ -420,16 +420,18 @@ def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_
     barrier()
     dt = max_over_ranks(e0.elapsed_time(e1) / 1e3)
     keys, rows = agent.export()
-    digest = float(np.abs(rows).sum())
-    digests = [digest]
+    nz = np.abs(rows).sum(1) > 0          # replicas differ only in untouched zero rows (their own shard's lookups)
+    digest = float(rows[nz].astype(np.float64).sum())   # sorted by key, same rows on every replica: same order
+    digests = [[digest, float(nz.sum())]]
     if world > 1:
-        t = torch.tensor([digest, float(len(keys))], dtype=torch.float64, device=dev)
+        t = torch.tensor([digest, float(nz.sum())], dtype=torch.float64, device=dev)
         all_t = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(all_t, t)
         digests = [x.tolist() for x in all_t]
     return {"env_steps_per_sec": world * n * steps / dt, "ms_per_step": dt / steps * 1e3, "envs_per_gpu": n,
             "records_gathered_per_step": world * n, "bytes_received_per_rank_per_step": world * n * 13,
-            "replica_digests": digests, "mode": "deterministic apply of all ranks' records on every replica"}
+            "replica_digests_sum_and_count_of_nonzero_rows": digests, "replicas_identical": len({tuple(d) for d in digests}) == 1,
+            "mode": "deterministic apply of all ranks' records on every replica"}
 
 
 def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
