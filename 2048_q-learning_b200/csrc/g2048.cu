@@ -46,7 +46,8 @@ int fail(int code, const char* what) {
 constexpr int kMaxDevices = 64;
 constexpr size_t kLutRowBytes = 65536 * sizeof(uint16_t);
 constexpr size_t kLutMergedBytes = 65536;
-constexpr size_t kLutBytes = kLutRowBytes + kLutMergedBytes + 256 * sizeof(uint32_t);  // row | merged | mscore
+constexpr size_t kLutCoreBytes = kLutRowBytes + kLutMergedBytes + 256 * sizeof(uint32_t);  // row | merged | mscore
+constexpr size_t kLutBytes = kLutCoreBytes + kHotDoubles * sizeof(double);               // + hot reward tables
 constexpr int kRolloutThreads = 1024;
 constexpr int kSmallRolloutThreads = 128;   // small batches: LUT through L1, more registers per thread
 
@@ -156,7 +157,7 @@ inline bool pow2(uint64_t c) { return c && !(c & (c - 1)); }
 // ============================================================================================ kernels
 namespace {
 
-__device__ __forceinline__ Lut global_lut(const Tables& T) { return Lut{T.lut_row, T.lut_merged, T.lut_mscore}; }
+__device__ __forceinline__ Lut global_lut(const Tables& T) { return Lut{T.lut_row, T.lut_merged, T.lut_mscore, nullptr}; }
 
 // Stage the 192 KB row LUT into dynamic shared memory with one bulk-async copy (TMA, UBLKCP) completing
 // on an mbarrier; every thread then waits on phase 0.
@@ -184,7 +185,8 @@ __device__ __forceinline__ Lut stage_lut(const Tables& T, unsigned char* smem) {
             : "memory");
     }
     return Lut{reinterpret_cast<const uint16_t*>(smem), smem + kLutRowBytes,
-               reinterpret_cast<const uint32_t*>(smem + kLutRowBytes + kLutMergedBytes)};
+               reinterpret_cast<const uint32_t*>(smem + kLutRowBytes + kLutMergedBytes),
+               reinterpret_cast<const double*>(smem + kLutCoreBytes)};
 }
 
 template <bool REPLAY>
@@ -293,14 +295,19 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
         float4 row;
         u32 slot = table_find<true>(tab, mask, e.board, row, c.inserts);
         c.dropped += (slot == kNoSlot);
-        bool ins_pending = false, upd_pending = false, upd_patch = false;
-        u64 ins_old = 0;
+        bool ins_pending = false, term_pending = false, upd_pending = false, upd_patch = false;
+        u64 ins_old = 0, term_old = 0, term_key = 0;   // speculative inserts: of the current state / of a terminal state
         u32 upd_old = 0, upd_assumed = 0;
         int upd_a = 0;
         for (long long k = 0; k < k_steps; ++k) {
             u64 t = step_base + (u64)k;
             Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
             // results of the speculative operations of the previous step
+            if (term_pending) {
+                term_pending = false;
+                if (term_old == 0) c.inserts += 1;
+                else if (term_old != term_key) { float4 r2; table_find<true>(tab, mask, term_key, r2, c.inserts); }
+            }
             if (ins_pending) {
                 ins_pending = false;
                 if (ins_old == 0) c.inserts += 1;
@@ -325,28 +332,32 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
             float4 row2 = row;
             u32 slot2 = slot;
             const bool same = (e.board == s_board);   // an invalid move leaves s' == s
-            if (!same) slot2 = table_find_spec(tab, mask, e.board, row2, ins_pending, ins_old, c.dropped);
+            if (!same) {
+                if (o.done) {   // a terminal s': its insert is checked through its own pair, the env moves on at once
+                    term_key = e.board;
+                    slot2 = table_find_spec(tab, mask, e.board, row2, term_pending, term_old, c.dropped);
+                } else {
+                    slot2 = table_find_spec(tab, mask, e.board, row2, ins_pending, ins_old, c.dropped);
+                }
+            }
             if (slot != kNoSlot) {
                 float q = q_at(row, a);
                 float nq = td_apply(q, lr, td_target(gamma, (float)o.reward, max4(row2), o.done));
                 upd_assumed = __float_as_uint(q);
                 upd_old = atomicCAS(reinterpret_cast<u32*>(&tab[slot].q[a]), upd_assumed, __float_as_uint(nq));
-                upd_pending = true; upd_patch = same; upd_a = a;
+                upd_pending = true; upd_patch = same && !o.done; upd_a = a;
                 if (same) q_set(row2, a, nq);
             }
             row = row2;
             slot = slot2;
-            if (o.done) {
-                if (ins_pending) {   // the terminal state's insert must land before the env moves on
-                    ins_pending = false;
-                    if (ins_old == 0) c.inserts += 1;
-                    else if (ins_old != e.board) { float4 r2; table_find<true>(tab, mask, e.board, r2, c.inserts); }
-                }
+            if (o.done) {   // state = env.reset() is read at once (main.py:81-82, :92), speculatively as well
                 philox_autoreset(e, seed, id, t);
-                slot = table_find<true>(tab, mask, e.board, row, c.inserts);
-                c.dropped += (slot == kNoSlot);
-                if (upd_pending) upd_patch = false;
+                slot = table_find_spec(tab, mask, e.board, row, ins_pending, ins_old, c.dropped);
             }
+        }
+        if (term_pending) {
+            if (term_old == 0) c.inserts += 1;
+            else if (term_old != term_key) { float4 r2; table_find<true>(tab, mask, term_key, r2, c.inserts); }
         }
         if (ins_pending) {
             if (ins_old == 0) c.inserts += 1;
@@ -633,6 +644,15 @@ G2048_API int g2048_init(int device) {
     CK(cudaMemcpy(lut, row.data(), kLutRowBytes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy((char*)lut + kLutRowBytes, merged.data(), kLutMergedBytes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy((char*)lut + kLutRowBytes + kLutMergedBytes, mscore.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    {   // hot reward entries, staged into shared memory together with the LUT
+        std::vector<double> hot(kHotDoubles, 0.0);
+        for (int i = 0; i < 512; ++i) hot[kHotInvalid + i] = invalid[i];
+        for (int i = 0; i < 32; ++i) hot[kHotPen + i] = pen[i];
+        for (int lvl = 0; lvl < 16; ++lvl)
+            for (int d = 0; d < 2; ++d)
+                for (int s4 = 0; s4 < 64; ++s4) hot[kHotValid + (lvl * 2 + d) * 64 + s4] = valid[(lvl * 16 + d) * 256 + s4];
+        CK(cudaMemcpy((char*)lut + kLutCoreBytes, hot.data(), hot.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpy(rv, valid.data(), valid.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ri, invalid.data(), invalid.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pn, pen.data(), pen.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -40,7 +40,11 @@ struct Lut {
     const uint16_t* row;
     const uint8_t* merged;
     const uint32_t* mscore;
+    // hot part of the reward tables staged next to the LUT (NULL on the global-LUT path):
+    // [rew_invalid 512][pen 32][rew_valid for d < 2 and score < 256: 16 levels x 2 x 64]
+    const double* rew_hot;
 };
+constexpr int kHotInvalid = 0, kHotPen = 512, kHotValid = 544, kHotDoubles = 544 + 16 * 2 * 64;
 // Bank swizzle of the LUT index, applied to two packed rows at once.  Real boards hold small levels, so the
 // plain index puts most lanes of a warp into ~8 of the 32 banks (measured 6.9 wavefronts per LDS); XOR-folding
 // bits 7-13 into bits 1-6 spreads them (2.7 wavefronts on rollout boards) and stays a bijection per row.
@@ -243,11 +247,15 @@ struct StepOut {
 // d = max(level - prev_level, 0) is the progress step (previous_max is raised even when the move was
 // invalid and the bonus discarded, :148-150).
 __device__ __forceinline__ double shaped_reward(int score, bool valid, bool game_over, int lvl, int& prev_level,
-                                                const Tables& T) {
+                                                const Tables& T, const Lut& L) {
     int d = lvl > prev_level ? lvl - prev_level : 0;
     if (lvl > prev_level) prev_level = lvl;
-    if (!valid) return __ldg(T.rew_invalid + ((game_over ? 256 : 0) + lvl * 16 + d));
+    if (!valid) {
+        int i = (game_over ? 256 : 0) + lvl * 16 + d;
+        return L.rew_hot ? L.rew_hot[kHotInvalid + i] : __ldg(T.rew_invalid + i);
+    }
     if (score >= 1024) return 10.0;
+    if (L.rew_hot && d < 2 && score < 256) return L.rew_hot[kHotValid + (lvl * 2 + d) * 64 + (score >> 2)];
     return __ldg(T.rew_valid + ((lvl * 16 + d) * 256 + (score >> 2)));
 }
 
@@ -266,7 +274,7 @@ __device__ __forceinline__ void penalty_step(Env& e, int a, u32 d0, u32 d1, cons
     e.score += ms;                                               // :104
     int prev_level = (int)(e.small & 0xFFu), cons_action = (int)((e.small >> 8) & 0xFFu);
     int pen_idx = (int)((e.small >> 16) & 0xFFu);
-    double reward = shaped_reward(ms, valid, game_over, lvl, prev_level, T);  // :107
+    double reward = shaped_reward(ms, valid, game_over, lvl, prev_level, T, L);  // :107
     if (a == cons_action) {                                      // :110-115
         if (e.cons_count != 0xFFFFFFFFu) e.cons_count += 1;
     } else {
@@ -278,7 +286,7 @@ __device__ __forceinline__ void penalty_step(Env& e, int a, u32 d0, u32 d1, cons
     if (e.cons_count > 10) {                                     // :121-127
         if (e.cons_count > 100) done = true;
         if (pen_idx < kPenSat) pen_idx += 1;
-        reward = __dadd_rn(reward, __ldg(T.pen + pen_idx));
+        reward = __dadd_rn(reward, L.rew_hot ? L.rew_hot[kHotPen + pen_idx] : __ldg(T.pen + pen_idx));
     }
     e.small = (u32)prev_level | ((u32)cons_action << 8) | ((u32)pen_idx << 16);
     o.reward = reward; o.move_score = ms; o.maxlvl = lvl;

@@ -69,6 +69,19 @@ def ncu_traffic():
         return None
 
 
+def rmw_peak():
+    """Live: random 32-byte load + 4-byte store to the same sector over 8 GiB (tools/membench3) -- the access pattern
+    of one Q-table lookup followed by the update of one of its values."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run([os.path.join(ROOT, "tools", "membench3")], capture_output=True, text=True, timeout=120).stdout
+        m = re.search(r"mode 3 .*?([0-9.]+) Gops/s", out)
+        return float(m.group(1)) * 1e9 if m else None
+    except Exception:
+        return None
+
+
 def ncu_dram_ops_per_step():
     try:
         return float(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_random_ops_per_env_step"])
@@ -372,6 +385,15 @@ def main():
                 "fused_kernel_bound_env_steps_per_sec": (rnd / per_step) if per_step else None,
                 "fused_kernel_frac_of_random_access_bound": (value / world * per_step / rnd) if per_step else None,
                 "note": "a hash table in HBM is bounded by random line fetches, not by its algorithmic bytes"}
+        rmw = rmw_peak()
+        if rmw:
+            c0 = counters.cpu().numpy()
+            valid_frac = float(c0[1]) / max(float(c0[0]), 1.0)     # an invalid move needs no lookup (s' == s)
+            extras["hbm_random_read_modify_write"] = {
+                "measured_rmw_per_sec": rmw, "rmw_per_env_step": valid_frac,
+                "fused_kernel_bound_env_steps_per_sec": rmw / valid_frac,
+                "fused_kernel_frac_of_bound": value / world * valid_frac / rmw,
+                "note": "one lookup of s' (32-byte sector) + one later 4-byte write into it per valid move"}
     if world > 1:
         dist.barrier()
 
