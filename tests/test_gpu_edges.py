@@ -144,3 +144,36 @@ def test_table_that_runs_full_drops_and_survives(L):
         assert L.g2048_ctx_qtable_size(small) <= 1 << 12
     finally:
         L.g2048_ctx_destroy(small)
+
+
+def test_concurrent_inserts_of_the_same_keys_never_duplicate(L):
+    """A million threads look up (with insert) only 1,000 distinct states at once, then 2^20 distinct ones: every key
+    ends up in exactly one slot and every later lookup finds it (races on the key CAS are resolved correctly)."""
+    import torch
+    cap = 1 << 22
+    table = torch.zeros(cap * 4, dtype=torch.int64, device="cuda")
+    rng = np.random.RandomState(5)
+    pool = (rng.randint(1, 1 << 62, size=1000, dtype=np.int64) | 1)
+    n = 1 << 20
+    keys = torch.from_numpy(pool[rng.randint(0, 1000, n)]).cuda()
+    rows = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    found = torch.empty(n, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.g2048_qtable_lookup(table.data_ptr(), cap, keys.data_ptr(), n, rows.data_ptr(), found.data_ptr(), 1, st) == 0
+    assert L.g2048_qtable_size(table.data_ptr(), cap, cnt.data_ptr(), st) == 0
+    assert int(cnt.item()) == 1000
+    assert L.g2048_qtable_lookup(table.data_ptr(), cap, keys.data_ptr(), n, rows.data_ptr(), found.data_ptr(), 0, st) == 0
+    assert bool(found.bool().all()) and float(rows.abs().sum()) == 0.0
+    distinct = torch.from_numpy(np.unique(rng.randint(1, 1 << 62, size=n, dtype=np.int64))).cuda()
+    m = distinct.numel()
+    assert L.g2048_qtable_lookup(table.data_ptr(), cap, distinct.data_ptr(), m, rows.data_ptr(), found.data_ptr(), 1, st) == 0
+    assert L.g2048_qtable_size(table.data_ptr(), cap, cnt.data_ptr(), st) == 0
+    extra = int((~torch.isin(distinct, torch.from_numpy(pool).cuda())).sum().item())
+    assert int(cnt.item()) == 1000 + extra
+    ek = torch.empty(cap, dtype=torch.int64, device="cuda")
+    er = torch.empty((cap, 4), dtype=torch.float32, device="cuda")
+    cnt.zero_()
+    assert L.g2048_qtable_export(table.data_ptr(), cap, ek.data_ptr(), er.data_ptr(), cap, cnt.data_ptr(), st) == 0
+    got = ek[: int(cnt.item())]
+    assert got.unique().numel() == got.numel()
