@@ -344,3 +344,30 @@ def test_rollout_qlearn_1M_envs_properties(L, ctx):
         assert (b != 0).all()
     finally:
         L.g2048_ctx_destroy(big)
+
+
+# ------------------------------------------------------------------------------------------ distributions
+def test_philox_mode_matches_the_reference_statistics(L, ctx):
+    """Philox cannot follow MT19937 draw by draw, so the Philox mode is checked statistically against the
+    reference's own random-policy numbers (SURVEY.md section 6 probes: 1,000 reference episodes each):
+    penalty env  : episode length 140.8, invalid-move fraction 0.161, mean game score 1088
+    nopenalty env: episode length 131.4, invalid-move fraction 0.135, mean game score 1002
+    plus the spawn law: 10 % fours, uniform over the empty cells (Game2048_env.py:16-20)."""
+    n, k = 1 << 16, 8000   # ~55 episodes per env: the unfinished last episode biases steps/episodes by < 1 %
+    for flavour, length, invalid, score in ((0, 140.8, 0.161, 1088.0), (1, 131.4, 0.135, 1002.0)):
+        b, a, s = fresh_envs(n, seed=77 + flavour)
+        c = np.zeros(9, np.int64)
+        ok(L, L.g2048_ctx_rollout_random(ctx, vp(b), vp(a), vp(s), n, k, flavour, 77 + flavour, 0, 0, vp(c)))
+        steps, valid, episodes, total_score = (float(x) for x in c[:4])
+        assert abs(steps / episodes - length) < 0.04 * length          # reference sample: +-1.4 (1 sigma of the mean)
+        assert abs((1 - valid / steps) - invalid) < 0.02
+        assert abs(total_score / episodes - score) < 0.05 * score
+    m = 1 << 20
+    boards = np.zeros(m, np.uint64)
+    ok(L, L.g2048_ctx_env_reset(ctx, vp(boards), None, None, None, m, 4242, 9, 0))
+    cells = oracle.unpack_i64(boards).reshape(m, 16)
+    assert ((cells != 0).sum(1) == 2).all()
+    fours = (cells == 4).sum() / (2.0 * m)
+    assert abs(fours - 0.1) < 0.002
+    occupancy = (cells != 0).mean(0)
+    assert np.abs(occupancy - 2 / 16).max() < 0.003                       # uniform over the 16 cells
