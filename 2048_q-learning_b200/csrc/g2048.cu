@@ -872,11 +872,13 @@ int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int6
         LAUNCH_CHECK("k_apply_atomic");
         return 0;
     }
-    (void)capacity;
-    // all 64 key bits take part so that the all-ones "no slot" key sorts last; the sort is stable, so
-    // equal keys keep ascending record (= env) order
+    // Valid keys are slot * 4 + action < 4 * capacity; the all-ones "no slot" key is also all ones in the low
+    // log2(capacity) + 3 bits, so sorting just those bits still puts it last (fewer radix passes than 64 bits).
+    // The sort is stable: equal keys keep ascending record (= env) order.
+    int end_bit = 3;
+    while ((1ull << (end_bit - 3)) < capacity) ++end_bit;
     CK(cub::DeviceRadixSort::SortPairs(s.cub_temp, s.cub_bytes, (const u64*)s.key_in, s.key_out, (const float*)s.val_in,
-                                       s.val_out, (int64_t)n, 0, 64, st));
+                                       s.val_out, (int64_t)n, 0, end_bit, st));
     k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n);
     LAUNCH_CHECK("k_segment_apply");
     return 0;
