@@ -243,3 +243,37 @@ def test_drivers_and_checkpoint(g, golden, tmp_path):
     d = bagent.to_dict()
     k0 = next(iter(d))
     assert len(d) == len(keys) and len(k0) == 4 and len(k0[0]) == 4
+
+
+def test_adapter_game_core_api(g):
+    """Game2048 adapter surface used by the reference's drivers: .board readable and assignable
+    (main.py:85, mainDQL_CNN_step2.py:163,237), move(a, trial=True) -> (legal, score) without side effects
+    (mainDQL_CNN_step2.py:169-174), is_game_over(), add_number(), showMatrix()."""
+    np.random.seed(3)
+    env = g.Game2048_env(flavour="nopenalty")
+    board = np.array([[2, 2, 4, 0], [0, 0, 0, 0], [8, 8, 8, 8], [2, 4, 2, 4]], dtype=np.int64)
+    env.game.board = board.copy()
+    state = np.random.get_state()[1].copy()
+    legal = []
+    for a in range(4):
+        moved, score = env.game.move(a, trial=True)
+        nb, mv, sc = oracle.move(np.array([g.pack_tiles(board)], np.uint64), np.array([a], np.uint8))
+        assert bool(moved) == bool(mv[0]) and int(score) == int(sc[0])
+        legal.append(bool(moved))
+    assert legal == [True, True, True, True]
+    assert np.array_equal(env.game.board, board)                       # trial moves do not touch the board
+    assert np.array_equal(np.random.get_state()[1], state)            # ... nor the global RNG
+    assert not env.game.is_game_over()
+    dead = np.array([[2, 4, 2, 4], [4, 2, 4, 2], [2, 4, 2, 4], [4, 2, 4, 2]], dtype=np.int64)
+    env.game.board = dead
+    assert env.game.is_game_over() and all(not env.game.move(a, trial=True)[0] for a in range(4))
+    nxt, reward, done, mx = env.step(0)                                 # a step from a dead board ends the episode
+    assert done and reward == 0 and mx == 4 and np.array_equal(nxt, dead)
+    penv = g.Game2048_env()                                              # penalty flavour: move() mutates and spawns
+    penv.game.board = board.copy()
+    moved, score = penv.game.move(0)
+    assert moved and score == 4 + 16 + 16 and (penv.game.board != 0).sum() == (board != 0).sum() - 3 + 1
+    before = (penv.game.board != 0).sum()
+    penv.game.add_number()
+    assert (penv.game.board != 0).sum() == before + 1
+    penv.showMatrix()
