@@ -159,7 +159,8 @@ namespace {
 
 __device__ __forceinline__ Lut global_lut(const Tables& T) { return Lut{T.lut_row, T.lut_merged, T.lut_mscore, nullptr}; }
 
-// Stage the 192 KB row LUT into dynamic shared memory with one bulk-async copy (TMA, UBLKCP) completing
+// Stage the 213 KB LUT blob (row table, merged levels, score table, hot reward tables) into dynamic shared
+// memory with one bulk-async copy (TMA, UBLKCP) completing
 // on an mbarrier; every thread then waits on phase 0.
 __device__ __forceinline__ Lut stage_lut(const Tables& T, unsigned char* smem) {
     __shared__ __align__(8) unsigned long long mbar;
@@ -773,7 +774,7 @@ G2048_API int g2048_select_action(const float* qvalues, const uint8_t* legal_mas
 }
 
 // fused rollouts: one persistent CTA per SM with the LUT in shared memory once there is enough work to
-// amortise the 192 KB staging copy; small batches read the LUT through L1 instead.
+// amortise the 213 KB staging copy; small batches read the LUT through L1 instead.
 static inline void rollout_geometry(const DeviceState* D, int64_t n, int& grid, int& block, int& smem_lut, size_t& smem) {
     if (n >= 16384) {
         block = kRolloutThreads;
