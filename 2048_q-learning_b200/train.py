@@ -75,3 +75,25 @@ def train_tabular_batched(env, agent, total_epochs: int, steps_per_epoch: int = 
             on_epoch(epoch, row)
         agent.decay_exploration(epoch)
     return history
+
+
+def evaluate_tabular(env, agent, episodes: int = 10):
+    """Greedy play (epsilon = 0) of the N = 1 adapters or the reference's objects -- the headless form of the
+    demo's "model play" mode (GameDemo.py:258-316).  Returns per-episode (game score, max tile, steps)."""
+    saved, agent.epsilon = agent.epsilon, 0.0
+    out = []
+    try:
+        for _ in range(episodes):
+            state = tuple(map(tuple, env.reset()))
+            done, steps, max_tile = False, 0, 0
+            while not done:
+                action = agent.choose_action(state)
+                board, reward, done, max_tile = env.step(action)
+                if hasattr(env.game, "moved_board"):      # nopenalty flavour: the caller commits the board
+                    env.game.board = board
+                state = tuple(map(tuple, board))
+                steps += 1
+            out.append((int(env.score), int(max_tile), steps))
+    finally:
+        agent.epsilon = saved
+    return out

@@ -277,3 +277,14 @@ def test_adapter_game_core_api(g):
     penv.game.add_number()
     assert (penv.game.board != 0).sum() == before + 1
     penv.showMatrix()
+
+
+def test_evaluate_tabular_greedy_play(g):
+    np.random.seed(11)
+    random.seed(11)
+    env = g.Game2048_env()
+    agent = g.QLearningAgent(5, action_space=4, exploration_rate=0.9)
+    g.train_tabular(env, agent, 5)
+    eps = agent.epsilon
+    res = g.evaluate_tabular(env, agent, episodes=3)
+    assert len(res) == 3 and all(r[2] > 0 and r[1] >= 2 for r in res) and agent.epsilon == eps
