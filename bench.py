@@ -148,6 +148,22 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on (and allocate pinned host memory from) the CPU cores NVML reports as local to
+    this GPU, so that the end-to-end arm's PCIe traffic does not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def fresh_host_envs(L, ctx, n, base, pinned):
     """Pinned host buffers with freshly reset boards (reset itself runs on the GPU through the C ABI)."""
     def alloc(dtype, count):
@@ -251,6 +267,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as dist
 

@@ -68,3 +68,19 @@ def test_tile_packing_roundtrip():
         assert np.array_equal(g2048.unpack_tiles(b), tiles)
     with pytest.raises(ValueError):
         g2048.pack_tiles(np.full((4, 4), 3))
+
+
+def test_header_compiles_as_c_and_links():
+    """include/g2048.h is plain C (C99) and a C program links against libg2048.so without any C++/CUDA symbols."""
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so_dir = os.path.dirname(g2048.build())
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "demo")
+        res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                              os.path.join(root, "examples", "c_api_demo.c"), "-L" + so_dir, "-lg2048",
+                              "-Wl,-rpath," + so_dir, "-o", exe], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        run = subprocess.run([exe], capture_output=True, text=True)
+        if ctypes.CDLL(g2048.build()).g2048_device_count() == 0:
+            assert run.returncode == 2 and "no CPU fallback" in run.stderr      # refuses loudly without a GPU

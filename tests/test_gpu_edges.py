@@ -177,3 +177,20 @@ def test_concurrent_inserts_of_the_same_keys_never_duplicate(L):
     assert L.g2048_qtable_export(table.data_ptr(), cap, ek.data_ptr(), er.data_ptr(), cap, cnt.data_ptr(), st) == 0
     got = ek[: int(cnt.item())]
     assert got.unique().numel() == got.numel()
+
+
+def test_c_program_drives_the_abi(L):
+    """examples/c_api_demo.c: reset / choose_action / step / update_q_value / fused rollout from plain C."""
+    import os
+    import subprocess
+    import tempfile
+    import g2048
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so_dir = os.path.dirname(g2048.build())
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "demo")
+        subprocess.run(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "c_api_demo.c"),
+                        "-L" + so_dir, "-lg2048", "-Wl,-rpath," + so_dir, "-o", exe], check=True)
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 0, run.stdout + run.stderr
+        assert "fused rollout: 1048576 steps" in run.stdout
