@@ -173,9 +173,10 @@ __device__ __forceinline__ int kth_empty_pos(u64 E, int k) {
 // otherwise d0/d1 are 32-bit uniform draws: k = floor(d0 * n_empty / 2^32), 4 iff d1 >= 0.9 * 2^32.
 // lvl_max is raised to the spawned level (1 or 2) when it is larger.
 template <bool REPLAY>
-__device__ __forceinline__ u64 spawn(u64 b, u32 d0, u32 d1, int& lvl_max) {
+__device__ __forceinline__ u64 spawn(u64 b, u32 d0, u32 d1, int& lvl_max, int* empties_left = nullptr) {
     u64 E = ~nzmask(b) & kNib1;
     int ne = __popcll(E);
+    if (empties_left) *empties_left = ne > 0 ? ne - 1 : 0;
     if (ne == 0) return b;
     int k = REPLAY ? (int)d0 : (int)__umulhi(d0, (u32)ne);
     if (k >= ne) k = ne - 1;  // malformed replay input: stay in range
@@ -201,6 +202,13 @@ __device__ __forceinline__ void equal_pairs(u64 b, u64 F, u64& eqH, u64& eqV) {
     eqH = ~nzmask(b ^ (b >> 4)) & kColsLeft3 & ok;
     eqV = ~nzmask(b ^ (b >> 16)) & kRowsTop3 & ok;
 }
+// is_game_over for a board KNOWN to be full: no two equal neighbours.  x = b ^ (b >> 4) has a zero nibble where two
+// horizontal neighbours are equal (column 3 pairs with the next row: forced non-zero), same with >> 16 vertically;
+// "has a zero nibble" is the exact (x - 0x11..1) & ~x & 0x88..8 test.  Level-15 pairs cannot merge (they are the
+// only equal neighbours that do not count): boards holding a 15 take the general path.
+__device__ __forceinline__ bool is_dead_full(u64 b);
+__device__ __forceinline__ bool has_zero_nibble(u64 x) { return ((x - kNib1) & ~x & (kNib1 << 3)) != 0; }
+
 // is_game_over as a predicate (Game2048_env.py:65-75): full and nothing merges
 __device__ __forceinline__ bool is_dead(u64 b) {
     u64 F = nzmask(b);
@@ -208,6 +216,12 @@ __device__ __forceinline__ bool is_dead(u64 b) {
     u64 eqH, eqV;
     equal_pairs(b, F, eqH, eqV);
     return (eqH | eqV) == 0;
+}
+__device__ __forceinline__ bool is_dead_full(u64 b) {
+    if (is15mask(b)) return is_dead(b);
+    u64 h = (b ^ (b >> 4)) | 0xF000F000F000F000ull;
+    u64 v = (b ^ (b >> 16)) | 0xFFFF000000000000ull;
+    return !has_zero_nibble(h) && !has_zero_nibble(v);
 }
 // bit a set iff move(a, trial=True) would move (mainDQL_CNN_step2.py:169-174)
 __device__ __forceinline__ u32 legal_mask(u64 b) {
@@ -266,8 +280,10 @@ __device__ __forceinline__ void penalty_step(Env& e, int a, u32 d0, u32 d1, cons
     bool valid = m.moved;
     int ms = m.score, lvl = max(e.maxlvl, m.hi_level);           // np.max(board) :100, incrementally
     u64 b1 = m.board;
-    if (valid) b1 = spawn<REPLAY>(b1, d0, d1, lvl);              // :61-62
-    bool game_over = is_dead(b1);                                // :99
+    int empties = 1;                                             // cells still empty after the spawn
+    if (valid) b1 = spawn<REPLAY>(b1, d0, d1, lvl, &empties);    // :61-62
+    else empties = (nzmask(b1) != kNib1);                        // unchanged board: only "full or not" matters
+    bool game_over = empties == 0 && is_dead_full(b1);           // :99
     if (lvl < 1) lvl = 1;                                        // max(2, max_number) :141
     e.board = b1;
     e.maxlvl = lvl;
