@@ -270,10 +270,11 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
 // main.py:91-101 fused.  Per step: Philox -> epsilon-greedy from the carried row of s -> env step ->
 // find-or-insert s' -> q <- q + lr (target - q) on Q[s][a] -> carry (slot, row) of s' as the next s.
 //
-// Measured on B200 (tools/membench.cu): random 32-byte sector LOADS that miss L2 saturate at ~36 G/s and
-// atomicCAS that misses L2 at ~20 G/s, both already at 256 threads/SM -- that, not the 6.5 TB/s streaming
-// peak, is what bounds a hash table in HBM.  So the kernel keeps the dependent chain per step at the probe
-// loads only:
+// Measured on B200 (tools/membench*.cu, profiles/r01_membench.txt): random loads that miss L2 saturate at ~36 G/s
+// (each moves a 128-byte line), atomicCAS that misses L2 at ~20 G/s, and "load a random 32-byte sector, then write
+// 4 bytes into it" -- exactly one table visit -- at 16.8 G/s.  That, not the 6.5 TB/s streaming peak, bounds a hash
+// table in HBM: ~20 G env-steps/s for this kernel (0.85 table visits per step).  So the kernel issues exactly one
+// load per probe and keeps everything else off the dependent chain:
 //   * lookup = plain 256-bit load(s); an empty slot is claimed with atomicCAS (an L2 hit by then) WITHOUT
 //     waiting for its result: the lane goes on as if the insert succeeded (a new state has a zero row
 //     wherever it lands) and checks the CAS result one step later, re-probing only if another state won the slot;
