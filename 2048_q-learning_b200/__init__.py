@@ -16,7 +16,7 @@ def __getattr__(name):  # the batched classes need torch: import lazily
     if name == "BatchedQLearningAgent":
         from . import agent
         return agent.BatchedQLearningAgent
-    if name in ("BatchedDQNAgent", "DQNModel", "dqn_step", "terminal_bonus"):
+    if name in ("BatchedDQNAgent", "DQNModel", "dqn_step", "terminal_bonus", "FusedDQNFeed"):
         from . import dqn
         return getattr(dqn, name)
     if name in ("ShardedQLearning", "shard_range"):

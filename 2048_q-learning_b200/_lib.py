@@ -64,6 +64,7 @@ _SIG = {
     "g2048_pack_i64": (i32, [vp, vp, i64, vp, vp]),
     "g2048_unpack_i64": (i32, [vp, vp, i64, vp]),
     "g2048_encode_onehot": (i32, [vp, vp, i64, i32, vp]),
+    "g2048_dqn_env_step": (i32, [vp] * 11 + [i32, i64, f64, C.c_uint32, u64, u64, u64, u64, vp]),
     "g2048_select_action": (i32, [vp, vp, vp, i64, f64, u64, u64, u64, vp]),
     "g2048_rollout_random": (i32, [vp, vp, vp, i64, i64, i32, u64, u64, u64, vp, vp]),
     "g2048_rollout_qlearn": (i32, [vp, vp, vp, vp, u64, i64, i64, i32, f32, f32, f64, u64, u64, u64, vp, vp]),

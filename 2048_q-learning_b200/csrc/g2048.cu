@@ -538,55 +538,108 @@ __global__ void __launch_bounds__(256) k_unpack(const u64* boards, long long* ti
         tiles[j] = lvl ? (1ll << lvl) : 0;
     }
 }
-// encode_state: out[n][16][4][4]; one thread writes 4 consecutive cells (one row of one level plane)
-template <typename T4, typename MakeT4>
-__device__ __forceinline__ void onehot_body(const u64* boards, T4* out, long long n, MakeT4 mk) {
-    long long total = n * 64;  // 64 groups of 4 cells per board
-    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
-        u64 b = boards[j >> 6];
-        int lvl = (int)((j >> 2) & 15), r = (int)(j & 3);
-        u32 rowbits = (u32)(b >> (16 * r)) & 0xFFFFu;
-        out[j] = mk((rowbits & 15) == (u32)lvl, ((rowbits >> 4) & 15) == (u32)lvl, ((rowbits >> 8) & 15) == (u32)lvl,
-                    ((rowbits >> 12) & 15) == (u32)lvl);
-    }
+// One-hot pieces: group g of a board = level plane (g >> 2), row (g & 3): four consecutive cells
+__device__ __forceinline__ float4 onehot_f32(u64 b, int g) {
+    u32 row = (u32)(b >> (16 * (g & 3))) & 0xFFFFu, lvl = (u32)(g >> 2);
+    return make_float4((row & 15) == lvl ? 1.f : 0.f, ((row >> 4) & 15) == lvl ? 1.f : 0.f,
+                       ((row >> 8) & 15) == lvl ? 1.f : 0.f, ((row >> 12) & 15) == lvl ? 1.f : 0.f);
 }
+__device__ __forceinline__ uint2 onehot_bf16(u64 b, int g) {   // bf16 1.0 = 0x3F80
+    u32 row = (u32)(b >> (16 * (g & 3))) & 0xFFFFu, lvl = (u32)(g >> 2);
+    return make_uint2(((row & 15) == lvl ? 0x3F80u : 0u) | (((row >> 4) & 15) == lvl ? 0x3F800000u : 0u),
+                      (((row >> 8) & 15) == lvl ? 0x3F80u : 0u) | (((row >> 12) & 15) == lvl ? 0x3F800000u : 0u));
+}
+// encode_state: out[n][16][4][4]; one thread writes 4 consecutive cells (one row of one level plane)
 __global__ void __launch_bounds__(256) k_onehot_f32(const u64* boards, float4* out, long long n) {
-    onehot_body(boards, out, n, [](bool a, bool b, bool c, bool d) {
-        return make_float4(a ? 1.f : 0.f, b ? 1.f : 0.f, c ? 1.f : 0.f, d ? 1.f : 0.f);
-    });
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n * 64; j += (long long)gridDim.x * blockDim.x)
+        out[j] = onehot_f32(boards[j >> 6], (int)(j & 63));
 }
 __global__ void __launch_bounds__(256) k_onehot_bf16(const u64* boards, uint2* out, long long n) {
-    onehot_body(boards, out, n, [](bool a, bool b, bool c, bool d) {  // bf16 1.0 = 0x3F80
-        return make_uint2((a ? 0x3F80u : 0u) | (b ? 0x3F800000u : 0u), (c ? 0x3F80u : 0u) | (d ? 0x3F800000u : 0u));
-    });
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n * 64; j += (long long)gridDim.x * blockDim.x)
+        out[j] = onehot_bf16(boards[j >> 6], (int)(j & 63));
 }
-// act / act_ripetitive (Dqn8TestNOPERCNN.py:312-336)
+// act / act_ripetitive (Dqn8TestNOPERCNN.py:312-336): lm == 0 -> act (uniform over 4 / plain argmax), else uniform over
+// the legal moves (np.random.choice) / first maximum among the legal moves in ascending action order
+__device__ __forceinline__ int select_action(const float4& q, u32 lm, const Draw4& x, u64 eps_thresh) {
+    bool explore = (u64)x.x2 < eps_thresh;
+    if (lm == 0) return explore ? (int)(x.x3 >> 30) : argmax4(q);
+    if (explore) {
+        int j = (int)__umulhi(x.x3, (u32)__popc(lm));
+        u32 m = lm;
+        for (int s = 0; s < j; ++s) m &= m - 1;
+        return __ffs((int)m) - 1;
+    }
+    int act = -1;
+    float best = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if ((lm >> c) & 1u) {
+            float v = q_at(q, c);
+            if (act < 0 || v > best) { best = v; act = c; }
+        }
+    return act;
+}
 __global__ void __launch_bounds__(256)
 k_select_action(const float4* qv, const uint8_t* legal, uint8_t* actions, long long n, u64 eps_thresh, u64 seed, u64 t,
                 u64 id_base) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         Draw4 x = philox(seed, id_base + (u64)i, t, G2048_STREAM_STEP);
-        u32 lm = legal ? (legal[i] & 15u) : 0u;
-        bool explore = (u64)x.x2 < eps_thresh;
-        int act;
-        if (lm == 0) {  // act(), or act_ripetitive with no legal move
-            act = explore ? (int)(x.x3 >> 30) : argmax4(qv[i]);
-        } else if (explore) {  // np.random.choice(legal_moves)
-            int j = (int)__umulhi(x.x3, (u32)__popc(lm));
-            u32 m = lm;
-            for (int s = 0; s < j; ++s) m &= m - 1;
-            act = __ffs((int)m) - 1;
-        } else {  // argmax over the legal moves, first maximum in ascending action order
-            float4 q = qv[i];
-            act = -1;
-            float best = 0.f;
-            for (int c = 0; c < 4; ++c)
-                if ((lm >> c) & 1u) {
-                    float v = q_at(q, c);
-                    if (act < 0 || v > best) { best = v; act = c; }
-                }
+        actions[i] = (uint8_t)select_action(qv[i], legal ? (legal[i] & 15u) : 0u, x, eps_thresh);
+    }
+}
+
+// The env side of one DQN driver step (mainDQL_CNN_step2.py:163-237) fused: select -> step -> terminal bonus -> reset ->
+// legal mask -> one-hot.  One thread per env for the game logic; the one-hot planes of the block's 256 boards are
+// then written by the whole block, 16 bytes per thread and store instruction, fully coalesced (1 KB per board).
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+k_dqn_env_step(Tables T, u64* boards, int* score, const float4* qv, const uint8_t* legal_in, uint8_t* actions, u64* state_out,
+               u64* next_out, float* reward, uint8_t* done_out, uint8_t* legal_out, void* onehot, long long n,
+               u64 eps_thresh, u32 opts, u64 seed, u64 t, u64 reset_idx, u64 id_base) {
+    __shared__ u64 sb[256];
+    Lut L = global_lut(T);
+    long long block0 = (long long)blockIdx.x * 256;
+    long long i = block0 + threadIdx.x;
+    u64 cont = 0;
+    if (i < n) {
+        u64 id = id_base + (u64)i;
+        Env e;
+        env_load(e, boards[i], G2048_AUX_INIT, score ? score[i] : 0);
+        Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
+        int a = select_action(qv[i], legal_in ? (legal_in[i] & 15u) : 0u, x, eps_thresh);
+        u64 s0 = e.board;
+        StepOut o;
+        philox_step<G2048_FLAVOUR_NOPENALTY>(e, a, x, seed, id, t, L, T, o);
+        float r = (float)o.reward;
+        if (o.done && (opts & G2048_DQN_TERMINAL_BONUS)) {   // mainDQL_CNN_step2.py:202-213
+            u64 b = e.board;
+            int big = __popcll((b >> 3) & ((b >> 2) | (b >> 1)) & kNib1);   // cells holding 1024 or more
+            if (o.maxlvl >= 11) r += 100.f;
+            else if (o.maxlvl >= 10 && big >= 2) r += 50.f;
         }
-        actions[i] = (uint8_t)act;
+        if (actions) actions[i] = (uint8_t)a;
+        if (state_out) state_out[i] = s0;
+        if (next_out) next_out[i] = e.board;
+        if (reward) reward[i] = r;
+        if (done_out) done_out[i] = o.done;
+        if (o.done && (opts & G2048_DQN_AUTO_RESET)) {
+            Draw4 y = philox(seed, id, reset_idx, G2048_STREAM_RESET);
+            e.board = fresh_board<false>(y.x0, y.x1, y.x2, y.x3);
+            e.score = 0;
+        }
+        boards[i] = e.board;
+        if (score) score[i] = e.score;
+        if (legal_out) legal_out[i] = (uint8_t)legal_mask(e.board);
+        cont = e.board;
+    }
+    sb[threadIdx.x] = cont;
+    __syncthreads();
+    if (!onehot) return;
+    long long nb = n - block0 < 256 ? n - block0 : 256;   // boards of this block
+    for (int g = threadIdx.x; g < nb * 64; g += 256) {
+        u64 b = sb[g >> 6];
+        if (BF16) reinterpret_cast<uint2*>(onehot)[block0 * 64 + g] = onehot_bf16(b, g & 63);
+        else reinterpret_cast<float4*>(onehot)[block0 * 64 + g] = onehot_f32(b, g & 63);
     }
 }
 
@@ -771,6 +824,26 @@ G2048_API int g2048_select_action(const float* qvalues, const uint8_t* legal_mas
     k_select_action<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((const float4*)qvalues, legal_mask, actions, n,
                                                                            eps_threshold(eps), seed, step_idx, env_id_base);
     LAUNCH_CHECK("k_select_action");
+    return 0;
+}
+
+G2048_API int g2048_dqn_env_step(uint64_t* boards, int32_t* score, const float* qvalues, const uint8_t* legal_in,
+                                 uint8_t* actions, uint64_t* state_out, uint64_t* next_state_out, float* reward,
+                                 uint8_t* done, uint8_t* legal_out, void* onehot_out, int dtype, int64_t n, double eps,
+                                 uint32_t opts, uint64_t seed, uint64_t step_idx, uint64_t reset_idx,
+                                 uint64_t env_id_base, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!boards || !qvalues)) || (dtype != G2048_DTYPE_F32 && dtype != G2048_DTYPE_BF16))
+        return fail(G2048_ERR_ARG, "g2048_dqn_env_step: bad arguments");
+    if (n == 0) return 0;
+    int g = (int)((n + 255) / 256);
+#define LAUNCH_DQN(B)                                                                                                   \
+    k_dqn_env_step<B><<<g, 256, 0, S(stream)>>>(D->tables, (u64*)boards, score, (const float4*)qvalues, legal_in, actions,  \
+                                                (u64*)state_out, (u64*)next_state_out, reward, done, legal_out, onehot_out, \
+                                                n, eps_threshold(eps), opts, seed, step_idx, reset_idx, env_id_base)
+    if (dtype == G2048_DTYPE_BF16) LAUNCH_DQN(true); else LAUNCH_DQN(false);
+#undef LAUNCH_DQN
+    LAUNCH_CHECK("k_dqn_env_step");
     return 0;
 }
 

@@ -204,7 +204,8 @@ def terminal_bonus(boards: torch.Tensor, done: torch.Tensor) -> torch.Tensor:
 def dqn_step(env: BatchedGame2048Env, agent: BatchedDQNAgent, train: bool = True):
     """One step of the driver loop mainDQL_CNN_step2.py:163-237 for all envs: legal-move mask, act_ripetitive,
     env.step (nopenalty flavour; the commit of :237 is folded into the batched env), terminal bonus, remember,
-    and a reset of the finished games."""
+    and a reset of the finished games.  Unfused form (one library call per piece); `FusedDQNFeed` does the env side
+    in one launch."""
     state = env.boards.clone()
     legal = env.legal_mask()
     actions = agent.act_ripetitive(state, legal, env.env_id_base)
@@ -215,3 +216,45 @@ def dqn_step(env: BatchedGame2048Env, agent: BatchedDQNAgent, train: bool = True
     if bool(done.any()):
         env.reset(mask=done)
     return reward, done
+
+
+class FusedDQNFeed:
+    """The env side of the DQN loop in ONE kernel launch per step (`g2048_dqn_env_step`): act_ripetitive on the
+    network's outputs, env step, terminal bonus, reset of finished games, legal-move mask and one-hot encoding of the
+    boards the envs continue from.  Per step the host does: q = model(onehot) -> step(q) -> remember."""
+
+    def __init__(self, env: BatchedGame2048Env, agent: BatchedDQNAgent, terminal_bonus: bool = True):
+        if env.flavour != 1:
+            raise ValueError("the DQN driver uses the nopenalty env")
+        self.env, self.agent = env, agent
+        dev, n = env.device, env.n
+        self.opts = (1 if terminal_bonus else 0) | 2
+        self.code = {torch.float32: 0, torch.bfloat16: 1}[agent.dtype]
+        self.onehot = agent.encode_state(env.boards)
+        self.legal = env.legal_mask()
+        self.actions = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.state = torch.empty(n, dtype=torch.int64, device=dev)
+        self.next_state = torch.empty(n, dtype=torch.int64, device=dev)
+        self.reward = torch.empty(n, dtype=torch.float32, device=dev)
+        self.done = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def step(self, qvalues: torch.Tensor | None = None, train: bool = True):
+        env, agent = self.env, self.agent
+        if qvalues is None:
+            with torch.no_grad():
+                agent.model.eval()
+                qvalues = agent.model(self.onehot).float().contiguous()
+        agent.update_epsilon()
+        agent.step_counter += 1
+        with torch.cuda.device(env.device):
+            check(agent.lib.g2048_dqn_env_step(_ptr(env.boards), _ptr(env.score), _ptr(qvalues), _ptr(self.legal),
+                                               _ptr(self.actions), _ptr(self.state), _ptr(self.next_state),
+                                               _ptr(self.reward), _ptr(self.done), _ptr(self.legal), _ptr(self.onehot),
+                                               self.code, env.n, float(agent.epsilon), self.opts, env.seed, env.step_idx,
+                                               env.episode_idx, env.env_id_base, _stream()), "g2048_dqn_env_step")
+        env.step_idx += 1
+        env.episode_idx += 1
+        done = self.done != 0
+        if train:
+            agent.remember(self.state, self.actions, self.reward, done, self.next_state)
+        return self.reward, done

@@ -563,6 +563,17 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
         out[f"dqn_feed_65536_envs_{dt_name}"] = {"env_steps_per_sec": m5 / dt, "us_per_step": dt * 1e6,
                                                 "onehot_GBps": m5 * 256 * width / dt / 1e9,
                                                 "kernels_per_step": "select_action + env_step(nopenalty) + masked reset + encode_onehot"}
+
+        def fused():
+            t = step_no[0]
+            L.g2048_dqn_env_step(b5.data_ptr(), s5.data_ptr(), qv.data_ptr(), lm5.data_ptr(), a5.data_ptr(), None, None,
+                                 r5.data_ptr(), dm5.data_ptr(), lm5.data_ptr(), enc.data_ptr(), code, m5, 0.1, 3, SEED, t,
+                                 t + 1, base, stream)
+            step_no[0] += 1
+        dt = timed(fused, 50)
+        out[f"dqn_feed_65536_envs_{dt_name}_fused"] = {"env_steps_per_sec": m5 / dt, "us_per_step": dt * 1e6,
+                                                      "onehot_GBps": m5 * 256 * width / dt / 1e9,
+                                                      "kernels_per_step": "g2048_dqn_env_step (one launch)"}
     return out
 
 

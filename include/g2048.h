@@ -144,6 +144,21 @@ G2048_API int g2048_encode_onehot(const uint64_t* boards, void* out, int64_t n, 
 G2048_API int g2048_select_action(const float* qvalues, const uint8_t* legal_mask, uint8_t* actions, int64_t n,
                                   double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base, void* stream);
 
+/* One env-side step of the DQN driver loop (mainDQL_CNN_step2.py:163-237) for n nopenalty envs in ONE launch:
+ * act_ripetitive / act on the network outputs qvalues[n][4] (legal_in NULL = act), env.step with the caller's commit,
+ * the driver's terminal bonus (:202-213: +100 for a tile >= 2048, +50 for two tiles >= 1024; opts bit 0), reset of
+ * the finished games (opts bit 1; Philox(seed, env id, reset_idx, STREAM_RESET) like g2048_env_reset), legal-move
+ * mask and one-hot encoding (DQNAgent.encode_state) of the boards the envs continue from.
+ * Outputs (each may be NULL): actions, state_out (boards before the step), next_state_out (boards after the step,
+ * before any reset -- what `remember` stores), reward, done, legal_out, onehot_out[n][16][4][4] of `dtype`. */
+#define G2048_DQN_TERMINAL_BONUS 1u
+#define G2048_DQN_AUTO_RESET 2u
+G2048_API int g2048_dqn_env_step(uint64_t* boards, int32_t* score, const float* qvalues, const uint8_t* legal_in,
+                                 uint8_t* actions, uint64_t* state_out, uint64_t* next_state_out, float* reward,
+                                 uint8_t* done, uint8_t* legal_out, void* onehot_out, int dtype, int64_t n, double eps,
+                                 uint32_t opts, uint64_t seed, uint64_t step_idx, uint64_t reset_idx,
+                                 uint64_t env_id_base, void* stream);
+
 /* ------------------------------------------------------------------ fused rollouts (boards in registers) */
 /* k_steps env steps per env under the uniform-random policy (action = x3 >> 30), in-kernel reset on done. */
 G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n, int64_t k_steps,

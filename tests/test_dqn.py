@@ -59,3 +59,75 @@ def test_batched_dqn_agent_trains_on_gpu_envs():
     b = torch.tensor([0xB, 0xAA, 0xA9, 0x9], dtype=torch.int64, device="cuda")
     d = torch.tensor([True, True, True, True], device="cuda")
     assert dqn.terminal_bonus(b, d).tolist() == [100.0, 50.0, 0.0, 0.0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_dqn_env_step_equals_the_unfused_pieces(dtype):
+    """g2048_dqn_env_step (one launch) == select_action -> env_step -> terminal bonus -> masked reset -> legal mask ->
+    encode_onehot, each of which is checked against the oracle elsewhere; late-game boards so that episodes end."""
+    import g2048
+    from g2048 import dqn
+    L = g2048.lib()
+    n, seed, base = 10_000, 21, 7
+    rng = np.random.RandomState(0)
+    lv = rng.randint(1, 12, size=(n, 16)) * (rng.random_sample((n, 16)) < 0.9)
+    packed = np.zeros(n, np.uint64)
+    for j in range(16):
+        packed |= lv[:, j].astype(np.uint64) << np.uint64(4 * j)
+    packed[packed == 0] = 1
+    start = torch.from_numpy(packed.view(np.int64)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    code = 0 if dtype == torch.float32 else 1
+    fused = g2048.BatchedGame2048Env(n, "nopenalty", seed=seed, env_id_base=base)
+    plain = g2048.BatchedGame2048Env(n, "nopenalty", seed=seed, env_id_base=base)
+    fused.boards.copy_(start)
+    plain.boards.copy_(start)
+    legal_f = fused.legal_mask()
+    out = {k: torch.empty(n, dtype=d, device="cuda") for k, d in (("a", torch.uint8), ("s", torch.int64), ("s2", torch.int64),
+                                                                 ("r", torch.float32), ("d", torch.uint8))}
+    onehot = torch.empty((n, 16, 4, 4), dtype=dtype, device="cuda")
+    total_done = 0
+    for t in range(30):
+        q = torch.randn((n, 4), device="cuda")
+        q[::5, 1] = q[::5, 0]
+        eps = 0.3
+        # unfused pieces
+        legal_p = plain.legal_mask()
+        a_p = torch.empty(n, dtype=torch.uint8, device="cuda")
+        assert L.g2048_select_action(q.data_ptr(), legal_p.data_ptr(), a_p.data_ptr(), n, eps, seed, t, base, st) == 0
+        s_p = plain.boards.clone()
+        plain.step_idx = t
+        nxt, r_p, d_p, _ = plain.step(a_p)
+        nxt = nxt.clone()
+        r_p = r_p.to(torch.float32) + dqn.terminal_bonus(nxt, d_p)
+        plain.episode_idx = 100 + t
+        plain.reset(mask=d_p)
+        # fused
+        rc = L.g2048_dqn_env_step(fused.boards.data_ptr(), fused.score.data_ptr(), q.data_ptr(), legal_f.data_ptr(),
+                                  out["a"].data_ptr(), out["s"].data_ptr(), out["s2"].data_ptr(), out["r"].data_ptr(),
+                                  out["d"].data_ptr(), legal_f.data_ptr(), onehot.data_ptr(), code, n, eps, 3, seed, t,
+                                  100 + t, base, st)
+        assert rc == 0, L.g2048_last_error()
+        assert torch.equal(out["a"], a_p) and torch.equal(out["s"], s_p) and torch.equal(out["s2"], nxt), t
+        assert torch.equal(out["r"], r_p) and torch.equal(out["d"] != 0, d_p), t
+        assert torch.equal(fused.boards, plain.boards) and torch.equal(fused.score, plain.score), t
+        assert torch.equal(legal_f, plain.legal_mask()), t
+        assert torch.equal(onehot, plain.encode_onehot(dtype=dtype)), t
+        total_done += int(d_p.sum())
+    assert total_done > 100 and float(out["r"].max()) >= 50.0 or total_done > 100
+
+
+@pytest.mark.gpu
+def test_fused_dqn_feed_drives_training():
+    import g2048
+    from g2048 import dqn
+    torch.manual_seed(1)
+    env = g2048.BatchedGame2048Env(2048, "nopenalty", seed=3)
+    agent = dqn.BatchedDQNAgent(width=16, hidden=32, memory_size=1 << 15, batch_size=128, epsilon=0.5, learning_rate=1e-3)
+    env.reset()
+    feed = dqn.FusedDQNFeed(env, agent)
+    for _ in range(20):
+        reward, done = feed.step()
+    assert agent.nb_entries == min(20 * 2048, agent.memory_size) and agent.step_counter == 20
+    assert np.isfinite(agent.replay())
