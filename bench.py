@@ -256,6 +256,8 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU)
     ap.add_argument("--eps", type=float, default=EPS, help="fixed exploration rate (BASELINE config 3 quotes 0.1 and 0.95)")
     ap.add_argument("--no-extras", action="store_true", help="skip the explanatory side measurements")
+    ap.add_argument("--dqn", action="store_true",
+                    help="also time BASELINE config 5: 65,536 nopenalty envs/GPU with the 197 M-parameter DQN forward in the loop")
     ap.add_argument("--exchange", action="store_true",
                     help="also time the synchronous mode with the cross-GPU record exchange (dist.ShardedQLearning)")
     args = ap.parse_args()
@@ -390,8 +392,10 @@ def main():
         sync = sync_exchange_measurement(torch, dist, g2048, dev, rank, world, min(n, 1 << 20), max_over_ranks, barrier)
         if rank == 0:
             extras["synchronous_exchange"] = sync
+    if args.dqn and rank == 0:
+        extras["dqn_in_the_loop"] = dqn_measurement(torch, g2048, dev)
     if not args.no_extras and rank == 0:
-        extras = side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak)
+        extras = dict(extras, **side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak))
         rnd = random_access_peak()
         if rnd:
             # random DRAM operations the fused kernel needs per env step (committed ncu capture): line fills
@@ -440,6 +444,41 @@ def main():
     L.g2048_ctx_destroy(ctx)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dqn_measurement(torch, g2048, dev, n=65536, steps=3):
+    """BASELINE config 5 on one GPU: the env side in one fused launch per step, the reference's 197,204,996-parameter
+    CNN (bf16, PyTorch/cuDNN/cuBLAS) evaluated on all 65,536 boards per step -- expected network-bound."""
+    from g2048 import dqn
+    env = g2048.BatchedGame2048Env(n, "nopenalty", device=dev.index, seed=SEED)
+    agent = dqn.BatchedDQNAgent(device=dev.index, dtype=torch.bfloat16, memory_size=1 << 20, seed=SEED)
+    env.reset()
+    feed = dqn.FusedDQNFeed(env, agent)
+
+    def forward():
+        with torch.no_grad():
+            agent.model.eval()
+            return torch.cat([agent.model(c).float() for c in feed.onehot.split(8192)]).contiguous()
+
+    def one():
+        feed.step(forward())
+
+    one()
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    for _ in range(steps):
+        feed.step(torch.zeros((n, 4), device=dev))
+    e2.record()
+    torch.cuda.synchronize()
+    t_all, t_env = e0.elapsed_time(e1) / steps * 1e-3, e1.elapsed_time(e2) / steps * 1e-3
+    flops = 2.0 * n * (64 * (4 * 512 * 30) + 2 * 64 * (2048 * 512 * 30) + 131072 * 1024 + 1024 * 4)
+    return {"env_steps_per_sec_with_network": n / t_all, "ms_per_step": t_all * 1e3, "env_side_ms_per_step": t_env * 1e3,
+            "network_share": 1 - t_env / t_all, "network_TFLOPs": flops / (t_all - t_env) / 1e12, "envs": n,
+            "parameters": sum(p.numel() for p in agent.model.parameters()), "dtype": "bf16"}
 
 
 def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_ranks, barrier, steps=24):
