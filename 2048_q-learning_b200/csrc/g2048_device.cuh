@@ -318,19 +318,18 @@ template <bool REPLAY>
 __device__ __forceinline__ void nopenalty_step(Env& e, int a, u32 d0, u32 d1, u32 q0, u32 q1, const Lut& L, StepOut& o) {
     u64 S = e.board;
     Moved m = do_move(S, a, L);                                  // :53-66
-    bool valid = m.moved;
-    int ms = m.score, lvl = max(e.maxlvl, m.hi_level);
-    u64 M = m.board;
-    if (valid) M = spawn<REPLAY>(M, d0, d1, lvl);
-    bool game_over = false;
-    if (nzmask(S) == kNib1) {                                    // :68-78, evaluated on S
+    bool valid = m.moved, game_over = false;
+    int ms = m.score, lvl = e.maxlvl;
+    u64 M = S;
+    if (nzmask(S) != kNib1) {                                    // S has an empty cell: is_game_over is False (:69)
+        if (valid) { lvl = max(lvl, m.hi_level); M = spawn<REPLAY>(m.board, d0, d1, lvl); }
+    } else {                                                     // :70-78, evaluated on S; the agent's own result is discarded
         u32 lm = legal_mask(S);
-        lvl = e.maxlvl;
         if (lm == 0) {
             game_over = true;
-            M = S;
         } else {
-            Moved m2 = do_move(S, __ffs((int)lm) - 1, L);
+            int a2 = __ffs((int)lm) - 1;
+            Moved m2 = (a2 == a) ? m : do_move(S, a2, L);
             lvl = max(lvl, m2.hi_level);
             M = spawn<REPLAY>(m2.board, q0, q1, lvl);
         }
@@ -343,20 +342,14 @@ __device__ __forceinline__ void nopenalty_step(Env& e, int a, u32 d0, u32 d1, u3
     o.valid = valid; o.game_over = game_over; o.done = game_over; // :117-118
 }
 
-// one env step with Philox draws x (STREAM_STEP); the nopenalty quirk spawn draws its own stream
+// one env step with Philox draws x (STREAM_STEP).  The nopenalty full-board spawn reuses x0, x1: in that case the
+// spawn of the agent's own move is discarded, so those two draws are otherwise unused and the joint distribution
+// is the reference's (which draws fresh numbers there).
 template <int FLAVOUR>
 __device__ __forceinline__ void philox_step(Env& e, int a, const Draw4& x, u64 seed, u64 env_id, u64 t, const Lut& L,
                                             const Tables& T, StepOut& o) {
-    if (FLAVOUR == G2048_FLAVOUR_PENALTY) {
-        penalty_step<false>(e, a, x.x0, x.x1, L, T, o);
-    } else {
-        u32 q0 = 0, q1 = 0;
-        if (nzmask(e.board) == kNib1) {
-            Draw4 y = philox(seed, env_id, t, G2048_STREAM_QUIRK);
-            q0 = y.x0; q1 = y.x1;
-        }
-        nopenalty_step<false>(e, a, x.x0, x.x1, q0, q1, L, o);
-    }
+    if (FLAVOUR == G2048_FLAVOUR_PENALTY) penalty_step<false>(e, a, x.x0, x.x1, L, T, o);
+    else nopenalty_step<false>(e, a, x.x0, x.x1, x.x0, x.x1, L, o);
 }
 __device__ __forceinline__ void philox_autoreset(Env& e, u64 seed, u64 env_id, u64 t) {
     Draw4 y = philox(seed, env_id, t, G2048_STREAM_AUTORESET);

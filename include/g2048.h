@@ -61,7 +61,7 @@
 /* Philox streams: counter = (env id, step, stream), key = seed */
 #define G2048_STREAM_STEP 0       /* x0,x1 spawn of the move; x2 epsilon test; x3 random action */
 #define G2048_STREAM_RESET 1      /* explicit env_reset: x0..x3 = the two spawns */
-#define G2048_STREAM_QUIRK 2      /* ENV-N full-board spawn */
+#define G2048_STREAM_QUIRK 2      /* reserved (the ENV-N full-board spawn reuses the step's x0, x1) */
 #define G2048_STREAM_AUTORESET 3  /* in-rollout reset after done */
 
 /* counters (int64[G2048_N_COUNTERS], accumulated with atomics; the caller zeroes them) */

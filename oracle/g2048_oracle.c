@@ -360,10 +360,11 @@ static void reset_env(env_t *e, int ka, int fa, int kb, int fb) {
 
 /* One env step with Philox draws: x = draws(STREAM_STEP) supplies the spawn of
  * the agent's move (x[0] -> cell, x[1] -> 2/4); the nopenalty full-board quirk
- * spawn takes y = draws(STREAM_QUIRK).  The spawn cell index is
+ * spawn reuses the same two draws.  The spawn cell index is
  * floor(x * n_empty / 2^32) with n_empty counted on the moved board. */
 static void philox_env_step(env_t *e, int a, int flavour, uint64_t seed, uint64_t env_id, uint64_t t,
                             const uint32_t x[4], out_t *o) {
+    (void)seed; (void)env_id; (void)t;
     int k1, f1, k2 = 0, f2 = 0;
     uint64_t tb = e->board; int64_t s = 0;
     move_nospawn(&tb, a, &s);
@@ -371,14 +372,14 @@ static void philox_env_step(env_t *e, int a, int flavour, uint64_t seed, uint64_
     k1 = ne ? draw_k(x[0], ne) : 0;
     f1 = x[1] >= IS4_THRESH;
     if (flavour == FLAVOUR_NOPENALTY && count_empty(e->board) == 0) {
-        uint32_t y[4];
-        draws(seed, env_id, t, STREAM_QUIRK, y);
+        /* full-board quirk spawn: the spawn of the agent's own move is discarded in this case, so its two draws
+         * x[0], x[1] are reused here (same joint distribution as the reference's fresh draws) */
         for (int a2 = 0; a2 < 4; ++a2) {
             uint64_t t2 = e->board; int64_t s2 = 0;
             if (move_nospawn(&t2, a2, &s2)) {
                 int ne2 = count_empty(t2);
-                k2 = ne2 ? draw_k(y[0], ne2) : 0;
-                f2 = y[1] >= IS4_THRESH;
+                k2 = ne2 ? draw_k(x[0], ne2) : 0;
+                f2 = x[1] >= IS4_THRESH;
                 break;
             }
         }
