@@ -166,9 +166,11 @@ G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* sco
                                    int64_t* counters, void* stream);
 
 /* The loop of main.py:91-101 for n envs and k_steps steps each, fused: epsilon-greedy choose_action
- * (main.py:34-38) -> env step -> update_q_value (main.py:40-43) on the HBM hash table, asynchronously
- * (each env applies q <- q + lr (target - q) at once as an atomic read-modify-write; N = 1 is the reference's
- * sequential order). */
+ * (main.py:34-38) -> env step -> update_q_value (main.py:40-43) on the HBM hash table, asynchronously:
+ * each env applies q <- q + lr (target - q) at once with ONE atomic compare-and-swap from the value it read; if
+ * another env changed that Q value in between, the update is skipped and counted in counters[G2048_C_LOST]
+ * (nothing stale is ever summed, no thread spins).  With one env nothing is lost: N = 1 is exactly the
+ * reference's sequential order.  Envs that finish (done) are reset in place (STREAM_AUTORESET). */
 G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
                                    int64_t n, int64_t k_steps, int flavour, float lr, float gamma, double eps,
                                    uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t* counters,
