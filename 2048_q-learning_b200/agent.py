@@ -22,8 +22,8 @@ class BatchedQLearningAgent:
                  capacity: int = 1 << 24, device: int | torch.device = 0, seed: int = 0x2048):
         if action_space != 4:
             raise ValueError("the 2048 Q-table has 4 actions per state")
-        if capacity & (capacity - 1) or capacity > (1 << 32):
-            raise ValueError("capacity must be a power of two <= 2^32")
+        if capacity & (capacity - 1) or capacity > (1 << 31):
+            raise ValueError("capacity must be a power of two <= 2^31")
         dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         if dev.type != "cuda":
             raise _lib.G2048Error("BatchedQLearningAgent needs a CUDA device (no CPU fallback)")

@@ -150,7 +150,7 @@ inline u64 eps_threshold(double eps) {
     if (eps >= 1) return 1ull << 32;
     return (u64)(eps * 4294967296.0);
 }
-inline bool pow2(uint64_t c) { return c && !(c & (c - 1)); }
+inline bool pow2(uint64_t c) { return c && !(c & (c - 1)) && c <= (1ull << 31); }   // table capacity: 2^k <= 2^31 slots
 
 }  // namespace
 
@@ -890,7 +890,7 @@ G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* sco
                                    uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t* counters,
                                    void* stream) {
     DEVSTATE();
-    if (n < 0 || k_steps < 0 || (n && !boards) || !table || !pow2(capacity) || capacity > (1ull << 32) ||
+    if (n < 0 || k_steps < 0 || (n && !boards) || !table || !pow2(capacity) || capacity > (1ull << 31) ||
         (flavour != 0 && flavour != 1))
         return fail(G2048_ERR_ARG, "g2048_rollout_qlearn: bad arguments");
     if (n == 0 || k_steps == 0) return 0;
@@ -968,7 +968,7 @@ G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score,
                                 uint64_t* rec_key, uint8_t* rec_action, float* rec_target, void* scratch,
                                 size_t scratch_bytes_, void* stream) {
     DEVSTATE();
-    if (n < 0 || (n && !boards) || !table || !pow2(capacity) || capacity > (1ull << 32) ||
+    if (n < 0 || (n && !boards) || !table || !pow2(capacity) || capacity > (1ull << 31) ||
         (flavour != 0 && flavour != 1) || (mode != 0 && mode != 1))
         return fail(G2048_ERR_ARG, "g2048_qlearn_step: bad arguments");
     if (n == 0) return 0;
@@ -1022,7 +1022,7 @@ G2048_API int g2048_qtable_update(void* table, uint64_t capacity, const uint64_t
                                   const uint64_t* s2, const uint8_t* done, int64_t n, float lr, float gamma, int mode,
                                   void* scratch, size_t scratch_bytes_, void* stream) {
     DEVSTATE();
-    if (n < 0 || !table || !pow2(capacity) || capacity > (1ull << 32) || (n && (!s || !a || !r || !s2 || !done)) ||
+    if (n < 0 || !table || !pow2(capacity) || capacity > (1ull << 31) || (n && (!s || !a || !r || !s2 || !done)) ||
         (mode != 0 && mode != 1))
         return fail(G2048_ERR_ARG, "g2048_qtable_update: bad arguments");
     if (n == 0) return 0;
@@ -1039,7 +1039,7 @@ G2048_API int g2048_qtable_apply_targets(void* table, uint64_t capacity, const u
                                          const float* target, int64_t n, float lr, int mode, void* scratch,
                                          size_t scratch_bytes_, void* stream) {
     DEVSTATE();
-    if (n < 0 || !table || !pow2(capacity) || capacity > (1ull << 32) || (n && (!keys || !a || !target)) ||
+    if (n < 0 || !table || !pow2(capacity) || capacity > (1ull << 31) || (n && (!keys || !a || !target)) ||
         (mode != 0 && mode != 1))
         return fail(G2048_ERR_ARG, "g2048_qtable_apply_targets: bad arguments");
     if (n == 0) return 0;

@@ -190,7 +190,8 @@ G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score,
                                 size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------ Q-table (device pointers) */
-/* QLearningAgent.q_table (main.py:16): `table` is capacity * 32 bytes of device memory, capacity = 2^k. */
+/* QLearningAgent.q_table (main.py:16): `table` is capacity * 32 bytes of device memory, 32-byte aligned,
+ * capacity = 2^k <= 2^31 slots (64 GiB). */
 G2048_API size_t g2048_qtable_bytes(uint64_t capacity);
 G2048_API int g2048_qtable_clear(void* table, uint64_t capacity, void* stream);
 /* q_table[state] for n states -> rows[n][4]; found[n] (may be NULL); insert != 0 creates missing zero rows
