@@ -549,6 +549,22 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
     gbs = n * ALGO_BYTES_SINGLE_STEP / dt / 1e9
     out["single_step_env_api"] = {"env_steps_per_sec": n / dt, "achieved_GBps_at_38B": gbs, "frac_of_hbm_peak": gbs / peak,
                                   "note": f"{n} envs = {n * 38 / 1e6:.0f} MB per call, L2-resident"}
+    # (b2) the same at 2^24 envs: 640 MB of state per call, far beyond L2 -- the HBM-resident case
+    nb = 1 << 24
+    bb = torch.zeros(nb, dtype=torch.int64, device=dev)
+    ab = torch.full((nb,), 0x000000000000FF01, dtype=torch.int64, device=dev)
+    sb = torch.zeros(nb, dtype=torch.int32, device=dev)
+    L.g2048_env_reset(bb.data_ptr(), sb.data_ptr(), None, None, nb, SEED, 0, base, stream)
+    actb = torch.randint(0, 4, (nb,), dtype=torch.uint8, device=dev)
+    rb = torch.zeros(nb, dtype=torch.float64, device=dev)
+    fb = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    mb = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    dt = timed(lambda: L.g2048_env_step(bb.data_ptr(), ab.data_ptr(), sb.data_ptr(), actb.data_ptr(), None, rb.data_ptr(),
+                                        None, fb.data_ptr(), mb.data_ptr(), None, nb, 0, SEED, 1, base, stream), 10)
+    gbs = nb * ALGO_BYTES_SINGLE_STEP / dt / 1e9
+    out["single_step_env_api_16M_envs"] = {"env_steps_per_sec": nb / dt, "achieved_GBps_at_38B": gbs,
+                                           "frac_of_hbm_peak": gbs / peak, "note": "640 MB of env state per call (HBM-resident)"}
+    del bb, ab, sb, actb, rb, fb, mb
     # (c) stand-alone batched update on random transitions over a pre-filled table (HBM bound: 40 B/update)
     m = 1 << 22
     L.g2048_ctx_qtable_clear(ctx)
