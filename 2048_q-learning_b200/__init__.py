@@ -6,7 +6,7 @@ reference's Python interfaces.  `import g2048` (repo root) is an importable alia
 """
 from ._lib import G2048Error, build, declared_symbols, init, lib  # noqa: F401
 from .compat import Game2048, Game2048_env, QLearningAgent, pack_tiles, unpack_tiles  # noqa: F401
-from .train import evaluate_tabular, train_tabular, train_tabular_batched  # noqa: F401
+from .train import evaluate_tabular, train_dqn, train_tabular, train_tabular_batched  # noqa: F401
 
 
 def __getattr__(name):  # the batched classes need torch: import lazily
@@ -19,7 +19,7 @@ def __getattr__(name):  # the batched classes need torch: import lazily
     if name in ("BatchedDQNAgent", "DQNModel", "dqn_step", "terminal_bonus", "FusedDQNFeed"):
         from . import dqn
         return getattr(dqn, name)
-    if name in ("ShardedQLearning", "shard_range"):
+    if name in ("ShardedQLearning", "shard_range", "PeerRecordBuffers", "TorchEngine", "GradientAllReduce"):
         from . import dist
         return getattr(dist, name)
     raise AttributeError(name)

@@ -115,6 +115,33 @@ class BatchedQLearningAgent:
         env.step_idx += 1
         return (rk, ra, rd) if records else None
 
+    def emit_records(self, env: BatchedGame2048Env, records) -> None:
+        """Synchronous step, exchange form: advance every env and write its packed 16-byte (state, action, target)
+        record to `records` (an int64[n, 2] tensor or a raw device pointer, e.g. NVLink peer memory); the table's
+        values stay untouched until `apply_records`."""
+        ptr = records if isinstance(records, int) else _ptr(records)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_qlearn_emit(_ptr(env.boards), _ptr(env.aux), _ptr(env.score), _ptr(self.table),
+                                             self.capacity, env.n, env.flavour, self.gamma, float(self.epsilon), env.seed,
+                                             env.step_idx, env.env_id_base, _ptr(env.counters), ptr, _stream()),
+                  "g2048_qlearn_emit")
+        env.step_idx += 1
+
+    def apply_records(self, lists, counts, mode: str = "deterministic", lr: float | None = None) -> None:
+        """Apply record lists in order (tensors or raw device pointers, local or peer memory): the gather of the
+        exchange step is fused into the kernel that looks the states up."""
+        import ctypes
+        ptrs = [(x if isinstance(x, int) else _ptr(x)) or 0 for x in lists]
+        m = len(ptrs)
+        arr_p = (ctypes.c_void_p * m)(*ptrs)
+        arr_n = (ctypes.c_int64 * m)(*[int(c) for c in counts])
+        n = int(sum(counts))
+        with torch.cuda.device(self.device):
+            sc = self._scratch_for(max(n, 1))
+            check(self.lib.g2048_qtable_apply_records(_ptr(self.table), self.capacity, arr_p, arr_n, m,
+                                                      self.lr if lr is None else lr, MODES[mode], _ptr(sc), sc.numel(),
+                                                      _stream()), "g2048_qtable_apply_records")
+
     # ---- table management ------------------------------------------------------------------------
     def clear(self):
         self.table.zero_()

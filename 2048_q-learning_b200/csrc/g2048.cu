@@ -379,7 +379,7 @@ template <int FLAVOUR>
 __global__ void __launch_bounds__(256)
 k_qlearn_phase_a(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mask, long long n, float lr, float gamma,
                  u64 eps_thresh, u64 seed, u64 t, u64 id_base, long long* counters, u64* sortkey, float* target_out,
-                 u64* rec_key, uint8_t* rec_action, float* rec_target) {
+                 u64* rec_key, uint8_t* rec_action, float* rec_target, ulonglong2* rec_packed) {
     Lut L = global_lut(T);
     Counters c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -403,6 +403,7 @@ k_qlearn_phase_a(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
         if (rec_key) rec_key[i] = s_key;
         if (rec_action) rec_action[i] = (uint8_t)a;
         if (rec_target) rec_target[i] = target;
+        if (rec_packed) rec_packed[i] = pack_record(s_key, a, target);
         if (o.done) philox_autoreset(e, seed, id, t);
         boards[i] = e.board;
         if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
@@ -435,6 +436,55 @@ k_keys_to_records(Slot* tab, u64 mask, const u64* keys, const uint8_t* a, long l
         sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)(a[i] & 3));
     }
 }
+// ---- record lists that may live in the HBM of OTHER GPUs (NVLink peer memory) ---------------------------------
+// Up to kMaxLists lists of 16-byte records {key, action | target bits << 32}; list j holds the records of rank j in
+// ascending env order, so walking the lists in order visits ascending GLOBAL env ids.
+struct RecordLists {
+    const ulonglong2* ptr[G2048_MAX_PEERS];
+    long long end[G2048_MAX_PEERS];   // exclusive prefix ends
+    int n_lists;
+};
+// The all-gather fused into its consumer: every rank pulls each record straight out of its owner's memory
+// (system-scope loads, never cached in L1), finds-or-inserts the state in ITS replica and writes the sort key +
+// target for the deterministic apply.  Consecutive threads read consecutive records: 512 B per warp over NVLink.
+__global__ void __launch_bounds__(256)
+k_peer_records_to_sortkeys(Slot* tab, u64 mask, RecordLists R, long long n, u64* sortkey, float* target) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (j + 1 < R.n_lists && i >= R.end[j]) ++j;
+        long long local = i - (j ? R.end[j - 1] : 0);
+        u64 key, at;
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(key), "=l"(at) : "l"(R.ptr[j] + local) : "memory");
+        float4 row;
+        u32 ins = 0;
+        u32 slot = table_find<true>(tab, mask, key, row, ins);
+        sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (at & 3));
+        target[i] = __uint_as_float((u32)(at >> 32));
+    }
+}
+// Barrier between the GPUs of one box through flags in peer memory: rank r stores `epoch` into flags[r] of every
+// peer (release, system scope) and waits until all of its own flags reached `epoch` (acquire).  Epochs only grow,
+// so the flags never need a reset.  A peer that never arrives is reported after `timeout_ns` instead of hanging.
+struct PeerFlags { u64* ptr[G2048_MAX_PEERS]; };
+__global__ void k_peer_barrier(PeerFlags F, int rank, int world, u64 epoch, u64 timeout_ns, int* timed_out) {
+    int t = threadIdx.x;
+    if (t >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.ptr[t] + rank), "l"(epoch) : "memory");
+    u64 t0, now, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(F.ptr[rank] + t) : "memory");
+        if (v >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) {
+            if (timed_out) atomicExch(timed_out, 1 + t);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_apply_atomic(Slot* tab, const u64* sortkey, const float* target, float lr, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -982,11 +1032,105 @@ G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score,
     k_qlearn_phase_a<F><<<g, 256, 0, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table, capacity - 1, \
                                                   n, lr, gamma, eps_threshold(eps), seed, step_idx, env_id_base,      \
                                                   (long long*)counters, s.key_in, s.val_in, (u64*)rec_key, rec_action, \
-                                                  rec_target)
+                                                  rec_target, nullptr)
     if (flavour == 0) PHASE_A(0); else PHASE_A(1);
 #undef PHASE_A
     LAUNCH_CHECK("k_qlearn_phase_a");
     if (apply) return apply_records(D, (Slot*)table, capacity, s, n, lr, mode, S(stream));
+    return 0;
+}
+
+// ---- synchronous step, exchange form: emit packed records / apply record lists (local or peer memory)
+G2048_API int g2048_qlearn_emit(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
+                                int64_t n, int flavour, float gamma, double eps, uint64_t seed, uint64_t step_idx,
+                                uint64_t env_id_base, int64_t* counters, g2048_record* records, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!boards || !records)) || !table || !pow2(capacity) || capacity > (1ull << 31) ||
+        (flavour != 0 && flavour != 1) || ((uintptr_t)records & 15))
+        return fail(G2048_ERR_ARG, "g2048_qlearn_emit: bad arguments");
+    if (n == 0) return 0;
+    int g = grid_for(n, 256, D->sm_count);
+#define EMIT(F)                                                                                                        \
+    k_qlearn_phase_a<F><<<g, 256, 0, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table, capacity - 1, \
+                                                  n, 0.f, gamma, eps_threshold(eps), seed, step_idx, env_id_base,      \
+                                                  (long long*)counters, nullptr, nullptr, nullptr, nullptr, nullptr,   \
+                                                  (ulonglong2*)records)
+    if (flavour == 0) EMIT(0); else EMIT(1);
+#undef EMIT
+    LAUNCH_CHECK("k_qlearn_phase_a");
+    return 0;
+}
+
+G2048_API int g2048_qtable_apply_records(void* table, uint64_t capacity, const g2048_record* const* lists,
+                                         const int64_t* counts, int n_lists, float lr, int mode, void* scratch,
+                                         size_t scratch_bytes_, void* stream) {
+    DEVSTATE();
+    if (!table || !pow2(capacity) || capacity > (1ull << 31) || !lists || !counts || n_lists < 1 ||
+        n_lists > G2048_MAX_PEERS || (mode != 0 && mode != 1))
+        return fail(G2048_ERR_ARG, "g2048_qtable_apply_records: bad arguments");
+    RecordLists R{};
+    long long n = 0;
+    for (int j = 0; j < n_lists; ++j) {
+        if (counts[j] < 0 || (counts[j] && !lists[j]) || ((uintptr_t)lists[j] & 15))
+            return fail(G2048_ERR_ARG, "g2048_qtable_apply_records: bad record list");
+        R.ptr[j] = (const ulonglong2*)lists[j];
+        n += counts[j];
+        R.end[j] = n;
+    }
+    R.n_lists = n_lists;
+    if (n == 0) return 0;
+    Scratch sc{};
+    int rc = carve(scratch, scratch_bytes_, n, sc);
+    if (rc) return rc;
+    k_peer_records_to_sortkeys<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((Slot*)table, capacity - 1, R, n,
+                                                                                      sc.key_in, sc.val_in);
+    LAUNCH_CHECK("k_peer_records_to_sortkeys");
+    return apply_records(D, (Slot*)table, capacity, sc, n, lr, mode, S(stream));
+}
+
+// ---- NVLink peer memory between the per-GPU processes of one box (CUDA IPC)
+G2048_API int g2048_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out) {
+    if (!dev_ptr || !ipc_handle_out || bytes == 0) return fail(G2048_ERR_ARG, "g2048_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == G2048_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail((int)e, "g2048_peer_alloc: cudaIpcGetMemHandle");
+    }
+    memcpy(ipc_handle_out, &h, sizeof h);
+    *dev_ptr = p;
+    return 0;
+}
+G2048_API int g2048_peer_open(const void* ipc_handle, void** dev_ptr) {
+    if (!ipc_handle || !dev_ptr) return fail(G2048_ERR_ARG, "g2048_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+G2048_API int g2048_peer_close(void* dev_ptr) {
+    if (dev_ptr) CK(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+G2048_API int g2048_peer_free(void* dev_ptr) {
+    if (dev_ptr) CK(cudaFree(dev_ptr));
+    return 0;
+}
+G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, uint64_t epoch, uint64_t timeout_ns,
+                                 int* timed_out, void* stream) {
+    if (!flags || world < 1 || world > G2048_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(G2048_ERR_ARG, "g2048_peer_barrier: bad arguments");
+    PeerFlags F{};
+    for (int j = 0; j < world; ++j) {
+        if (!flags[j]) return fail(G2048_ERR_ARG, "g2048_peer_barrier: null flag pointer");
+        F.ptr[j] = (u64*)flags[j];
+    }
+    k_peer_barrier<<<1, 32, 0, S(stream)>>>(F, rank, world, epoch, timeout_ns ? timeout_ns : 5000000000ull, timed_out);
+    LAUNCH_CHECK("k_peer_barrier");
     return 0;
 }
 

@@ -453,6 +453,10 @@ __device__ __forceinline__ float td_apply(float q, float lr, float target) {
 // updates of the same (state, action) compose like the reference's sequential loop (a contraction
 // towards the targets) instead of summing stale deltas, which diverges once the number of
 // simultaneous updaters exceeds 2 / lr.  `guess` is the caller's last view of the value.
+// 16-byte exchange record of one transition: {state key, action | float bits of the TD target << 32}
+__device__ __forceinline__ ulonglong2 pack_record(u64 key, int a, float target) {
+    return make_ulonglong2(key, (u64)(a & 3) | ((u64)__float_as_uint(target) << 32));
+}
 __device__ __forceinline__ float q_update_atomic(float* addr, float guess, float lr, float target) {
     u32 assumed = __float_as_uint(guess);
     while (true) {

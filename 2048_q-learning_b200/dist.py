@@ -5,8 +5,13 @@ ids [lo, hi) and its Philox draws are keyed by the GLOBAL env id: results do not
 The Q-table is replicated; the only exchange step is the list of (state key, action, target) records of one
 synchronous step (16 B per transition, fixed size per rank): `all_gather` in rank order = ascending global
 env id, then every replica applies the whole list with the same deterministic kernel (sort by
-(state, action) + segmented sum), so all replicas stay identical and equal to the 1-GPU result.
-NCCL (NVLink 5 / NVSwitch) on GPUs; the same code runs on gloo for the CPU tests with an oracle-backed engine.
+(state, action), then each run applied in order), so all replicas stay identical and equal to the 1-GPU result.
+Two transports on GPUs:
+  "peer"  records are written into CUDA-IPC shared device memory; after a flag barrier in that memory every rank's
+          apply kernel reads each record straight from its owner over NVLink 5 / NVSwitch (gather fused into the
+          lookup kernel, no collective call, no gathered copy) -- `PeerRecordBuffers`;
+  "nccl"  one `all_gather_into_tensor` of the packed 16-byte records, then the same apply kernel on the result.
+The same class runs on gloo for the CPU tests with an oracle-backed engine (plain emit()/apply() protocol).
 
 The fused asynchronous rollout (agent.rollout) has no exchange step: across GPUs it runs as independent
 replicas (DESIGN.md "Multi-GPU": a replicated table cannot scale an exact per-step exchange, every replica
@@ -37,17 +42,107 @@ class TorchEngine:
     def apply(self, keys, actions, targets):
         self.agent.apply_targets(keys, actions, targets, mode="deterministic")
 
+    # packed 16-byte records (g2048_qlearn_emit / g2048_qtable_apply_records)
+    def emit_records(self, records):
+        self.agent.emit_records(self.env, records)
+
+    def apply_records(self, lists, counts):
+        self.agent.apply_records(lists, counts, mode="deterministic")
+
+
+class PeerRecordBuffers:
+    """Per rank one CUDA-IPC allocation [flags: 256 B][records slot 0][records slot 1], mapped by every other rank
+    of the box.  Slots alternate per step, so a rank may write step t+1's records while a slower peer still reads
+    step t's; the flag barrier of step t+1 is what releases slot t for reuse at step t+2."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, lib, device: torch.device, n_max: int, group=None):
+        import ctypes
+        self.lib, self.device, self.n_max, self.group = lib, device, int(n_max), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise ValueError("peer exchange supports up to 16 GPUs of one box")
+        self.slot_bytes = ((self.n_max * 16 + 255) // 256) * 256
+        nbytes = self.FLAG_BYTES + 2 * self.slot_bytes
+        mine, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            self._check(lib.g2048_peer_alloc(nbytes, ctypes.byref(mine), handle), "g2048_peer_alloc")
+            allh = [None] * self.world      # 64-byte handles through the control plane (any backend)
+            dist.all_gather_object(allh, bytes(handle), group=group)
+            self.base, self._opened = [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.base.append(mine.value)
+                    continue
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64)(*allh[r])
+                self._check(lib.g2048_peer_open(buf, ctypes.byref(p)), "g2048_peer_open")
+                self.base.append(p.value)
+                self._opened.append(p.value)
+            self._mine = mine.value
+            self._flags = (ctypes.c_void_p * self.world)(*self.base)
+            self.timed_out = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = 0
+        dist.barrier(group=group)          # every rank has mapped every buffer before anyone signals
+
+    def _check(self, rc, what):
+        from ._lib import check
+        check(rc, what)
+
+    def records(self, rank: int, slot: int) -> int:
+        return self.base[rank] + self.FLAG_BYTES + (slot & 1) * self.slot_bytes
+
+    def barrier(self, timeout_ns: int = 0):
+        """Stream-ordered barrier over all ranks (k_peer_barrier); returns immediately on the host."""
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            self._check(self.lib.g2048_peer_barrier(self._flags, self.rank, self.world, self.epoch, timeout_ns,
+                                                    self.timed_out.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream), "g2048_peer_barrier")
+
+    def check_timeout(self):
+        v = int(self.timed_out.item())
+        if v:
+            raise RuntimeError(f"peer barrier timed out waiting for rank {v - 1}")
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)   # nobody unmaps while a peer may still read
+            for p in self._opened:
+                self.lib.g2048_peer_close(p)
+            self._opened = []
+            if self._mine:
+                self.lib.g2048_peer_free(self._mine)
+                self._mine = None
+
 
 class ShardedQLearning:
-    """Synchronous data-parallel tabular Q-learning: step() = local emit -> all_gather -> apply everywhere."""
+    """Synchronous data-parallel tabular Q-learning: step() = local emit -> exchange -> apply everywhere.
 
-    def __init__(self, engine, n_total: int, group=None):
-        self.engine, self.group = engine, group
+    transport: "auto" (generic emit()/apply() engines, e.g. the oracle engine on gloo), "nccl" (packed records,
+    one all_gather_into_tensor) or "peer" (NVLink peer memory, no collective on the data path)."""
+
+    def __init__(self, engine, n_total: int, group=None, transport: str = "auto"):
+        self.engine, self.group, self.transport = engine, group, transport
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_total = n_total
         self.sizes = [hi - lo for lo, hi in (shard_range(n_total, r, self.world) for r in range(self.world))]
         self.pad = max(self.sizes)
+        self.t = 0
+        self.peers = None
+        if transport == "peer":
+            agent = engine.agent
+            self.peers = PeerRecordBuffers(agent.lib, agent.device, self.pad, group)
+        elif transport == "nccl":
+            dev = engine.agent.device
+            self._mine = torch.zeros((self.pad, 2), dtype=torch.int64, device=dev)
+            self._all = torch.zeros((self.world, self.pad, 2), dtype=torch.int64, device=dev)
+        elif transport != "auto":
+            raise ValueError("transport must be auto, nccl or peer")
 
     def _gather(self, t: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
@@ -59,5 +154,57 @@ class ShardedQLearning:
         return torch.cat([o[:n] for o, n in zip(out, self.sizes)])
 
     def step(self):
-        keys, actions, targets = self.engine.emit()
-        self.engine.apply(self._gather(keys), self._gather(actions), self._gather(targets))
+        if self.transport == "peer":
+            p, slot = self.peers, self.t & 1
+            self.engine.emit_records(p.records(self.rank, slot))
+            p.barrier()
+            self.engine.apply_records([p.records(r, slot) for r in range(self.world)], self.sizes)
+        elif self.transport == "nccl":
+            self.engine.emit_records(self._mine)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self._all, self._mine, group=self.group)
+                self.engine.apply_records([self._all[r] for r in range(self.world)], self.sizes)
+            else:
+                self.engine.apply_records([self._mine], self.sizes)
+        else:
+            keys, actions, targets = self.engine.emit()
+            self.engine.apply(self._gather(keys), self._gather(actions), self._gather(targets))
+        self.t += 1
+
+    def close(self):
+        if self.peers is not None:
+            self.peers.check_timeout()
+            self.peers.close()
+            self.peers = None
+
+
+class GradientAllReduce:
+    """Data-parallel DQN (BASELINE config 5): every parameter's .grad is a view into ONE flat buffer,
+    so a training step costs a single all-reduce over NVSwitch (no per-tensor launches, no bucket copies), followed
+    by the division by the world size.  `sync_parameters()` broadcasts rank 0's weights once at start."""
+
+    def __init__(self, model: torch.nn.Module, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        p0 = self.params[0]
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=p0.dtype, device=p0.device)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def sync_parameters(self, src: int = 0):
+        if self.world > 1:
+            for p in self.params:
+                dist.broadcast(p.data, src, group=self.group)
+
+    def zero_grad(self):
+        self.flat.zero_()
+
+    def __call__(self):
+        """Average the gradients of all ranks in place (call between backward() and optimizer.step())."""
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(self.world)

@@ -80,6 +80,7 @@ class BatchedDQNAgent:
         self.update_target_model()
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=learning_rate)
         self.step_counter = 0
+        self.grad_sync = None
         self.loss_history: list[float] = []
         # replay memory: packed boards, never one-hot (16 B per transition instead of 2 KB)
         m = memory_size
@@ -158,14 +159,28 @@ class BatchedDQNAgent:
             targets = q.detach().clone()
             targets.scatter_(1, actions.unsqueeze(1), target_a.unsqueeze(1))
         loss = torch.mean((targets - q) ** 2)                                                         # :376
-        self.optimizer.zero_grad(set_to_none=True)
-        loss.backward()
+        if self.grad_sync is not None:              # data parallel: gradients live in one flat all-reduce buffer
+            self.grad_sync.zero_grad()
+            loss.backward()
+            self.grad_sync()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+            loss.backward()
         self.optimizer.step()
         self.loss_history.append(float(loss.detach()))
         return self.loss_history[-1]
 
     def update_target_model(self):
         self.target_model.load_state_dict(self.model.state_dict())
+
+    def data_parallel(self, group=None):
+        """Train this agent data-parallel over the ranks of `group` (one process per GPU, envs sharded): weights
+        start from rank 0's, every replay() averages the gradients with one NCCL all-reduce (dist.GradientAllReduce)."""
+        from .dist import GradientAllReduce
+        self.grad_sync = GradientAllReduce(self.model, group)
+        self.grad_sync.sync_parameters()
+        self.update_target_model()
+        return self
 
     def change_lr_function(self, reached_1024: bool = False):
         """:299-310: lr <- max(lr * 0.98, 1e-6) whenever an episode ended with a 1024 tile."""

@@ -77,6 +77,78 @@ def train_tabular_batched(env, agent, total_epochs: int, steps_per_epoch: int = 
     return history
 
 
+DQN_CSV_HEADER = ["Step", "Episodes", "Epsilon", "Mean Reward", "Done", "Replays", "Loss", "LR", "Best Tile", "Buffer"]
+
+
+def train_dqn(env, agent, total_steps: int, *, replays_per_episode: int = 100, max_replays_per_step: int = 100,
+              target_sync_episodes: int = 20, save_every_episodes: int = 100, save_dir: str | None = None,
+              log_file: str | None = None, on_step=None):
+    """The DQN driver loop (mainDQL_CNN_step2.py:151-333) for N envs at once on the batched nopenalty env.
+
+    Per step (one launch of the fused env side, `FusedDQNFeed`): legal-move mask -> act_ripetitive (:169-185) ->
+    env.step (:200) -> terminal bonus (:202-213) -> remember (:220) -> board commit (:237) -> reset of finished games.
+    Episode-level cadence as in the reference, counted in finished episodes of ANY env: `replays_per_episode` replay()
+    calls per finished game (:223-226, capped per step), learning-rate cut when a game ended on a board holding a
+    1024 tile (Dqn8TestNOPERCNN.py:283-284, :299-310), target sync every 20 episodes (:275-277), full agent save every
+    100 episodes (:322-328).  Not reproduced: the plotting (:271), the commented-out rollback block, and
+    clean_low_score_episodes (:317-319; keras-rl episode bookkeeping that a flat transition ring does not keep).
+    Returns {"episodes", "steps", "max_tile_list", "score_list", "loss_history", "best_tile"} like the arrays the
+    reference keeps (:100-103)."""
+    import os
+
+    import torch
+
+    from .dqn import FusedDQNFeed
+    if log_file:
+        with open(log_file, mode="w", newline="") as f:
+            csv.writer(f).writerow(DQN_CSV_HEADER)
+    if env.step_idx == 0 and int(env.boards.ne(0).sum()) == 0:
+        env.reset()
+    feed = FusedDQNFeed(env, agent)
+    episodes, best_tile = 0, 0
+    max_tile_list, score_list, loss_history = [], [], []
+    next_sync, next_save = target_sync_episodes, save_every_episodes
+    for step in range(total_steps):
+        prev_score = env.score.clone()                       # env.score of a finished game is reset inside the launch
+        reward, done = feed.step()
+        n_done = int(done.sum())
+        replays, loss = 0, None
+        if n_done:
+            final = feed.next_state[done]
+            lv = torch.stack([(final >> (4 * j)) & 15 for j in range(16)], dim=1).max(dim=1).values
+            tiles = (1 << lv.to(torch.int64)).tolist()
+            max_tile_list += tiles
+            score_list += prev_score[done].tolist()
+            best_tile = max(best_tile, max(tiles))
+            start = feed.state[done]
+            lv0 = torch.stack([(start >> (4 * j)) & 15 for j in range(16)], dim=1).max(dim=1).values
+            if bool((lv0 >= 10).any()):
+                agent.change_lr_function(True)
+            episodes += n_done
+            replays = min(replays_per_episode * n_done, max_replays_per_step)
+            for _ in range(replays):
+                out = agent.replay(episodes)
+                loss = out if out is not None else loss
+            if loss is not None:
+                loss_history.append(loss)
+            if target_sync_episodes and episodes >= next_sync:
+                agent.update_target_model()
+                next_sync = (episodes // target_sync_episodes + 1) * target_sync_episodes
+            if save_dir and save_every_episodes and episodes >= next_save:
+                os.makedirs(save_dir, exist_ok=True)
+                agent.save_agent_state(os.path.join(save_dir, f"agent_episode_{episodes}.pt"))
+                next_save = (episodes // save_every_episodes + 1) * save_every_episodes
+        row = [step, episodes, agent.epsilon, float(reward.mean()), n_done, replays, loss,
+               agent.optimizer.param_groups[0]["lr"], best_tile, agent.nb_entries]
+        if log_file:
+            with open(log_file, mode="a", newline="") as f:
+                csv.writer(f).writerow(row)
+        if on_step:
+            on_step(step, row)
+    return {"episodes": episodes, "steps": total_steps, "max_tile_list": max_tile_list, "score_list": score_list,
+            "loss_history": loss_history, "best_tile": best_tile}
+
+
 def evaluate_tabular(env, agent, episodes: int = 10):
     """Greedy play (epsilon = 0) of the N = 1 adapters or the reference's objects -- the headless form of the
     demo's "model play" mode (GameDemo.py:258-316).  Returns per-episode (game score, max tile, steps)."""

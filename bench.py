@@ -482,36 +482,48 @@ def dqn_measurement(torch, g2048, dev, n=65536, steps=3):
 
 
 def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_ranks, barrier, steps=24):
-    """Synchronous data-parallel Q-learning: every step all ranks all_gather their (state, action, target) records
-    over NCCL and apply the whole list deterministically, so the replicas stay identical."""
+    """Synchronous data-parallel Q-learning: every step all ranks exchange their packed (state, action, target)
+    records and apply the whole list deterministically, so the replicas stay identical.
+    Two transports: "peer" = records read in place from the owner's HBM over NVLink inside the apply kernel after a
+    flag barrier in peer memory (no collective); "nccl" = one all_gather_into_tensor, then the same kernel."""
     from g2048 import dist as gdist
-    env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
-    agent = g2048.BatchedQLearningAgent(1000, 4, LR, GAMMA, EPS, capacity=1 << 28, device=dev.index, seed=SEED)
-    env.reset()
-    sh = gdist.ShardedQLearning(gdist.TorchEngine(env, agent), n * world)
-    for _ in range(3):
-        sh.step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        sh.step()
-    e1.record()
-    barrier()
-    dt = max_over_ranks(e0.elapsed_time(e1) / 1e3)
-    keys, rows = agent.export()
-    nz = np.abs(rows).sum(1) > 0          # replicas differ only in untouched zero rows (their own shard's lookups)
-    digest = float(rows[nz].astype(np.float64).sum())   # sorted by key, same rows on every replica: same order
-    digests = [[digest, float(nz.sum())]]
-    if world > 1:
-        t = torch.tensor([digest, float(nz.sum())], dtype=torch.float64, device=dev)
-        all_t = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(all_t, t)
-        digests = [x.tolist() for x in all_t]
-    return {"env_steps_per_sec": world * n * steps / dt, "ms_per_step": dt / steps * 1e3, "envs_per_gpu": n,
-            "records_gathered_per_step": world * n, "bytes_received_per_rank_per_step": world * n * 13,
-            "replica_digests_sum_and_count_of_nonzero_rows": digests, "replicas_identical": len({tuple(d) for d in digests}) == 1,
-            "mode": "deterministic apply of all ranks' records on every replica"}
+    out = {"envs_per_gpu": n, "records_per_step": world * n, "bytes_pulled_per_rank_per_step": (world - 1) * n * 16,
+           "mode": "deterministic apply of all ranks' records on every replica"}
+    transports = ["nccl"] + (["peer"] if world > 1 else [])
+    for transport in transports:
+        env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
+        agent = g2048.BatchedQLearningAgent(1000, 4, LR, GAMMA, EPS, capacity=1 << 28, device=dev.index, seed=SEED)
+        env.reset()
+        sh = gdist.ShardedQLearning(gdist.TorchEngine(env, agent), n * world, transport=transport)
+        for _ in range(3):
+            sh.step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            sh.step()
+        e1.record()
+        barrier()
+        dt = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+        keys, rows = agent.export()
+        nz = np.abs(rows).sum(1) > 0          # replicas differ only in untouched zero rows (their own shard's lookups)
+        digest = float(rows[nz].astype(np.float64).sum())   # sorted by key, same rows on every replica: same order
+        digests = [[digest, float(nz.sum())]]
+        if world > 1:
+            t = torch.tensor([digest, float(nz.sum())], dtype=torch.float64, device=dev)
+            all_t = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(all_t, t)
+            digests = [x.tolist() for x in all_t]
+        sh.close()
+        del sh, env, agent
+        torch.cuda.empty_cache()
+        out[transport] = {"env_steps_per_sec": world * n * steps / dt, "ms_per_step": dt / steps * 1e3,
+                          "replica_digests_sum_and_count_of_nonzero_rows": digests,
+                          "replicas_identical": len({tuple(d) for d in digests}) == 1}
+    if "peer" in out:
+        out["transports_agree"] = (out["peer"]["replica_digests_sum_and_count_of_nonzero_rows"] ==
+                                   out["nccl"]["replica_digests_sum_and_count_of_nonzero_rows"])
+    return out
 
 
 def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):

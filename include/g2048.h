@@ -189,6 +189,44 @@ G2048_API int g2048_qlearn_step(uint64_t* boards, uint64_t* aux, int32_t* score,
                                 uint64_t* rec_key, uint8_t* rec_action, float* rec_target, void* scratch,
                                 size_t scratch_bytes, void* stream);
 
+/* ---------------------------------------------- synchronous step across GPUs: records over NVLink peer memory */
+/* One transition of a synchronous step as it travels between GPUs (16 bytes): the state key, and the action
+ * (bits 0-1) with the float32 bits of the TD target in bits 32-63. */
+typedef struct g2048_record {
+    uint64_t key;
+    uint64_t action_target;
+} g2048_record;
+#define G2048_MAX_PEERS 16
+#define G2048_IPC_HANDLE_BYTES 64
+
+/* g2048_qlearn_step with apply = 0, writing the records packed (16-byte aligned `records[n]`): choose_action
+ * (main.py:34-38) + env step + the target of update_q_value (main.py:41-42) for every env, table values untouched. */
+G2048_API int g2048_qlearn_emit(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
+                                int64_t n, int flavour, float gamma, double eps, uint64_t seed, uint64_t step_idx,
+                                uint64_t env_id_base, int64_t* counters, g2048_record* records, void* stream);
+/* Apply n_lists record lists (HOST arrays `lists[j]` = device pointer, `counts[j]` = records in it), list after
+ * list and record after record: q <- q + lr (target - q) (main.py:43).  The pointers may be peer memory of other
+ * GPUs (g2048_peer_open): the kernel reads each record directly from its owner over NVLink, so the "all-gather"
+ * of the exchange step and the table lookups of the apply are one kernel and no gathered copy exists.  With the
+ * lists in rank order the DETERMINISTIC result equals the single-GPU step over all envs. scratch: sized by
+ * g2048_qlearn_scratch_bytes(sum of counts). */
+G2048_API int g2048_qtable_apply_records(void* table, uint64_t capacity, const g2048_record* const* lists,
+                                         const int64_t* counts, int n_lists, float lr, int mode, void* scratch,
+                                         size_t scratch_bytes, void* stream);
+/* Device memory other processes of this box can map (CUDA IPC): alloc (zero-filled) + 64-byte handle to send to
+ * the peers; open/close on the peers' side; free by the owner. */
+G2048_API int g2048_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out);
+G2048_API int g2048_peer_open(const void* ipc_handle, void** dev_ptr);
+G2048_API int g2048_peer_close(void* dev_ptr);
+G2048_API int g2048_peer_free(void* dev_ptr);
+/* Stream-ordered barrier between the `world` GPUs: flags[j] (HOST array of device pointers) = rank j's flag
+ * block (uint64[world], zero at start, in peer memory); epoch must grow by one per barrier.  Work enqueued
+ * before it on every rank is visible to work enqueued after it on every rank.  If a peer does not arrive within
+ * timeout_ns (0 = 5 s), *timed_out (device int, may be NULL) is set to 1 + the missing rank and the kernel
+ * returns instead of hanging. */
+G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, uint64_t epoch, uint64_t timeout_ns,
+                                 int* timed_out, void* stream);
+
 /* ------------------------------------------------------------------ Q-table (device pointers) */
 /* QLearningAgent.q_table (main.py:16): `table` is capacity * 32 bytes of device memory, 32-byte aligned,
  * capacity = 2^k <= 2^31 slots (64 GiB). */

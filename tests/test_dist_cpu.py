@@ -78,3 +78,48 @@ def test_two_rank_exchange_equals_single_process(tmp_path):
         assert np.array_equal(d["boards"], single.boards[int(d["lo"]):int(d["hi"])])
         assert np.array_equal(d["keys"], keys[nz])
         assert np.array_equal(d["rows"], rows[nz])     # float32 sums in the same (global env id) order: bit-identical
+
+
+def _grad_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import oracle
+    from g2048 import dist as gdist
+    from g2048 import dqn
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # different initial weights: sync_parameters must fix that
+    model = dqn.DQNModel(width=8, hidden=8).eval()      # eval: no dropout noise in the comparison
+    sync = gdist.GradientAllReduce(model)
+    sync.sync_parameters()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    rng = np.random.RandomState(rank)
+    boards = rng.randint(1, 1 << 62, size=32).astype(np.uint64)
+    x = torch.from_numpy(oracle.encode_onehot(boards))
+    y = torch.from_numpy(rng.standard_normal((32, 4)).astype(np.float32))
+    local = []
+    for _ in range(3):
+        sync.zero_grad()
+        loss = torch.mean((model(x) - y) ** 2)
+        loss.backward()
+        local.append(sync.flat.clone())
+        sync()
+        opt.step()
+    torch.save({"local": local, "avg": sync.flat.clone(), "params": [p.detach().clone() for p in model.parameters()],
+                "views": all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in model.parameters())},
+               os.path.join(out, f"grad{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_dqn_gradient_allreduce_keeps_two_replicas_identical(tmp_path):
+    """Data-parallel DQN plumbing: one flat gradient buffer, one all-reduce, identical replicas."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f"grad{r}.pt") for r in range(2))
+    assert a["views"] and b["views"]
+    assert torch.allclose(a["avg"], (a["local"][-1] + b["local"][-1]) / 2, atol=1e-7)
+    assert torch.equal(a["avg"], b["avg"])
+    assert not torch.equal(a["local"][0], b["local"][0])          # the ranks really saw different data
+    for p, q in zip(a["params"], b["params"]):
+        assert torch.equal(p, q)

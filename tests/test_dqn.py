@@ -131,3 +131,41 @@ def test_fused_dqn_feed_drives_training():
         reward, done = feed.step()
     assert agent.nb_entries == min(20 * 2048, agent.memory_size) and agent.step_counter == 20
     assert np.isfinite(agent.replay())
+
+
+@pytest.mark.gpu
+def test_train_dqn_driver_cadence(tmp_path):
+    """train_dqn = mainDQL_CNN_step2.py:151-333 batched: episode bookkeeping, replay burst at episode end, target
+    sync, lr cut after a game that reached 1024, periodic save, CSV log."""
+    import csv
+    import g2048
+    from g2048 import dqn
+    torch.manual_seed(2)
+    n = 1024
+    env = g2048.BatchedGame2048Env(n, "nopenalty", seed=5)
+    agent = dqn.BatchedDQNAgent(width=16, hidden=32, memory_size=1 << 14, batch_size=64, epsilon=0.5, learning_rate=1e-3)
+    env.reset()
+    rng = np.random.RandomState(1)
+    lv = rng.randint(1, 11, size=(n, 16)) * (rng.random_sample((n, 16)) < 0.95)      # crowded late-game boards
+    lv[:256, 0] = 10                                                                   # a few hold a 1024 tile
+    packed = np.zeros(n, np.uint64)
+    for j in range(16):
+        packed |= lv[:, j].astype(np.uint64) << np.uint64(4 * j)
+    env.boards.copy_(torch.from_numpy(packed.view(np.int64)).cuda())
+    log = tmp_path / "dqn.csv"
+    out = g2048.train_dqn(env, agent, 40, replays_per_episode=2, max_replays_per_step=6, target_sync_episodes=20,
+                          save_every_episodes=50, save_dir=str(tmp_path / "saves"), log_file=str(log))
+    assert out["steps"] == 40 and out["episodes"] > 50
+    assert len(out["max_tile_list"]) == out["episodes"] == len(out["score_list"])
+    assert out["best_tile"] == max(out["max_tile_list"]) and all(t & (t - 1) == 0 for t in out["max_tile_list"])
+    assert all(np.isfinite(l) for l in out["loss_history"]) and out["loss_history"]
+    rows = list(csv.reader(open(log)))
+    assert rows[0] == g2048.train.DQN_CSV_HEADER and len(rows) == 41
+    assert int(rows[-1][1]) == out["episodes"]
+    assert agent.optimizer.param_groups[0]["lr"] < 1e-3            # at least one finished game held a 1024 tile
+    saves = sorted(p.name for p in (tmp_path / "saves").iterdir())
+    assert saves and all(s.startswith("agent_episode_") for s in saves)
+    # resume from the save
+    other = dqn.BatchedDQNAgent(width=16, hidden=32, memory_size=1 << 14, batch_size=64)
+    other.load_agent_state(str(tmp_path / "saves" / saves[-1]))
+    assert other.nb_entries > 0 and other.step_counter > 0
