@@ -71,6 +71,8 @@ _SIG = {
     "g2048_qlearn_scratch_bytes": (sz, [i64]),
     "g2048_qlearn_step": (i32, [vp, vp, vp, vp, u64, i64, i32, f32, f32, f64, i32, i32, u64, u64, u64, vp, vp, vp, vp,
                                 vp, sz, vp]),
+    "g2048_rollout_qlearn_sharded": (i32, [vp, vp, vp, vp, i32, u64, i64, i64, i32, f32, f32, f64, u64, u64, u64, vp, vp]),
+    "g2048_qtable_lookup_sharded": (i32, [vp, i32, u64, vp, i64, vp, vp, i32, vp]),
     "g2048_qlearn_emit": (i32, [vp, vp, vp, vp, u64, i64, i32, f32, f64, u64, u64, u64, vp, vp, vp]),
     "g2048_qtable_apply_records": (i32, [vp, u64, vp, vp, i32, f32, i32, vp, sz, vp]),
     "g2048_peer_alloc": (i32, [sz, vp, vp]),

@@ -283,11 +283,14 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
 //     the same Q value in between -- stale deltas are never summed, so heavily shared early-game states cannot
 //     diverge, and no lane spins on a contended address.  With one env nothing is ever lost: N = 1 is the
 //     reference's sequential order exactly.
-template <int FLAVOUR, bool SMEM_LUT>
+template <int FLAVOUR, bool SMEM_LUT, class TAB>
 __global__ void __launch_bounds__(SMEM_LUT ? kRolloutThreads : kSmallRolloutThreads, 1)
-k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mask, long long n, long long k_steps,
-                 float lr, float gamma, u64 eps_thresh, u64 seed, u64 step_base, u64 id_base, long long* counters) {
+k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ TAB table, long long n,
+                 long long k_steps, float lr, float gamma, u64 eps_thresh, u64 seed, u64 step_base, u64 id_base,
+                 long long* counters) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ Slot* shard_base[G2048_MAX_PEERS];
+    const auto tab = table.view(shard_base);
     Lut L = SMEM_LUT ? stage_lut(T, smem) : global_lut(T);
     Counters c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -295,7 +298,7 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
         env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
         u64 id = id_base + (u64)i;
         float4 row;
-        u32 slot = table_find<true>(tab, mask, e.board, row, c.inserts);
+        u32 slot = table_find<true>(tab, e.board, row, c.inserts);
         c.dropped += (slot == kNoSlot);
         bool ins_pending = false, term_pending = false, upd_pending = false, upd_patch = false;
         u64 ins_old = 0, term_old = 0, term_key = 0;   // speculative inserts: of the current state / of a terminal state
@@ -308,14 +311,14 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
             if (term_pending) {
                 term_pending = false;
                 if (term_old == 0) c.inserts += 1;
-                else if (term_old != term_key) { float4 r2; table_find<true>(tab, mask, term_key, r2, c.inserts); }
+                else if (term_old != term_key) { float4 r2; table_find<true>(tab, term_key, r2, c.inserts); }
             }
             if (ins_pending) {
                 ins_pending = false;
                 if (ins_old == 0) c.inserts += 1;
                 else if (ins_old != e.board) {   // another state won the slot: find a place for ours now
                     float4 r2;
-                    slot = table_find<true>(tab, mask, e.board, r2, c.inserts);
+                    slot = table_find<true>(tab, e.board, r2, c.inserts);
                     c.dropped += (slot == kNoSlot);
                 }
             }
@@ -337,16 +340,16 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
             if (!same) {
                 if (o.done) {   // a terminal s': its insert is checked through its own pair, the env moves on at once
                     term_key = e.board;
-                    slot2 = table_find_spec(tab, mask, e.board, row2, term_pending, term_old, c.dropped);
+                    slot2 = table_find_spec(tab, e.board, row2, term_pending, term_old, c.dropped);
                 } else {
-                    slot2 = table_find_spec(tab, mask, e.board, row2, ins_pending, ins_old, c.dropped);
+                    slot2 = table_find_spec(tab, e.board, row2, ins_pending, ins_old, c.dropped);
                 }
             }
             if (slot != kNoSlot) {
                 float q = q_at(row, a);
                 float nq = td_apply(q, lr, td_target(gamma, (float)o.reward, max4(row2), o.done));
                 upd_assumed = __float_as_uint(q);
-                upd_old = atomicCAS(reinterpret_cast<u32*>(&tab[slot].q[a]), upd_assumed, __float_as_uint(nq));
+                upd_old = cas32<decltype(tab)::kSys>(reinterpret_cast<u32*>(&tab.at(slot)->q[a]), upd_assumed, __float_as_uint(nq));
                 upd_pending = true; upd_patch = same && !o.done; upd_a = a;
                 if (same) q_set(row2, a, nq);
             }
@@ -354,16 +357,16 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, Slot* tab, u64 mas
             slot = slot2;
             if (o.done) {   // state = env.reset() is read at once (main.py:81-82, :92), speculatively as well
                 philox_autoreset(e, seed, id, t);
-                slot = table_find_spec(tab, mask, e.board, row, ins_pending, ins_old, c.dropped);
+                slot = table_find_spec(tab, e.board, row, ins_pending, ins_old, c.dropped);
             }
         }
         if (term_pending) {
             if (term_old == 0) c.inserts += 1;
-            else if (term_old != term_key) { float4 r2; table_find<true>(tab, mask, term_key, r2, c.inserts); }
+            else if (term_old != term_key) { float4 r2; table_find<true>(tab, term_key, r2, c.inserts); }
         }
         if (ins_pending) {
             if (ins_old == 0) c.inserts += 1;
-            else if (ins_old != e.board) { float4 r2; table_find<true>(tab, mask, e.board, r2, c.inserts); }
+            else if (ins_old != e.board) { float4 r2; table_find<true>(tab, e.board, r2, c.inserts); }
         }
         if (upd_pending && upd_old != upd_assumed) c.lost += 1;
         boards[i] = e.board;
@@ -514,6 +517,19 @@ k_q_lookup(Slot* tab, u64 mask, const u64* keys, long long n, float4* rows, uint
         float4 row;
         u32 ins = 0;
         u32 slot = table_find<INSERT>(tab, mask, keys[i], row, ins);
+        rows[i] = row;
+        if (found) found[i] = (slot != kNoSlot) && !ins;
+    }
+}
+template <bool INSERT, class TAB>
+__global__ void __launch_bounds__(256)
+k_q_lookup_tab(const __grid_constant__ TAB table, const u64* keys, long long n, float4* rows, uint8_t* found) {
+    __shared__ Slot* shard_base[G2048_MAX_PEERS];
+    const auto tab = table.view(shard_base);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float4 row;
+        u32 ins = 0;
+        u32 slot = table_find<INSERT>(tab, keys[i], row, ins);
         rows[i] = row;
         if (found) found[i] = (slot != kNoSlot) && !ins;
     }
@@ -768,8 +784,10 @@ G2048_API int g2048_init(int device) {
     CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaFuncSetAttribute(k_rollout_random<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_rollout_random<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
-    CK(cudaFuncSetAttribute(k_rollout_qlearn<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
-    CK(cudaFuncSetAttribute(k_rollout_qlearn<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_qlearn<0, true, LocalTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_qlearn<1, true, LocalTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_qlearn<0, true, ShardedTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_rollout_qlearn<1, true, ShardedTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     d.ready = true;
     return 0;
 }
@@ -935,6 +953,42 @@ G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* sco
     return 0;
 }
 
+namespace {
+template <class TAB>
+int launch_rollout_qlearn(DeviceState* D, const TAB& tab, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n,
+                          int64_t k_steps, int flavour, float lr, float gamma, double eps, uint64_t seed,
+                          uint64_t step_base, uint64_t env_id_base, int64_t* counters, void* stream) {
+    int grid, block, smem_lut;
+    size_t smem;
+    rollout_geometry(D, n, grid, block, smem_lut, smem);
+#define LAUNCH_RQ(F, SM)                                                                                              \
+    k_rollout_qlearn<F, SM, TAB><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, tab, n,   \
+                                                                   k_steps, lr, gamma, eps_threshold(eps), seed,       \
+                                                                   step_base, env_id_base, (long long*)counters)
+    if (flavour == 0) { if (smem_lut) LAUNCH_RQ(0, true); else LAUNCH_RQ(0, false); }
+    else { if (smem_lut) LAUNCH_RQ(1, true); else LAUNCH_RQ(1, false); }
+#undef LAUNCH_RQ
+    LAUNCH_CHECK("k_rollout_qlearn");
+    return 0;
+}
+// shards[j] = device pointer to slots_per_shard slots (local or peer memory); n_shards and slots_per_shard powers of two
+int make_sharded(const void* const* shards, int n_shards, uint64_t slots_per_shard, ShardedTable& t, const char* who) {
+    if (!shards || n_shards < 1 || n_shards > G2048_MAX_PEERS || (n_shards & (n_shards - 1)) || !pow2(slots_per_shard) ||
+        slots_per_shard * (uint64_t)n_shards > (1ull << 31))
+        return fail(G2048_ERR_ARG, who);
+    t = ShardedTable{};
+    for (int j = 0; j < n_shards; ++j) {
+        if (!shards[j] || ((uintptr_t)shards[j] & 31)) return fail(G2048_ERR_ARG, who);
+        t.base[j] = (Slot*)shards[j];
+    }
+    t.mask = slots_per_shard * (uint64_t)n_shards - 1;
+    t.low = slots_per_shard - 1;
+    t.shift = 0;
+    while ((1ull << t.shift) < slots_per_shard) ++t.shift;
+    return 0;
+}
+}  // namespace
+
 G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
                                    int64_t n, int64_t k_steps, int flavour, float lr, float gamma, double eps,
                                    uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t* counters,
@@ -944,17 +998,38 @@ G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* sco
         (flavour != 0 && flavour != 1))
         return fail(G2048_ERR_ARG, "g2048_rollout_qlearn: bad arguments");
     if (n == 0 || k_steps == 0) return 0;
-    int grid, block, smem_lut;
-    size_t smem;
-    rollout_geometry(D, n, grid, block, smem_lut, smem);
-#define LAUNCH_RQ(F, SM)                                                                                                  \
-    k_rollout_qlearn<F, SM><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, (Slot*)table,      \
-                                                              capacity - 1, n, k_steps, lr, gamma, eps_threshold(eps), seed, \
-                                                              step_base, env_id_base, (long long*)counters)
-    if (flavour == 0) { if (smem_lut) LAUNCH_RQ(0, true); else LAUNCH_RQ(0, false); }
-    else { if (smem_lut) LAUNCH_RQ(1, true); else LAUNCH_RQ(1, false); }
-#undef LAUNCH_RQ
-    LAUNCH_CHECK("k_rollout_qlearn");
+    return launch_rollout_qlearn(D, LocalTable{(Slot*)table, capacity - 1}, boards, aux, score, n, k_steps, flavour, lr,
+                                 gamma, eps, seed, step_base, env_id_base, counters, stream);
+}
+
+G2048_API int g2048_rollout_qlearn_sharded(uint64_t* boards, uint64_t* aux, int32_t* score, const void* const* shards,
+                                           int n_shards, uint64_t slots_per_shard, int64_t n, int64_t k_steps,
+                                           int flavour, float lr, float gamma, double eps, uint64_t seed,
+                                           uint64_t step_base, uint64_t env_id_base, int64_t* counters, void* stream) {
+    DEVSTATE();
+    if (n < 0 || k_steps < 0 || (n && !boards) || (flavour != 0 && flavour != 1))
+        return fail(G2048_ERR_ARG, "g2048_rollout_qlearn_sharded: bad arguments");
+    ShardedTable t;
+    int rc = make_sharded(shards, n_shards, slots_per_shard, t, "g2048_rollout_qlearn_sharded: bad shard list");
+    if (rc) return rc;
+    if (n == 0 || k_steps == 0) return 0;
+    return launch_rollout_qlearn(D, t, boards, aux, score, n, k_steps, flavour, lr, gamma, eps, seed, step_base,
+                                 env_id_base, counters, stream);
+}
+
+G2048_API int g2048_qtable_lookup_sharded(const void* const* shards, int n_shards, uint64_t slots_per_shard,
+                                          const uint64_t* keys, int64_t n, float* rows, uint8_t* found, int insert,
+                                          void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && (!keys || !rows))) return fail(G2048_ERR_ARG, "g2048_qtable_lookup_sharded: bad arguments");
+    ShardedTable t;
+    int rc = make_sharded(shards, n_shards, slots_per_shard, t, "g2048_qtable_lookup_sharded: bad shard list");
+    if (rc) return rc;
+    if (n == 0) return 0;
+    int g = grid_for(n, 256, D->sm_count);
+    if (insert) k_q_lookup_tab<true, ShardedTable><<<g, 256, 0, S(stream)>>>(t, (const u64*)keys, n, (float4*)rows, found);
+    else k_q_lookup_tab<false, ShardedTable><<<g, 256, 0, S(stream)>>>(t, (const u64*)keys, n, (float4*)rows, found);
+    LAUNCH_CHECK("k_q_lookup_tab");
     return 0;
 }
 

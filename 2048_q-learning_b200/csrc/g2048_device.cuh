@@ -374,10 +374,57 @@ __device__ __forceinline__ u64 mix64(u64 x) {  // splitmix64 finaliser
     x ^= x >> 31;
     return x;
 }
-// one 256-bit L2-coherent load of a whole slot (L1 is bypassed: other SMs update rows with atomics)
+// Where the slots live.  LocalTable: one array in this GPU's HBM.  ShardedTable: the global slot range cut into
+// 2^k equal shards, shard j in the HBM of GPU j and mapped into every process of the box (CUDA IPC over NVLink 5 /
+// NVSwitch): a slot is addressed the same way from every GPU, reads are plain (system-scope) loads and updates are
+// system-scope atomics executed at the owner's L2, so all GPUs learn ONE table.  Shard = the TOP bits of the slot
+// index, so a probe sequence stays on one GPU.
+struct LocalTable {
+    Slot* base;
+    u64 mask;
+    static constexpr bool kSys = false;
+    static constexpr bool kSysLoad = false;
+    __device__ __forceinline__ Slot* at(u64 h) const { return base + h; }
+    __device__ __forceinline__ LocalTable view(Slot**) const { return *this; }
+};
+// device-side view of a sharded table: the shard pointers sit in shared memory (a per-lane index into the kernel
+// parameters would be a constant-bank load, which the hardware serialises per distinct index)
+template <bool SYS_LOAD, bool SYS_ATOM>
+struct ShardedView {
+    Slot* const* base;
+    u64 mask, low;
+    u32 shift;
+    static constexpr bool kSys = SYS_ATOM;
+    static constexpr bool kSysLoad = SYS_LOAD;
+    __device__ __forceinline__ Slot* at(u64 h) const { return base[h >> shift] + (h & low); }
+};
+template <bool SYS_LOAD, bool SYS_ATOM>
+struct ShardedTableT {
+    Slot* base[G2048_MAX_PEERS];
+    u64 mask;       // global capacity - 1
+    u64 low;        // slots per shard - 1
+    u32 shift;      // log2(slots per shard)
+    // call from all threads of the block, once, at kernel start; `sm` = G2048_MAX_PEERS pointers of shared memory
+    __device__ __forceinline__ ShardedView<SYS_LOAD, SYS_ATOM> view(Slot** sm) const {
+        if (threadIdx.x < G2048_MAX_PEERS) sm[threadIdx.x] = base[threadIdx.x];
+        __syncthreads();
+        return ShardedView<SYS_LOAD, SYS_ATOM>{sm, mask, low, shift};
+    }
+};
+using ShardedTable = ShardedTableT<true, true>;
+template <bool SYS> __device__ __forceinline__ u64 cas64(u64* p, u64 cmp, u64 val) {
+    return SYS ? atomicCAS_system((unsigned long long*)p, cmp, val) : atomicCAS((unsigned long long*)p, cmp, val);
+}
+template <bool SYS> __device__ __forceinline__ u32 cas32(u32* p, u32 cmp, u32 val) {
+    return SYS ? atomicCAS_system(p, cmp, val) : atomicCAS(p, cmp, val);
+}
+// one 256-bit load of a whole slot, coherent at L2 (L1 is bypassed: other SMs -- or, system scope, other GPUs --
+// update rows with atomics)
+template <bool SYS = false>
 __device__ __forceinline__ void load_slot(const Slot* s, u64& key, float4& q) {
     u64 k, m, q01, q23;
-    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(m), "=l"(q01), "=l"(q23) : "l"(s));
+    if (SYS) asm volatile("ld.relaxed.sys.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(m), "=l"(q01), "=l"(q23) : "l"(s));
+    else asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(m), "=l"(q01), "=l"(q23) : "l"(s));
     key = k;
     q.x = __uint_as_float((u32)q01); q.y = __uint_as_float((u32)(q01 >> 32));
     q.z = __uint_as_float((u32)q23); q.w = __uint_as_float((u32)(q23 >> 32));
@@ -387,39 +434,45 @@ __device__ __forceinline__ void load_slot(const Slot* s, u64& key, float4& q) {
 // fetch granularity, tools/membench.cu -- so every extra sector costs, even an adjacent one.)
 // defaultdict semantics (main.py:16): reading a state creates its zero row.  Returns the slot index
 // (kNoSlot if the probe limit is hit: the state is then treated as a zero row and not updated).
-template <bool INSERT>
-__device__ __forceinline__ u32 table_find(Slot* tab, u64 mask, u64 key, float4& q, u32& inserted) {
-    u64 h = mix64(key) & mask;
-    for (int p = 0; p < kMaxProbe; ++p, h = (h + 1) & mask) {
+template <bool INSERT, class TAB>
+__device__ __forceinline__ u32 table_find(const TAB& tab, u64 key, float4& q, u32& inserted) {
+    u64 h = mix64(key) & tab.mask;
+    for (int p = 0; p < kMaxProbe; ++p, h = (h + 1) & tab.mask) {
         u64 k;
-        load_slot(tab + h, k, q);
+        Slot* sp = tab.at(h);
+        load_slot<TAB::kSysLoad>(sp, k, q);
         if (k == key) return (u32)h;
         if (k == 0) {
             if (!INSERT) break;
-            u64 old = atomicCAS(&tab[h].key, 0ull, key);
+            u64 old = cas64<TAB::kSys>(&sp->key, 0ull, key);
             if (old == 0) { inserted += 1; q = make_float4(0.f, 0.f, 0.f, 0.f); return (u32)h; }
-            if (old == key) { load_slot(tab + h, k, q); return (u32)h; }
+            if (old == key) { load_slot<TAB::kSysLoad>(sp, k, q); return (u32)h; }
         }
     }
     q = make_float4(0.f, 0.f, 0.f, 0.f);
     return kNoSlot;
 }
+template <bool INSERT>
+__device__ __forceinline__ u32 table_find(Slot* tab, u64 mask, u64 key, float4& q, u32& inserted) {
+    return table_find<INSERT>(LocalTable{tab, mask}, key, q, inserted);
+}
 // Speculative find-or-insert for the fused rollout: probe with plain loads; an empty slot is claimed with ONE
 // atomicCAS (issued after the probe loop, so its destination register is not touched again) whose result
 // (ins_old) the caller inspects one step later -- the row of a new state is zero wherever it finally lands, only
 // the slot index may need a re-probe (ins_old neither 0 nor key).
-__device__ __forceinline__ u32 table_find_spec(Slot* tab, u64 mask, u64 key, float4& q, bool& ins_pending, u64& ins_old,
+template <class TAB>
+__device__ __forceinline__ u32 table_find_spec(const TAB& tab, u64 key, float4& q, bool& ins_pending, u64& ins_old,
                                                u32& dropped) {
-    u64 h = mix64(key) & mask, k = 1;
+    u64 h = mix64(key) & tab.mask, k = 1;
     int p = 0;
-    for (; p < kMaxProbe; ++p, h = (h + 1) & mask) {
-        load_slot(tab + h, k, q);
+    for (; p < kMaxProbe; ++p, h = (h + 1) & tab.mask) {
+        load_slot<TAB::kSysLoad>(tab.at(h), k, q);
         if (k == key || k == 0) break;
     }
     if (k == key) return (u32)h;
     q = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p == kMaxProbe) { dropped += 1; return kNoSlot; }
-    ins_old = atomicCAS(&tab[h].key, 0ull, key);
+    ins_old = cas64<TAB::kSys>(&tab.at(h)->key, 0ull, key);
     ins_pending = true;
     return (u32)h;
 }
@@ -449,14 +502,14 @@ __device__ __forceinline__ float td_target(float gamma, float r, float best_next
 __device__ __forceinline__ float td_apply(float q, float lr, float target) {
     return __fadd_rn(q, __fmul_rn(lr, __fsub_rn(target, q)));
 }
-// Atomic read-modify-write of one Q value: q <- q + lr * (target - q) as a CAS loop, so concurrent
-// updates of the same (state, action) compose like the reference's sequential loop (a contraction
-// towards the targets) instead of summing stale deltas, which diverges once the number of
-// simultaneous updaters exceeds 2 / lr.  `guess` is the caller's last view of the value.
 // 16-byte exchange record of one transition: {state key, action | float bits of the TD target << 32}
 __device__ __forceinline__ ulonglong2 pack_record(u64 key, int a, float target) {
     return make_ulonglong2(key, (u64)(a & 3) | ((u64)__float_as_uint(target) << 32));
 }
+// Atomic read-modify-write of one Q value: q <- q + lr * (target - q) as a CAS loop, so concurrent
+// updates of the same (state, action) compose like the reference's sequential loop (a contraction
+// towards the targets) instead of summing stale deltas, which diverges once the number of
+// simultaneous updaters exceeds 2 / lr.  `guess` is the caller's last view of the value.
 __device__ __forceinline__ float q_update_atomic(float* addr, float guess, float lr, float target) {
     u32 assumed = __float_as_uint(guess);
     while (true) {

@@ -178,6 +178,134 @@ class ShardedQLearning:
             self.peers = None
 
 
+class SharedQTable:
+    """ONE Q-table for all GPUs of the box (the reference's single `q_table`, main.py:16, at box scale): shard j of
+    the slot range lives in the HBM of rank j, every rank maps every shard (CUDA IPC) and runs the fused rollout on
+    its own env shard; lookups and compare-and-swap updates of remote slots travel over NVLink 5 / NVSwitch inside
+    the kernel (g2048_rollout_qlearn_sharded).  No exchange step, no replicas, table memory adds up over the GPUs.
+
+    `shards` (list of int64 tensors on this device) builds a table from local allocations instead -- the
+    single-process form used by the tests and by 1-GPU runs."""
+
+    def __init__(self, lib, device: torch.device, slots_per_shard: int, group=None, shards=None):
+        import ctypes
+        if slots_per_shard & (slots_per_shard - 1):
+            raise ValueError("slots_per_shard must be a power of two")
+        self.lib, self.device, self.group, self.slots_per_shard = lib, device, group, int(slots_per_shard)
+        self._opened, self._mine, self._local = [], None, None
+        from ._lib import check
+        self._check = check
+        if shards is not None:
+            self.rank, self.world = 0, 1
+            self._tensors = list(shards)
+            self.ptrs = [t.data_ptr() for t in self._tensors]
+            self._local = self.ptrs            # all shards are local
+        else:
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            nbytes = self.slots_per_shard * 32
+            mine, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+            with torch.cuda.device(device):
+                check(lib.g2048_peer_alloc(nbytes, ctypes.byref(mine), handle), "g2048_peer_alloc")
+                allh = [None] * self.world
+                dist.all_gather_object(allh, bytes(handle), group=group)
+                self.ptrs = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.ptrs.append(mine.value)
+                        continue
+                    p = ctypes.c_void_p()
+                    check(lib.g2048_peer_open((ctypes.c_ubyte * 64)(*allh[r]), ctypes.byref(p)), "g2048_peer_open")
+                    self.ptrs.append(p.value)
+                    self._opened.append(p.value)
+            self._mine = mine.value
+            self._local = [mine.value]
+            dist.barrier(group=group)
+        m = len(self.ptrs)
+        if m & (m - 1) or m * self.slots_per_shard > (1 << 31):
+            raise ValueError("number of shards must be a power of two and the table at most 2^31 slots")
+        self.n_shards = m
+        self._arr = (ctypes.c_void_p * m)(*self.ptrs)
+        self._count = torch.zeros(1, dtype=torch.int64, device=device)
+
+    @property
+    def capacity(self) -> int:
+        return self.n_shards * self.slots_per_shard
+
+    def rollout(self, env, k_steps: int, lr: float, gamma: float, eps: float) -> torch.Tensor:
+        """k_steps of main.py:91-101 for every env of this rank on the shared table (asynchronous updates)."""
+        with torch.cuda.device(self.device):
+            env.counters.zero_()
+            self._check(self.lib.g2048_rollout_qlearn_sharded(
+                env.boards.data_ptr(), env.aux.data_ptr(), env.score.data_ptr(), self._arr, self.n_shards,
+                self.slots_per_shard, env.n, k_steps, env.flavour, lr, gamma, float(eps), env.seed, env.step_idx,
+                env.env_id_base, env.counters.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                "g2048_rollout_qlearn_sharded")
+        env.step_idx += k_steps
+        return env.counters
+
+    def lookup(self, boards: torch.Tensor, insert: bool = False):
+        n = boards.numel()
+        rows = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+        found = torch.empty(n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.g2048_qtable_lookup_sharded(self._arr, self.n_shards, self.slots_per_shard,
+                                                             boards.data_ptr(), n, rows.data_ptr(), found.data_ptr(),
+                                                             int(insert), torch.cuda.current_stream().cuda_stream),
+                        "g2048_qtable_lookup_sharded")
+        return rows, found != 0
+
+    def local_size(self) -> int:
+        """States stored in the shard(s) this rank owns."""
+        total = 0
+        with torch.cuda.device(self.device):
+            for p in self._local:
+                self._check(self.lib.g2048_qtable_size(p, self.slots_per_shard, self._count.data_ptr(),
+                                                       torch.cuda.current_stream().cuda_stream), "g2048_qtable_size")
+                total += int(self._count.item())
+        return total
+
+    def size(self) -> int:
+        n = self.local_size()
+        if self.world > 1:
+            t = torch.tensor([n], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, group=self.group)
+            n = int(t.item())
+        return n
+
+    def export_local(self):
+        """(keys uint64[n], rows float32[n,4]) of this rank's shard(s), sorted by key."""
+        import numpy as np
+        ks, rs = [], []
+        with torch.cuda.device(self.device):
+            for p in self._local:
+                self._check(self.lib.g2048_qtable_size(p, self.slots_per_shard, self._count.data_ptr(),
+                                                       torch.cuda.current_stream().cuda_stream), "g2048_qtable_size")
+                n = int(self._count.item())
+                keys = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+                rows = torch.empty((max(n, 1), 4), dtype=torch.float32, device=self.device)
+                self._count.zero_()
+                self._check(self.lib.g2048_qtable_export(p, self.slots_per_shard, keys.data_ptr(), rows.data_ptr(), n,
+                                                         self._count.data_ptr(),
+                                                         torch.cuda.current_stream().cuda_stream), "g2048_qtable_export")
+                ks.append(keys[:n].cpu().numpy().view(np.uint64))
+                rs.append(rows[:n].cpu().numpy())
+        k, r = np.concatenate(ks), np.concatenate(rs)
+        order = np.argsort(k)
+        return k[order], r[order]
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)
+            for p in self._opened:
+                self.lib.g2048_peer_close(p)
+            self._opened = []
+            if self._mine:
+                self.lib.g2048_peer_free(self._mine)
+                self._mine = None
+
+
 class GradientAllReduce:
     """Data-parallel DQN (BASELINE config 5): every parameter's .grad is a view into ONE flat buffer,
     so a training step costs a single all-reduce over NVSwitch (no per-tensor launches, no bucket copies), followed

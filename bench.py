@@ -260,6 +260,8 @@ def main():
                     help="also time BASELINE config 5: 65,536 nopenalty envs/GPU with the 197 M-parameter DQN forward in the loop")
     ap.add_argument("--exchange", action="store_true",
                     help="also time the synchronous mode with the cross-GPU record exchange (dist.ShardedQLearning)")
+    ap.add_argument("--shared-table", action="store_true",
+                    help="also time the fused rollout on ONE Q-table sharded over the GPUs' HBM (NVLink peer loads/atomics)")
     args = ap.parse_args()
     EPS = args.eps
     rank = int(os.environ.get("RANK", "0"))
@@ -278,6 +280,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the g2048 hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g2048.init(local_rank)
     L = g2048.lib()
@@ -349,6 +352,8 @@ def main():
         ev[i + 1].record()
     barrier()
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    if os.environ.get("G2048_PRINT_LAUNCHES") and rank == 0:
+        print("per-launch ms:", [round(x, 3) for x in per_launch_ms], "cap", cap, file=sys.stderr)
     elapsed_s = max_over_ranks(ev[0].elapsed_time(ev[-1]) / 1e3)
     c = counters.cpu().numpy()
     assert int(c[0]) == n * k * launches, (int(c[0]), n * k * launches)
@@ -392,6 +397,10 @@ def main():
         sync = sync_exchange_measurement(torch, dist, g2048, dev, rank, world, min(n, 1 << 20), max_over_ranks, barrier)
         if rank == 0:
             extras["synchronous_exchange"] = sync
+    if args.shared_table:
+        sh = shared_table_measurement(torch, dist, g2048, dev, rank, world, min(n, 1 << 20), max_over_ranks, barrier)
+        if rank == 0:
+            extras["shared_table_over_nvlink"] = sh
     if args.dqn and rank == 0:
         extras["dqn_in_the_loop"] = dqn_measurement(torch, g2048, dev)
     if not args.no_extras and rank == 0:
@@ -523,6 +532,48 @@ def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_
     if "peer" in out:
         out["transports_agree"] = (out["peer"]["replica_digests_sum_and_count_of_nonzero_rows"] ==
                                    out["nccl"]["replica_digests_sum_and_count_of_nonzero_rows"])
+    return out
+
+
+def shared_table_measurement(torch, dist, g2048, dev, rank, world, n, max_over_ranks, barrier, launches=8, warm=2, k=16):
+    launches = int(os.environ.get('G2048_SHARED_LAUNCHES', launches))
+    """The fused asynchronous rollout of every rank on ONE Q-table: shard j of the slot range in the HBM of GPU j,
+    remote lookups / compare-and-swap updates over NVLink inside the kernel (dist.SharedQTable).  (world-1)/world of
+    all table accesses are remote.  Table = 2^31 slots (64 GiB) in total."""
+    from g2048 import dist as gdist
+    if world & (world - 1):
+        return {"skipped": "needs a power-of-two number of GPUs"}
+    slots = (1 << 31) // world
+    env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
+    env.reset()
+    if world > 1:
+        shared = gdist.SharedQTable(g2048.lib(), dev, slots)
+    else:
+        shared = gdist.SharedQTable(g2048.lib(), dev, slots, shards=[torch.zeros(slots * 4, dtype=torch.int64, device=dev)])
+    tot = torch.zeros(9, dtype=torch.int64, device=dev)
+    for _ in range(warm):
+        tot += shared.rollout(env, k, LR, GAMMA, EPS)      # (also loads torch's add kernel outside the timed region)
+    tot.zero_()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(launches + 1)]
+    ev[0].record()
+    for i in range(launches):
+        tot += shared.rollout(env, k, LR, GAMMA, EPS)
+        ev[i + 1].record()
+    barrier()
+    dt = max_over_ranks(ev[0].elapsed_time(ev[-1]) / 1e3)
+    per_launch = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(launches)]
+    c = tot.cpu().numpy()
+    states = shared.size()
+    shared.close()
+    out = {"env_steps_per_sec": world * n * k * launches / dt, "per_gpu": n * k * launches / dt, "ms_per_launch": dt / launches * 1e3,
+           "rank0_ms_of_each_launch": per_launch,
+           "envs_per_gpu": n, "env_steps_per_launch": k, "table_slots_total": 1 << 31, "slots_per_gpu": slots,
+           "states_in_table": states, "load_factor_end": states / float(1 << 31), "remote_access_fraction": (world - 1) / world,
+           "rank0_lost_update_fraction": float(c[8]) / max(float(c[1]), 1.0), "rank0_dropped": int(c[7]),
+           "mode": "one table for all GPUs, async single-shot CAS updates at the owner's L2, no exchange step"}
+    del env
+    torch.cuda.empty_cache()
     return out
 
 

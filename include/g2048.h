@@ -176,6 +176,22 @@ G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* sco
                                    uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t* counters,
                                    void* stream);
 
+/* g2048_rollout_qlearn on ONE Q-table spread over the GPUs of the box: the global slot range is cut into n_shards
+ * (a power of two) shards of slots_per_shard (a power of two) slots, shards[j] (HOST array of device pointers) being
+ * shard j -- this GPU's own memory or a peer's, mapped with g2048_peer_open.  Every GPU runs the call on its own env
+ * shard at the same time; lookups are plain loads and updates single atomic compare-and-swaps that travel over NVLink 5 /
+ * NVSwitch to the owner's L2 (system scope), so all envs of the box learn the same table (q_table, main.py:16) with
+ * no exchange step at all.  n_shards * slots_per_shard <= 2^31.  Each shard is an ordinary slot array: clear, size and
+ * export it with the g2048_qtable_* calls on its owner. */
+G2048_API int g2048_rollout_qlearn_sharded(uint64_t* boards, uint64_t* aux, int32_t* score, const void* const* shards,
+                                           int n_shards, uint64_t slots_per_shard, int64_t n, int64_t k_steps,
+                                           int flavour, float lr, float gamma, double eps, uint64_t seed,
+                                           uint64_t step_base, uint64_t env_id_base, int64_t* counters, void* stream);
+/* q_table[state] (main.py:16) on a sharded table; see g2048_qtable_lookup. */
+G2048_API int g2048_qtable_lookup_sharded(const void* const* shards, int n_shards, uint64_t slots_per_shard,
+                                          const uint64_t* keys, int64_t n, float* rows, uint8_t* found, int insert,
+                                          void* stream);
+
 /* One synchronous batched Q-learning step: every env chooses from and bootstraps
  * on the table as it is at step start (target_i = r_i + gamma max Q[s'_i] (1 - done_i)); afterwards every
  * (state, action) receives its targets one after another, q <- q + lr (target_i - q) -- the reference's own

@@ -139,3 +139,121 @@ def test_two_processes_exchange_through_ipc_peer_memory(tmp_path):
         assert int(d["epoch"]) == STEPS
         assert np.array_equal(d["boards"], boards1[int(d["lo"]):int(d["hi"])])
         assert np.array_equal(d["keys"], keys1) and np.array_equal(d["rows"], rows1)
+
+
+# ---------------------------------------------------------------- one Q-table spread over several GPUs' memory
+def test_sharded_table_with_one_env_is_the_local_table_bit_for_bit():
+    """N = 1 is sequential, hence deterministic: 4 shards of 2^12 slots hold exactly the bytes of one 2^14 table."""
+    import torch
+    import g2048
+    from g2048 import dist as gdist
+    L = g2048.lib()
+    for flavour in ("penalty", "nopenalty"):
+        env_a = g2048.BatchedGame2048Env(1, flavour, seed=SEED)
+        env_b = g2048.BatchedGame2048Env(1, flavour, seed=SEED)
+        agent = g2048.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 0.3, capacity=1 << 14, seed=SEED)
+        shards = [torch.zeros((1 << 12) * 4, dtype=torch.int64, device="cuda") for _ in range(4)]
+        shared = gdist.SharedQTable(L, torch.device("cuda", 0), 1 << 12, shards=shards)
+        env_a.reset(); env_b.reset()
+        for _ in range(5):
+            ca = agent.rollout(env_a, 200).clone()
+            cb = shared.rollout(env_b, 200, 0.1, 0.99, 0.3).clone()
+            assert torch.equal(ca, cb)
+        assert torch.equal(env_a.boards, env_b.boards) and torch.equal(env_a.aux, env_b.aux)
+        assert torch.equal(torch.cat(shards), agent.table)
+        assert shared.size() == len(agent) and shared.capacity == 1 << 14
+
+
+def test_sharded_table_many_envs_random_policy():
+    """epsilon = 1: trajectories do not depend on the table, so counters and the SET of stored states must equal the
+    local-table run exactly (values may differ by update order); every stored state is found by the sharded lookup."""
+    import torch
+    import g2048
+    from g2048 import dist as gdist
+    L = g2048.lib()
+    n = 50_000
+    env_a = g2048.BatchedGame2048Env(n, "penalty", seed=SEED)
+    env_b = g2048.BatchedGame2048Env(n, "penalty", seed=SEED)
+    agent = g2048.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 1.0, capacity=1 << 23, seed=SEED)
+    shards = [torch.zeros((1 << 22) * 4, dtype=torch.int64, device="cuda") for _ in range(2)]
+    shared = gdist.SharedQTable(L, torch.device("cuda", 0), 1 << 22, shards=shards)
+    env_a.reset(); env_b.reset()
+    ca = agent.rollout(env_a, 48).clone()
+    cb = shared.rollout(env_b, 48, 0.1, 0.99, 1.0).clone()
+    assert torch.equal(ca[:8], cb[:8])                      # everything but the lost-update count
+    assert torch.equal(env_a.boards, env_b.boards)
+    k_local, r_local = agent.export()
+    k_shared, r_shared = shared.export_local()
+    assert np.array_equal(k_local, k_shared)
+    assert np.isfinite(r_shared).all() and np.abs(r_shared).max() <= 10.0 / (1 - 0.99) + 1e-3
+    assert abs(float(np.abs(r_shared).mean()) / float(np.abs(r_local).mean()) - 1) < 0.10
+    keys = torch.from_numpy(k_shared.view(np.int64)).cuda()
+    rows, found = shared.lookup(keys)
+    assert bool(found.all()) and np.array_equal(rows.cpu().numpy(), r_shared)
+    # both halves of the slot range are in use
+    assert all(int((s.view(-1, 4)[:, 0] != 0).sum()) > 0.4 * len(k_shared) for s in shards)
+
+
+def test_sharded_rollout_rejects_bad_shard_lists():
+    import ctypes
+    import torch
+    import g2048
+    L = g2048.lib()
+    t = torch.zeros(4 * 1024, dtype=torch.int64, device="cuda")
+    b = torch.zeros(8, dtype=torch.int64, device="cuda")
+    three = (ctypes.c_void_p * 3)(t.data_ptr(), t.data_ptr(), t.data_ptr())
+    args = (8, 4, 0, 0.1, 0.9, 0.1, 1, 0, 0, None, None)
+    assert L.g2048_rollout_qlearn_sharded(b.data_ptr(), None, None, three, 3, 1024, *args) == -1     # not 2^k shards
+    two = (ctypes.c_void_p * 2)(t.data_ptr(), 0)
+    assert L.g2048_rollout_qlearn_sharded(b.data_ptr(), None, None, two, 2, 1024, *args) == -1        # null shard
+    one = (ctypes.c_void_p * 1)(t.data_ptr())
+    assert L.g2048_rollout_qlearn_sharded(b.data_ptr(), None, None, one, 1, 1000, *args) == -1        # not 2^k slots
+    assert L.g2048_rollout_qlearn_sharded(b.data_ptr(), None, None, one, 1, 1 << 32, *args) == -1     # > 2^31 slots
+
+
+def _shared_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import g2048
+    from g2048 import dist as gdist
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = gdist.shard_range(20_000, rank, world)
+    env = g2048.BatchedGame2048Env(hi - lo, "penalty", seed=SEED, env_id_base=lo)
+    env.reset()
+    shared = gdist.SharedQTable(g2048.lib(), torch.device("cuda", 0), 1 << 21)
+    for _ in range(3):
+        shared.rollout(env, 16, 0.1, 0.99, 1.0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    total = shared.size()
+    keys, rows = shared.export_local()
+    np.savez(os.path.join(out, f"shared{rank}.npz"), keys=keys, rows=rows, total=total, boards=np_boards(env.boards))
+    shared.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_processes_learn_one_table_through_peer_memory(tmp_path):
+    """Two processes each own half of the slot range and run the fused rollout on their env shard at the same time;
+    the union of the two shards holds exactly the states a single process visits with all the envs."""
+    import torch
+    import torch.multiprocessing as mp
+    import g2048
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_shared_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    env = g2048.BatchedGame2048Env(20_000, "penalty", seed=SEED)
+    agent = g2048.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 1.0, capacity=1 << 22, seed=SEED)
+    env.reset()
+    for _ in range(3):
+        agent.rollout(env, 16)
+    k1, r1 = agent.export()
+    d = [np.load(tmp_path / f"shared{r}.npz") for r in range(2)]
+    union = np.sort(np.concatenate([d[0]["keys"], d[1]["keys"]]))
+    assert np.array_equal(union, k1)
+    assert int(d[0]["total"]) == int(d[1]["total"]) == len(k1)
+    assert min(len(d[0]["keys"]), len(d[1]["keys"])) > 0.4 * len(k1)
+    assert np.array_equal(np.concatenate([d[0]["boards"], d[1]["boards"]]), np_boards(env.boards))
