@@ -89,6 +89,9 @@ def ncu_dram_ops_per_step():
         return None
 
 
+NVLINK_REQUESTS_PER_SEC = 6.69e9   # measured: tools/membench4.cu on 2 B200 (profiles/r01_membench.txt)
+
+
 def random_access_peak():
     """Live measurement of what HBM gives random slot reads (tools/membench: dependent random 32-byte loads over
     8 GiB at 1024 threads/SM).  Every such miss moves a 128-byte line (profiles/r01_membench.txt)."""
@@ -566,7 +569,16 @@ def shared_table_measurement(torch, dist, g2048, dev, rank, world, n, max_over_r
     c = tot.cpu().numpy()
     states = shared.size()
     shared.close()
+    # table requests of one env step: one update CAS, a lookup (x probes) when the move changed the board or the game
+    # was reset, an insert CAS per new state; (world-1)/world of them cross NVLink, which carries
+    # NVLINK_REQUESTS_PER_SEC small requests per GPU whatever their kind (tools/membench4.cu, profiles/r01_membench.txt)
+    req = (float(c[0]) + float(c[1]) + float(c[2]) + float(c[6])) / max(float(c[0]), 1.0)
+    remote = (world - 1) / world
+    bound = NVLINK_REQUESTS_PER_SEC / (req * remote) if remote else None
     out = {"env_steps_per_sec": world * n * k * launches / dt, "per_gpu": n * k * launches / dt, "ms_per_launch": dt / launches * 1e3,
+           "table_requests_per_env_step": req, "nvlink_small_requests_per_sec_per_gpu": NVLINK_REQUESTS_PER_SEC,
+           "nvlink_bound_env_steps_per_sec_per_gpu": bound,
+           "frac_of_nvlink_request_bound": (n * k * launches / dt / bound) if bound else None,
            "rank0_ms_of_each_launch": per_launch,
            "envs_per_gpu": n, "env_steps_per_launch": k, "table_slots_total": 1 << 31, "slots_per_gpu": slots,
            "states_in_table": states, "load_factor_end": states / float(1 << 31), "remote_access_fraction": (world - 1) / world,
