@@ -497,16 +497,61 @@ k_apply_atomic(Slot* tab, const u64* sortkey, const float* target, float lr, lon
         q_update_atomic(q, __ldcg(q), lr, target[i]);
     }
 }
-// sorted (stable) records: the head of every run applies its run in order, q <- q + lr (target - q)
+// sorted (stable) records: every run of equal keys is applied in order, q <- q + lr (target - q) record after
+// record (the reference's update, main.py:43, in sequence).  The head of a run of up to kInlineRun records applies
+// it itself; longer runs (early-game states shared by thousands of envs) are queued for k_long_run_apply, because
+// one thread walking a long run pays a full load latency per record (measured: 16 ms for the first step after a
+// reset of 8 M envs).  worklist[0] = number of queued runs (zeroed by the caller), worklist[1 + w] = index of the head.
+constexpr int kInlineRun = 8;
 __global__ void __launch_bounds__(256)
-k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n) {
+k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, u64* worklist) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         u64 k = sortkey[i];
         if (k == ~0ull || (i > 0 && sortkey[i - 1] == k)) continue;
+        long long j = i + 1;
+        while (j - i <= kInlineRun && j < n && sortkey[j] == k) ++j;
+        if (j - i > kInlineRun) {
+            u64 w = atomicAdd((unsigned long long*)&worklist[0], 1ull);
+            worklist[1 + w] = (u64)i;
+            continue;
+        }
         float* qp = &tab[k >> 2].q[k & 3];
-        float q = td_apply(*qp, lr, target[i]);
-        for (long long j = i + 1; j < n && sortkey[j] == k; ++j) q = td_apply(q, lr, target[j]);
+        float q = *qp;
+        for (long long t = i; t < j; ++t) q = td_apply(q, lr, target[t]);
         *qp = q;
+    }
+}
+// One warp per long run: the lanes fetch 32 records at a time (coalesced, the next chunk in flight while the
+// current one is consumed) and every lane runs the same sequential chain over the shuffled targets -- 3 dependent
+// float operations per record, the order of the records untouched, so the result is bit-identical to the serial walk.
+__global__ void __launch_bounds__(256)
+k_long_run_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, const u64* worklist) {
+    const int lane = threadIdx.x & 31;
+    const u64 n_warps = (u64)gridDim.x * (blockDim.x >> 5);
+    const u64 count = worklist[0];
+    for (u64 w = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += n_warps) {
+        long long j = (long long)worklist[1 + w];
+        const u64 k = sortkey[j];
+        float* qp = &tab[k >> 2].q[k & 3];
+        float q = *qp;
+        u64 kk = (j + lane < n) ? sortkey[j + lane] : ~k;
+        float tt = (j + lane < n) ? target[j + lane] : 0.f;
+        for (;;) {
+            unsigned m = __ballot_sync(0xFFFFFFFFu, kk == k);
+            int cnt = (m == 0xFFFFFFFFu) ? 32 : __ffs(~m) - 1;   // records of this run in the chunk (a prefix)
+            u64 kn = ~k;
+            float tn = 0.f;
+            if (cnt == 32 && j + 32 + lane < n) { kn = sortkey[j + 32 + lane]; tn = target[j + 32 + lane]; }
+            if (cnt == 32) {
+#pragma unroll
+                for (int l = 0; l < 32; ++l) q = td_apply(q, lr, __shfl_sync(0xFFFFFFFFu, tt, l));
+            } else {
+                for (int l = 0; l < cnt; ++l) q = td_apply(q, lr, __shfl_sync(0xFFFFFFFFu, tt, l));
+                break;
+            }
+            j += 32; kk = kn; tt = tn;
+        }
+        if (lane == 0) *qp = q;
     }
 }
 
@@ -1079,8 +1124,14 @@ int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int6
     while ((1ull << (end_bit - 3)) < capacity) ++end_bit;
     CK(cub::DeviceRadixSort::SortPairs(s.cub_temp, s.cub_bytes, (const u64*)s.key_in, s.key_out, (const float*)s.val_in,
                                        s.val_out, (int64_t)n, 0, end_bit, st));
-    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n);
+    u64* worklist = s.key_in;   // the sort's input is dead now: reuse it for the queue of long runs (< n / 8 entries)
+    CK(cudaMemsetAsync(worklist, 0, sizeof(u64), st));
+    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist);
     LAUNCH_CHECK("k_segment_apply");
+    if (n > kInlineRun) {
+        k_long_run_apply<<<D->sm_count * 4, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist);
+        LAUNCH_CHECK("k_long_run_apply");
+    }
     return 0;
 }
 }  // namespace
