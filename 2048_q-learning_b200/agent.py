@@ -54,8 +54,12 @@ class BatchedQLearningAgent:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._scratch
 
-    def update_q_value(self, state, action, reward, next_state, done, mode: str = "atomic") -> None:
-        """update_q_value (main.py:40-43) for N transitions as one synchronous batch (float32)."""
+    def update_q_value(self, state, action, reward, next_state, done, mode: str = "deterministic") -> None:
+        """update_q_value (main.py:40-43) for N transitions as one synchronous batch (float32).  "deterministic"
+        applies the targets of one (state, action) in batch order (any number of collisions, long runs go to a
+        warp-cooperative kernel); "atomic" skips the sort -- faster for batches with few collisions (7.8 vs 5.6 G
+        updates/s), but a value that thousands of transitions hit at once is then updated at one L2 round trip per
+        transition."""
         n = state.numel()
         with torch.cuda.device(self.device):
             a, d = _u8(action, self.device), _u8(done, self.device)

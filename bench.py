@@ -69,6 +69,24 @@ def ncu_traffic():
         return None
 
 
+def ncu_rollout_random_pipes():
+    """Integer-pipe picture of k_rollout_random<penalty> from the committed ncu --set full capture: the env step is
+    ALU-bound, not memory-bound (SURVEY.md 8d 'Roofline -- env step')."""
+    try:
+        ks = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_final_build.json")))["kernels"]
+        k = next(x for x in ks if "k_rollout_random" in x["kernel"])
+        num = lambda key: float(str(k[key]).split()[0])
+        return {"alu_pipe_active_pct": num("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                "issue_slots_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "thread_instructions_per_env_step": num("smsp__inst_executed.sum") *
+                num("smsp__thread_inst_executed_per_inst_executed.ratio") / (float(1 << 20) * 64),
+                "shared_wavefronts_per_warp_step": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") * 32 / (float(1 << 20) * 64),
+                "dram_throughput_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                "source": "profiles/r01_ncu_full_final_build.json (ncu --set full)"}
+    except Exception:
+        return None
+
+
 def rmw_peak():
     """Live: random 32-byte load + 4-byte store to the same sector over 8 GiB (tools/membench3) -- the access pattern
     of one Q-table lookup followed by the update of one of its values."""
@@ -614,6 +632,9 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
         dt = timed(lambda: L.g2048_rollout_random(b.data_ptr(), a.data_ptr(), s.data_ptr(), n, 64, flavour, SEED, 0, base,
                                                   cnt.data_ptr(), stream), 10)
         out[f"random_policy_rollout_{name}"] = {"env_steps_per_sec": n * 64 / dt, "ms_per_launch": dt * 1e3}
+        if flavour == 0:
+            out[f"random_policy_rollout_{name}"]["bound"] = "integer ALU pipe"
+            out[f"random_policy_rollout_{name}"]["ncu"] = ncu_rollout_random_pipes()
     # (b) single-step env API, state in HBM every call (HBM bound: 38 B/step)
     act = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev)
     r64 = torch.zeros(n, dtype=torch.float64, device=dev)

@@ -77,7 +77,9 @@
 #define G2048_N_COUNTERS 9
 
 /* Q-learning modes */
-#define G2048_MODE_ATOMIC 0         /* q <- q + lr (target - q) as an atomic CAS loop (order among duplicates unspecified) */
+#define G2048_MODE_ATOMIC 0         /* q <- q + lr (target - q) as an atomic CAS loop (order among duplicates unspecified);
+                                       no sort: the fast choice for batches with few collisions.  A value hit by thousands
+                                       of records at once costs one L2 round trip per record: use DETERMINISTIC there */
 #define G2048_MODE_DETERMINISTIC 1  /* sort by (state, action), duplicates applied one after another in ascending env order */
 
 #define G2048_QTABLE_SLOT_BYTES 32  /* key u64 | meta u64 | float q[4] */
