@@ -422,6 +422,10 @@ def main():
         sh = shared_table_measurement(torch, dist, g2048, dev, rank, world, min(n, 1 << 20), max_over_ranks, barrier)
         if rank == 0:
             extras["shared_table_over_nvlink"] = sh
+    if args.dqn and world > 1:
+        dp = dqn_data_parallel_measurement(torch, dist, g2048, dev, rank, world, max_over_ranks, barrier)
+        if rank == 0:
+            extras["dqn_data_parallel_replay"] = dp
     if args.dqn and rank == 0:
         extras["dqn_in_the_loop"] = dqn_measurement(torch, g2048, dev)
     if not args.no_extras and rank == 0:
@@ -509,6 +513,41 @@ def dqn_measurement(torch, g2048, dev, n=65536, steps=3):
     return {"env_steps_per_sec_with_network": n / t_all, "ms_per_step": t_all * 1e3, "env_side_ms_per_step": t_env * 1e3,
             "network_share": 1 - t_env / t_all, "network_TFLOPs": flops / (t_all - t_env) / 1e12, "envs": n,
             "parameters": sum(p.numel() for p in agent.model.parameters()), "dtype": "bf16"}
+
+
+def dqn_data_parallel_measurement(torch, dist, g2048, dev, rank, world, max_over_ranks, barrier, n=4096, steps=5):
+    """Config 5, training side across GPUs: every rank feeds its own env shard into its replay memory and replay()
+    averages the gradients of the 197 M-parameter network with ONE all-reduce of a flat fp32 buffer (789 MB) over
+    NVLink (BatchedDQNAgent.data_parallel / dist.GradientAllReduce)."""
+    from g2048 import dqn
+    env = g2048.BatchedGame2048Env(n, "nopenalty", device=dev.index, seed=SEED, env_id_base=rank * n)
+    agent = dqn.BatchedDQNAgent(device=dev.index, memory_size=1 << 16, batch_size=64, epsilon=0.5, seed=SEED + rank)
+    env.reset()
+    agent.data_parallel()
+    for _ in range(4):
+        dqn.dqn_step(env, agent)
+    agent.replay()
+    barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(steps):
+        agent.replay()
+    e1.record()
+    for _ in range(steps):
+        agent.grad_sync()
+    e2.record()
+    barrier()
+    t_replay = max_over_ranks(e0.elapsed_time(e1) / steps)
+    t_ar = max_over_ranks(e1.elapsed_time(e2) / steps)
+    nbytes = agent.grad_sync.flat.numel() * agent.grad_sync.flat.element_size()
+    p0 = torch.cat([p.detach().flatten()[:64] for p in agent.model.parameters()]).double().sum()
+    allp = [torch.zeros_like(p0) for _ in range(world)]
+    dist.all_gather(allp, p0)
+    del agent, env
+    torch.cuda.empty_cache()
+    return {"ms_per_replay_step_batch64": t_replay, "ms_allreduce_alone": t_ar, "gradient_bytes": nbytes,
+            "allreduce_bus_GBps": nbytes * 2 * (world - 1) / world / (t_ar * 1e-3) / 1e9,
+            "replicas_identical_after_training": len({float(x) for x in allp}) == 1, "dtype": "fp32"}
 
 
 def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_ranks, barrier, steps=24):
