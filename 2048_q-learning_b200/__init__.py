@@ -19,7 +19,7 @@ def __getattr__(name):  # the batched classes need torch: import lazily
     if name in ("BatchedDQNAgent", "DQNModel", "dqn_step", "terminal_bonus", "FusedDQNFeed"):
         from . import dqn
         return getattr(dqn, name)
-    if name in ("ShardedQLearning", "shard_range", "PeerRecordBuffers", "TorchEngine", "GradientAllReduce", "SharedQTable"):
+    if name in ("ShardedQLearning", "shard_range", "PeerRecordBuffers", "TorchEngine", "GradientAllReduce", "SharedQTable", "OwnerComputesQLearning"):
         from . import dist
         return getattr(dist, name)
     raise AttributeError(name)

@@ -439,6 +439,70 @@ k_keys_to_records(Slot* tab, u64 mask, const u64* keys, const uint8_t* a, long l
         sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (u64)(a[i] & 3));
     }
 }
+// ---- exact synchronous step on a SHARDED table: owner computes -------------------------------------------------
+// Phase A of the synchronous step with the table spread over the GPUs: s and s' are looked up (found-or-inserted)
+// wherever their slots live, and the record of the transition is appended to the list of the GPU that OWNS the slot
+// of s.  A record carries the owner-local sort key directly -- ((local slot * 4 + action) << idx_bits) | global
+// env index -- so the owner neither looks anything up nor depends on the order of the appends: sorting the composite
+// key groups each (state, action) and orders its records by global env id, exactly the single-GPU order.
+struct OwnedLists {
+    ulonglong2* list[G2048_MAX_PEERS];   // list[j]: this rank's records for owner j (room for n each)
+    unsigned long long* count;           // count[j], zeroed by the caller
+    int idx_bits;
+};
+template <int FLAVOUR>
+__global__ void __launch_bounds__(256)
+k_qlearn_emit_owned(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ ShardedTable table, long long n,
+                    float gamma, u64 eps_thresh, u64 seed, u64 t, u64 id_base, u64 rec_base, long long* counters,
+                    const __grid_constant__ OwnedLists out) {
+    __shared__ Slot* shard_base[G2048_MAX_PEERS];
+    __shared__ ulonglong2* list_base[G2048_MAX_PEERS];
+    if (threadIdx.x < G2048_MAX_PEERS) list_base[threadIdx.x] = out.list[threadIdx.x];
+    const auto tab = table.view(shard_base);   // (syncs the block)
+    Lut L = global_lut(T);
+    Counters c;
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {   // warp-uniform
+        const long long i = i0 + lane;
+        int owner = -1;
+        u64 key = 0;
+        float target = 0.f;
+        if (i < n) {
+            Env e;
+            env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
+            u64 id = id_base + (u64)i;
+            float4 row, row2;
+            u32 slot = table_find<true>(tab, e.board, row, c.inserts);
+            c.dropped += (slot == kNoSlot);
+            Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
+            int a = choose_action(row, x, eps_thresh);
+            StepOut o;
+            philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
+            c.add(o);
+            u32 slot2 = table_find<true>(tab, e.board, row2, c.inserts);
+            c.dropped += (slot2 == kNoSlot);
+            target = td_target(gamma, (float)o.reward, max4(row2), o.done);
+            if (slot != kNoSlot) {
+                owner = (int)((u64)slot >> tab.shift);
+                key = (((((u64)slot & tab.low) << 2) | (u64)a) << out.idx_bits) | (rec_base + (u64)i);
+            }
+            if (o.done) philox_autoreset(e, seed, id, t);
+            boards[i] = e.board;
+            if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
+            if (score) score[i] = e.score;
+        }
+        // one atomicAdd per (warp, owner): the lanes that share an owner take consecutive places
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, owner);
+        int leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if (lane == leader && owner >= 0) base = atomicAdd(&out.count[owner], (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (owner >= 0)
+            list_base[owner][base + __popc(peers & ((1u << lane) - 1))] = make_ulonglong2(key, (u64)__float_as_uint(target));
+    }
+    flush_counters(c, counters);
+}
 // ---- record lists that may live in the HBM of OTHER GPUs (NVLink peer memory) ---------------------------------
 // Up to kMaxLists lists of 16-byte records {key, action | target bits << 32}; list j holds the records of rank j in
 // ascending env order, so walking the lists in order visits ascending GLOBAL env ids.
@@ -463,6 +527,20 @@ k_peer_records_to_sortkeys(Slot* tab, u64 mask, RecordLists R, long long n, u64*
         u32 slot = table_find<true>(tab, mask, key, row, ins);
         sortkey[i] = slot == kNoSlot ? ~0ull : ((u64)slot * 4 + (at & 3));
         target[i] = __uint_as_float((u32)(at >> 32));
+    }
+}
+// owner-computes form: the owner pulls its lists out of every rank's memory (NVLink peer reads, coalesced) into the
+// sort buffers; the records already carry the sort key
+__global__ void __launch_bounds__(256)
+k_gather_owned(RecordLists R, long long n, u64* sortkey, float* target) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (j + 1 < R.n_lists && i >= R.end[j]) ++j;
+        long long local = i - (j ? R.end[j - 1] : 0);
+        u64 key, tb;
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(key), "=l"(tb) : "l"(R.ptr[j] + local) : "memory");
+        sortkey[i] = key;
+        target[i] = __uint_as_float((u32)tb);
     }
 }
 // Barrier between the GPUs of one box through flags in peer memory: rank r stores `epoch` into flags[r] of every
@@ -504,12 +582,15 @@ k_apply_atomic(Slot* tab, const u64* sortkey, const float* target, float lr, lon
 // reset of 8 M envs).  worklist[0] = number of queued runs (zeroed by the caller), worklist[1 + w] = index of the head.
 constexpr int kInlineRun = 8;
 __global__ void __launch_bounds__(256)
-k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, u64* worklist) {
+k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, u64* worklist, int kshift) {
+    // kshift: low bits of the sort key that only order the records of a run (0 here; the global env index in the
+    // owner-computes form); the all-ones key ("no slot") is checked before shifting
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        u64 k = sortkey[i];
-        if (k == ~0ull || (i > 0 && sortkey[i - 1] == k)) continue;
+        u64 raw = sortkey[i];
+        u64 k = raw >> kshift;
+        if (raw == ~0ull || (i > 0 && (sortkey[i - 1] >> kshift) == k)) continue;
         long long j = i + 1;
-        while (j - i <= kInlineRun && j < n && sortkey[j] == k) ++j;
+        while (j - i <= kInlineRun && j < n && (sortkey[j] >> kshift) == k) ++j;
         if (j - i > kInlineRun) {
             u64 w = atomicAdd((unsigned long long*)&worklist[0], 1ull);
             worklist[1 + w] = (u64)i;
@@ -525,23 +606,24 @@ k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, lo
 // current one is consumed) and every lane runs the same sequential chain over the shuffled targets -- 3 dependent
 // float operations per record, the order of the records untouched, so the result is bit-identical to the serial walk.
 __global__ void __launch_bounds__(256)
-k_long_run_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, const u64* worklist) {
+k_long_run_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, const u64* worklist,
+                 int kshift) {
     const int lane = threadIdx.x & 31;
     const u64 n_warps = (u64)gridDim.x * (blockDim.x >> 5);
     const u64 count = worklist[0];
     for (u64 w = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += n_warps) {
         long long j = (long long)worklist[1 + w];
-        const u64 k = sortkey[j];
+        const u64 k = sortkey[j] >> kshift;
         float* qp = &tab[k >> 2].q[k & 3];
         float q = *qp;
-        u64 kk = (j + lane < n) ? sortkey[j + lane] : ~k;
+        u64 kk = (j + lane < n) ? (sortkey[j + lane] >> kshift) : ~k;
         float tt = (j + lane < n) ? target[j + lane] : 0.f;
         for (;;) {
             unsigned m = __ballot_sync(0xFFFFFFFFu, kk == k);
             int cnt = (m == 0xFFFFFFFFu) ? 32 : __ffs(~m) - 1;   // records of this run in the chunk (a prefix)
             u64 kn = ~k;
             float tn = 0.f;
-            if (cnt == 32 && j + 32 + lane < n) { kn = sortkey[j + 32 + lane]; tn = target[j + 32 + lane]; }
+            if (cnt == 32 && j + 32 + lane < n) { kn = sortkey[j + 32 + lane] >> kshift; tn = target[j + 32 + lane]; }
             if (cnt == 32) {
 #pragma unroll
                 for (int l = 0; l < 32; ++l) q = td_apply(q, lr, __shfl_sync(0xFFFFFFFFu, tt, l));
@@ -1110,7 +1192,8 @@ int carve(void* scratch, size_t bytes, int64_t n, Scratch& s) {
     return 0;
 }
 // apply the records in s.key_in / s.val_in
-int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, float lr, int mode, cudaStream_t st) {
+int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, float lr, int mode, cudaStream_t st,
+                  int kshift = 0) {
     int g = grid_for(n, 256, D->sm_count);
     if (mode == G2048_MODE_ATOMIC) {
         k_apply_atomic<<<g, 256, 0, st>>>(tab, s.key_in, s.val_in, lr, n);
@@ -1122,14 +1205,16 @@ int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int6
     // The sort is stable: equal keys keep ascending record (= env) order.
     int end_bit = 3;
     while ((1ull << (end_bit - 3)) < capacity) ++end_bit;
+    end_bit += kshift;
+    if (end_bit > 64) end_bit = 64;
     CK(cub::DeviceRadixSort::SortPairs(s.cub_temp, s.cub_bytes, (const u64*)s.key_in, s.key_out, (const float*)s.val_in,
                                        s.val_out, (int64_t)n, 0, end_bit, st));
     u64* worklist = s.key_in;   // the sort's input is dead now: reuse it for the queue of long runs (< n / 8 entries)
     CK(cudaMemsetAsync(worklist, 0, sizeof(u64), st));
-    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist);
+    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist, kshift);
     LAUNCH_CHECK("k_segment_apply");
     if (n > kInlineRun) {
-        k_long_run_apply<<<D->sm_count * 4, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist);
+        k_long_run_apply<<<D->sm_count * 4, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist, kshift);
         LAUNCH_CHECK("k_long_run_apply");
     }
     return 0;
@@ -1212,6 +1297,80 @@ G2048_API int g2048_qtable_apply_records(void* table, uint64_t capacity, const g
                                                                                       sc.key_in, sc.val_in);
     LAUNCH_CHECK("k_peer_records_to_sortkeys");
     return apply_records(D, (Slot*)table, capacity, sc, n, lr, mode, S(stream));
+}
+
+G2048_API int g2048_qlearn_emit_owned(uint64_t* boards, uint64_t* aux, int32_t* score, const void* const* shards,
+                                      int n_shards, uint64_t slots_per_shard, int64_t n, int flavour, float gamma,
+                                      double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base,
+                                      uint64_t record_index_base, int idx_bits, int64_t* counters,
+                                      g2048_record* const* owner_lists, uint64_t* owner_counts, void* stream) {
+    DEVSTATE();
+    if (n < 0 || (n && !boards) || (flavour != 0 && flavour != 1) || !owner_lists || !owner_counts || idx_bits < 1 ||
+        idx_bits > 40)
+        return fail(G2048_ERR_ARG, "g2048_qlearn_emit_owned: bad arguments");
+    ShardedTable t;
+    int rc = make_sharded(shards, n_shards, slots_per_shard, t, "g2048_qlearn_emit_owned: bad shard list");
+    if (rc) return rc;
+    if ((int)t.shift + 2 + idx_bits > 64 || ((record_index_base + (uint64_t)n - 1) >> idx_bits) != 0)
+        return fail(G2048_ERR_ARG, "g2048_qlearn_emit_owned: record index does not fit idx_bits");
+    OwnedLists out{};
+    for (int j = 0; j < n_shards; ++j) {
+        if (!owner_lists[j] || ((uintptr_t)owner_lists[j] & 15)) return fail(G2048_ERR_ARG, "g2048_qlearn_emit_owned: bad owner list");
+        out.list[j] = (ulonglong2*)owner_lists[j];
+    }
+    out.count = (unsigned long long*)owner_counts;
+    out.idx_bits = idx_bits;
+    if (n == 0) return 0;
+    int g = grid_for(n, 256, D->sm_count);
+#define EMIT(F)                                                                                                       \
+    k_qlearn_emit_owned<F><<<g, 256, 0, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, t, n, gamma,           \
+                                                     eps_threshold(eps), seed, step_idx, env_id_base, record_index_base, \
+                                                     (long long*)counters, out)
+    if (flavour == 0) EMIT(0); else EMIT(1);
+#undef EMIT
+    LAUNCH_CHECK("k_qlearn_emit_owned");
+    return 0;
+}
+
+G2048_API int g2048_qtable_apply_owned(void* shard, uint64_t slots_per_shard, const g2048_record* const* lists,
+                                       const int64_t* counts, int n_lists, int idx_bits, float lr, void* scratch,
+                                       size_t scratch_bytes_, void* stream) {
+    DEVSTATE();
+    if (!shard || !pow2(slots_per_shard) || !lists || !counts || n_lists < 1 || n_lists > G2048_MAX_PEERS || idx_bits < 1 ||
+        idx_bits > 40)
+        return fail(G2048_ERR_ARG, "g2048_qtable_apply_owned: bad arguments");
+    RecordLists R{};
+    long long n = 0;
+    for (int j = 0; j < n_lists; ++j) {
+        if (counts[j] < 0 || (counts[j] && !lists[j]) || ((uintptr_t)lists[j] & 15))
+            return fail(G2048_ERR_ARG, "g2048_qtable_apply_owned: bad record list");
+        R.ptr[j] = (const ulonglong2*)lists[j];
+        n += counts[j];
+        R.end[j] = n;
+    }
+    R.n_lists = n_lists;
+    if (n == 0) return 0;
+    Scratch sc{};
+    int rc = carve(scratch, scratch_bytes_, n, sc);
+    if (rc) return rc;
+    k_gather_owned<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>(R, n, sc.key_in, sc.val_in);
+    LAUNCH_CHECK("k_gather_owned");
+    return apply_records(D, (Slot*)shard, slots_per_shard, sc, n, lr, G2048_MODE_DETERMINISTIC, S(stream), idx_bits);
+}
+
+G2048_API int g2048_peer_read_u64(const uint64_t* const* src, int n, uint64_t* host_out, void* stream) {
+    if (!src || !host_out || n < 0) return fail(G2048_ERR_ARG, "g2048_peer_read_u64: bad arguments");
+    for (int j = 0; j < n; ++j) {
+        if (!src[j]) return fail(G2048_ERR_ARG, "g2048_peer_read_u64: null pointer");
+        CK(cudaMemcpyAsync(host_out + j, src[j], sizeof(uint64_t), cudaMemcpyDeviceToHost, S(stream)));
+    }
+    CK(cudaStreamSynchronize(S(stream)));
+    return 0;
+}
+G2048_API int g2048_peer_memset(void* dev_ptr, int value, size_t bytes, void* stream) {
+    if (!dev_ptr) return fail(G2048_ERR_ARG, "g2048_peer_memset: bad arguments");
+    CK(cudaMemsetAsync(dev_ptr, value, bytes, S(stream)));
+    return 0;
 }
 
 // ---- NVLink peer memory between the per-GPU processes of one box (CUDA IPC)

@@ -306,6 +306,108 @@ class SharedQTable:
                 self._mine = None
 
 
+class OwnerComputesQLearning:
+    """Exact synchronous Q-learning on ONE table sharded over the GPUs (`SharedQTable`), owner computes: per step every
+    rank advances its envs against the shared table and appends each transition's record to the list of the GPU that
+    owns the slot of its state; after a flag barrier every GPU sorts and applies only the records for ITS shard, which
+    it reads in place from the other GPUs' memory.  Same result as the single-GPU deterministic step (bit for bit),
+    but the sort/apply work per GPU is 1/G of the global batch instead of all of it (`ShardedQLearning`)."""
+
+    HEAD = 512                                   # flags (256 B) + 2 x 16 counters
+
+    def __init__(self, env, shared: SharedQTable, n_total: int, lr: float, gamma: float, eps: float, group=None):
+        import ctypes
+        from ._lib import check
+        self._check, self._ct = check, ctypes
+        self.env, self.shared, self.group = env, shared, group
+        self.lr, self.gamma, self.eps = lr, gamma, eps
+        self.lib, self.device = shared.lib, shared.device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if shared.n_shards != self.world:
+            raise ValueError("one shard per rank")
+        self.n_total = int(n_total)
+        self.idx_bits = max(1, (self.n_total - 1).bit_length())
+        self.lo, _ = shard_range(self.n_total, self.rank, self.world)
+        self.cap = max(hi - lo for lo, hi in (shard_range(self.n_total, r, self.world) for r in range(self.world)))
+        self.list_bytes = ((self.cap * 16 + 255) // 256) * 256
+        nbytes = self.HEAD + 2 * self.world * self.list_bytes
+        mine, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_peer_alloc(nbytes, ctypes.byref(mine), handle), "g2048_peer_alloc")
+            allh = [None] * self.world
+            dist.all_gather_object(allh, bytes(handle), group=group)
+            self.base, self._opened = [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.base.append(mine.value)
+                    continue
+                p = ctypes.c_void_p()
+                check(self.lib.g2048_peer_open((ctypes.c_ubyte * 64)(*allh[r]), ctypes.byref(p)), "g2048_peer_open")
+                self.base.append(p.value)
+                self._opened.append(p.value)
+            self._mine = mine.value
+            self._flags = (ctypes.c_void_p * self.world)(*self.base)
+            self.timed_out = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._scratch = None
+        self.epoch, self.t = 0, 0
+        dist.barrier(group=group)
+
+    # layout helpers: counts[slot][j] and list[slot][j] inside rank r's buffer
+    def _counts(self, r, slot):
+        return self.base[r] + 256 + slot * 128
+
+    def _list(self, r, slot, j):
+        return self.base[r] + self.HEAD + (slot * self.world + j) * self.list_bytes
+
+    def _barrier(self):
+        self.epoch += 1
+        self._check(self.lib.g2048_peer_barrier(self._flags, self.rank, self.world, self.epoch, 0,
+                                                self.timed_out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                    "g2048_peer_barrier")
+
+    def step(self):
+        ct, env, sh, slot = self._ct, self.env, self.shared, self.t & 1
+        st = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(self.device):
+            self._check(self.lib.g2048_peer_memset(self._counts(self.rank, slot), 0, 128, st), "g2048_peer_memset")
+            lists = (ct.c_void_p * self.world)(*[self._list(self.rank, slot, j) for j in range(self.world)])
+            self._check(self.lib.g2048_qlearn_emit_owned(
+                env.boards.data_ptr(), env.aux.data_ptr(), env.score.data_ptr(), sh._arr, sh.n_shards, sh.slots_per_shard,
+                env.n, env.flavour, self.gamma, float(self.eps), env.seed, env.step_idx, env.env_id_base, self.lo,
+                self.idx_bits, env.counters.data_ptr(), lists, self._counts(self.rank, slot), st), "g2048_qlearn_emit_owned")
+            env.step_idx += 1
+            self._barrier()                                     # every rank's records and counts are written
+            src = (ct.c_void_p * self.world)(*[self._counts(r, slot) + 8 * self.rank for r in range(self.world)])
+            host = (ct.c_uint64 * self.world)()
+            self._check(self.lib.g2048_peer_read_u64(src, self.world, host, st), "g2048_peer_read_u64")
+            counts = (ct.c_int64 * self.world)(*[int(x) for x in host])
+            total = sum(int(x) for x in host)
+            need = int(self.lib.g2048_qlearn_scratch_bytes(max(total, 1)))
+            if self._scratch is None or self._scratch.numel() < need:
+                self._scratch = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
+            mine = (ct.c_void_p * self.world)(*[self._list(r, slot, self.rank) for r in range(self.world)])
+            self._check(self.lib.g2048_qtable_apply_owned(sh.ptrs[self.rank], sh.slots_per_shard, mine, counts, self.world,
+                                                          self.idx_bits, self.lr, self._scratch.data_ptr(),
+                                                          self._scratch.numel(), st), "g2048_qtable_apply_owned")
+            self._barrier()                                     # all shards updated before anyone reads them again
+        self.t += 1
+        return total
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            v = int(self.timed_out.item())
+            dist.barrier(group=self.group)
+            for p in self._opened:
+                self.lib.g2048_peer_close(p)
+            self._opened = []
+            if self._mine:
+                self.lib.g2048_peer_free(self._mine)
+                self._mine = None
+        if v:
+            raise RuntimeError(f"peer barrier timed out waiting for rank {v - 1}")
+
+
 class GradientAllReduce:
     """Data-parallel DQN (BASELINE config 5): every parameter's .grad is a view into ONE flat buffer,
     so a training step costs a single all-reduce over NVSwitch (no per-tensor launches, no bucket copies), followed

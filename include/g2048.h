@@ -231,6 +231,29 @@ G2048_API int g2048_qlearn_emit(uint64_t* boards, uint64_t* aux, int32_t* score,
 G2048_API int g2048_qtable_apply_records(void* table, uint64_t capacity, const g2048_record* const* lists,
                                          const int64_t* counts, int n_lists, float lr, int mode, void* scratch,
                                          size_t scratch_bytes, void* stream);
+/* The exact synchronous step on ONE table sharded over the GPUs (see g2048_rollout_qlearn_sharded for the shard
+ * list), owner computes: g2048_qlearn_emit_owned advances the envs like g2048_qlearn_emit, looking s and s' up
+ * wherever their slots live, and appends the record of each transition to owner_lists[j] (HOST array of n_shards
+ * device pointers, room for n records each) of the GPU j that owns the slot of s; owner_counts[j] (device, zeroed by
+ * the caller) counts them.  A record holds ((owner-local slot * 4 + action) << idx_bits) | (record_index_base + i)
+ * and the float32 target; idx_bits >= log2(total envs of the job), record_index_base = first global env index of
+ * this rank.  After a barrier, g2048_qtable_apply_owned on GPU j sorts the lists every rank wrote for j (read in place,
+ * local or peer memory; counts[] on the HOST, e.g. from g2048_peer_read_u64) and applies them to ITS shard, record
+ * after record in global env order: q <- q + lr (target - q) (main.py:43).  The result equals the single-GPU
+ * deterministic step bit for bit, and every GPU sorts only its share of the records.  A second barrier must separate
+ * the apply from the next emit (which reads remote shards). */
+G2048_API int g2048_qlearn_emit_owned(uint64_t* boards, uint64_t* aux, int32_t* score, const void* const* shards,
+                                      int n_shards, uint64_t slots_per_shard, int64_t n, int flavour, float gamma,
+                                      double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base,
+                                      uint64_t record_index_base, int idx_bits, int64_t* counters,
+                                      g2048_record* const* owner_lists, uint64_t* owner_counts, void* stream);
+G2048_API int g2048_qtable_apply_owned(void* shard, uint64_t slots_per_shard, const g2048_record* const* lists,
+                                       const int64_t* counts, int n_lists, int idx_bits, float lr, void* scratch,
+                                       size_t scratch_bytes, void* stream);
+/* n 8-byte values at device (local or peer) addresses src[j] -> host_out[j]; waits for the stream. */
+G2048_API int g2048_peer_read_u64(const uint64_t* const* src, int n, uint64_t* host_out, void* stream);
+G2048_API int g2048_peer_memset(void* dev_ptr, int value, size_t bytes, void* stream);
+
 /* Device memory other processes of this box can map (CUDA IPC): alloc (zero-filled) + 64-byte handle to send to
  * the peers; open/close on the peers' side; free by the owner. */
 G2048_API int g2048_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out);

@@ -257,3 +257,103 @@ def test_two_processes_learn_one_table_through_peer_memory(tmp_path):
     assert int(d[0]["total"]) == int(d[1]["total"]) == len(k1)
     assert min(len(d[0]["keys"]), len(d[1]["keys"])) > 0.4 * len(k1)
     assert np.array_equal(np.concatenate([d[0]["boards"], d[1]["boards"]]), np_boards(env.boards))
+
+
+# ---------------------------------------------------------------- exact synchronous step, owner computes
+def test_owner_computes_step_equals_the_single_table_deterministic_step():
+    """Virtual ranks in one process through the raw C ABI: 2 env shards (ragged), a table of 2 shards; every owner sorts
+    and applies only the records for its shard.  Boards and table content equal the single-GPU deterministic run."""
+    import ctypes
+    import torch
+    import g2048
+    from g2048 import dist as gdist
+    L = g2048.lib()
+    sizes, G, steps, slots = [1700, 1301], 2, 14, 1 << 17
+    n = sum(sizes)
+    boards1, keys1, rows1 = single_process_result(g2048, n, steps)       # capacity CAP = 2 * slots
+    assert CAP == G * slots
+    lo = [0, sizes[0]]
+    idx_bits = (n - 1).bit_length()
+    shards = [torch.zeros(slots * 4, dtype=torch.int64, device="cuda") for _ in range(G)]
+    shared = gdist.SharedQTable(L, torch.device("cuda", 0), slots, shards=shards)
+    envs = [g2048.BatchedGame2048Env(sizes[r], "penalty", seed=SEED, env_id_base=lo[r]) for r in range(G)]
+    for e in envs:
+        e.reset()
+    lists = [[torch.zeros((max(sizes), 2), dtype=torch.int64, device="cuda") for _ in range(G)] for _ in range(G)]
+    counts = [torch.zeros(G, dtype=torch.int64, device="cuda") for _ in range(G)]
+    scratch = torch.empty(L.g2048_qlearn_scratch_bytes(n), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    applied = 0
+    for t in range(steps):
+        for r in range(G):
+            counts[r].zero_()
+            arr = (ctypes.c_void_p * G)(*[x.data_ptr() for x in lists[r]])
+            rc = L.g2048_qlearn_emit_owned(envs[r].boards.data_ptr(), envs[r].aux.data_ptr(), envs[r].score.data_ptr(),
+                                           shared._arr, G, slots, sizes[r], 0, 0.99, 0.4, SEED, t, lo[r], lo[r], idx_bits,
+                                           envs[r].counters.data_ptr(), arr, counts[r].data_ptr(), st)
+            assert rc == 0, L.g2048_last_error()
+        host = torch.stack(counts).cpu().numpy()                 # [rank][owner]
+        assert host.sum() == n
+        for j in range(G):
+            arr = (ctypes.c_void_p * G)(*[lists[r][j].data_ptr() for r in range(G)])
+            cnt = (ctypes.c_int64 * G)(*[int(host[r][j]) for r in range(G)])
+            rc = L.g2048_qtable_apply_owned(shards[j].data_ptr(), slots, arr, cnt, G, idx_bits, 0.1, scratch.data_ptr(),
+                                            scratch.numel(), st)
+            assert rc == 0, L.g2048_last_error()
+            applied += int(host[:, j].sum())
+    assert applied == n * steps
+    got = np.concatenate([np_boards(e.boards) for e in envs])
+    assert np.array_equal(got, boards1)
+    k, rows = shared.export_local()
+    nz = np.abs(rows).sum(1) > 0
+    assert np.array_equal(k[nz], keys1) and np.array_equal(rows[nz], rows1)
+    # both owners had work
+    assert min(int((s.view(-1, 4)[:, 0] != 0).sum()) for s in shards) > 1000
+    # misuse: record index that does not fit idx_bits
+    arr = (ctypes.c_void_p * G)(*[x.data_ptr() for x in lists[0]])
+    assert L.g2048_qlearn_emit_owned(envs[0].boards.data_ptr(), None, None, shared._arr, G, slots, sizes[0], 0, 0.99, 0.4,
+                                     SEED, 0, 0, 1 << 20, 8, None, arr, counts[0].data_ptr(), st) == -1
+
+
+def _owner_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import g2048
+    from g2048 import dist as gdist
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = gdist.shard_range(N_TOTAL, rank, world)
+    env = g2048.BatchedGame2048Env(hi - lo, "penalty", seed=SEED, env_id_base=lo)
+    env.reset()
+    shared = gdist.SharedQTable(g2048.lib(), torch.device("cuda", 0), CAP // world)
+    oc = gdist.OwnerComputesQLearning(env, shared, N_TOTAL, 0.1, 0.99, 0.4)
+    handled = [oc.step() for _ in range(STEPS)]
+    torch.cuda.synchronize()
+    dist.barrier()
+    keys, rows = shared.export_local()
+    nz = np.abs(rows).sum(1) > 0
+    np.savez(os.path.join(out, f"owner{rank}.npz"), boards=np_boards(env.boards), keys=keys[nz], rows=rows[nz], lo=lo, hi=hi,
+             handled=np.array(handled))
+    oc.close()
+    shared.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_processes_owner_computes_through_ipc_peer_memory(tmp_path):
+    import torch.multiprocessing as mp
+    import g2048
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_owner_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    boards1, keys1, rows1 = single_process_result(g2048, N_TOTAL, STEPS)
+    d = [np.load(tmp_path / f"owner{r}.npz") for r in range(2)]
+    for x in d:
+        assert np.array_equal(x["boards"], boards1[int(x["lo"]):int(x["hi"])])
+    assert np.array_equal(d[0]["handled"] + d[1]["handled"], np.full(STEPS, N_TOTAL))
+    keys = np.concatenate([d[0]["keys"], d[1]["keys"]])
+    rows = np.concatenate([d[0]["rows"], d[1]["rows"]])
+    order = np.argsort(keys)
+    assert np.array_equal(keys[order], keys1) and np.array_equal(rows[order], rows1)
