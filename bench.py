@@ -589,6 +589,33 @@ def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_
         out[transport] = {"env_steps_per_sec": world * n * steps / dt, "ms_per_step": dt / steps * 1e3,
                           "replica_digests_sum_and_count_of_nonzero_rows": digests,
                           "replicas_identical": len({tuple(d) for d in digests}) == 1}
+    if world > 1 and world & (world - 1) == 0:
+        # owner computes: ONE table sharded over the GPUs, every GPU sorts/applies only the records for its shard
+        env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
+        env.reset()
+        shared = gdist.SharedQTable(g2048.lib(), dev, (1 << 28) // world)
+        oc = gdist.OwnerComputesQLearning(env, shared, n * world, LR, GAMMA, EPS)
+        for _ in range(3):
+            oc.step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            oc.step()
+        e1.record()
+        barrier()
+        dt = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+        keys, rows = shared.export_local()
+        nz = np.abs(rows).sum(1) > 0
+        t = torch.tensor([float(rows[nz].astype(np.float64).sum()), float(nz.sum())], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        oc.close()
+        shared.close()
+        del env
+        torch.cuda.empty_cache()
+        out["owner_computes"] = {"env_steps_per_sec": world * n * steps / dt, "ms_per_step": dt / steps * 1e3,
+                                 "table_digest_sum_and_count_of_nonzero_rows": t.tolist(),
+                                 "note": "one sharded table; digest = sum over all shards, to compare with one replica's"}
     if "peer" in out:
         out["transports_agree"] = (out["peer"]["replica_digests_sum_and_count_of_nonzero_rows"] ==
                                    out["nccl"]["replica_digests_sum_and_count_of_nonzero_rows"])
