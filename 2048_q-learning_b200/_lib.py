@@ -91,6 +91,7 @@ _SIG = {
     "g2048_qtable_update": (i32, [vp, u64, vp, vp, vp, vp, vp, i64, f32, f32, i32, vp, sz, vp]),
     "g2048_qtable_apply_targets": (i32, [vp, u64, vp, vp, vp, i64, f32, i32, vp, sz, vp]),
     "g2048_qtable_size": (i32, [vp, u64, vp, vp]),
+    "g2048_qtable_probe_stats": (i32, [vp, u64, vp, vp]),
     "g2048_qtable_export": (i32, [vp, u64, vp, vp, i64, vp, vp]),
     "g2048_ctx_create": (vp, [i32, i64, u64]),
     "g2048_ctx_destroy": (None, [vp]),

@@ -156,6 +156,16 @@ class BatchedQLearningAgent:
                   "g2048_qtable_size")
         return int(self._count.item())
 
+    def probe_stats(self) -> dict:
+        """{"states", "mean_probe_length", "max_probe_length", "load_factor"} of the table as it is now."""
+        st = torch.zeros(3, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_qtable_probe_stats(_ptr(self.table), self.capacity, _ptr(st), _stream()),
+                  "g2048_qtable_probe_stats")
+        n, total, mx = (int(x) for x in st.tolist())
+        return {"states": n, "mean_probe_length": 1 + total / max(n, 1), "max_probe_length": 1 + mx,
+                "load_factor": n / self.capacity}
+
     def export(self):
         """(keys uint64[n] as int64 tensor, rows float32[n,4]) sorted by key."""
         n = len(self)

@@ -679,6 +679,28 @@ __global__ void __launch_bounds__(256) k_q_size(const Slot* tab, u64 capacity, l
     c = warp_sum(c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long*)count, (unsigned long long)c);
 }
+// occupancy statistics: out[0] = states, out[1] = sum over states of the distance (in slots) from the home slot
+// mix64(key) & mask, out[2] = the largest distance.  A lookup of a stored state costs 1 + distance probes.
+__global__ void __launch_bounds__(256) k_q_probe_stats(const Slot* tab, u64 capacity, long long* out) {
+    long long cnt = 0, sum = 0, mx = 0;
+    const u64 mask = capacity - 1;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < capacity; i += (u64)gridDim.x * blockDim.x) {
+        u64 k = __ldcg(&tab[i].key);
+        if (k) {
+            long long d = (long long)((i - (mix64(k) & mask)) & mask);
+            cnt += 1; sum += d; mx = max(mx, d);
+        }
+    }
+    cnt = warp_sum(cnt);
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, s));
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd((unsigned long long*)out, (unsigned long long)cnt);
+        atomicAdd((unsigned long long*)(out + 1), (unsigned long long)sum);
+        atomicMax(out + 2, mx);
+    }
+}
 __global__ void __launch_bounds__(256)
 k_q_export(const Slot* tab, u64 capacity, u64* keys, float4* rows, long long max_out, long long* count) {
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < capacity; i += (u64)gridDim.x * blockDim.x) {
@@ -1488,6 +1510,15 @@ G2048_API int g2048_qtable_size(const void* table, uint64_t capacity, int64_t* c
     k_q_size<<<grid_for((int64_t)capacity, 256, D->sm_count, 16), 256, 0, S(stream)>>>((const Slot*)table, capacity,
                                                                                         (long long*)count);
     LAUNCH_CHECK("k_q_size");
+    return 0;
+}
+G2048_API int g2048_qtable_probe_stats(const void* table, uint64_t capacity, int64_t* stats, void* stream) {
+    DEVSTATE();
+    if (!table || !pow2(capacity) || !stats) return fail(G2048_ERR_ARG, "g2048_qtable_probe_stats: bad arguments");
+    CK(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t), S(stream)));
+    k_q_probe_stats<<<grid_for((int64_t)capacity, 256, D->sm_count, 16), 256, 0, S(stream)>>>((const Slot*)table, capacity,
+                                                                                               (long long*)stats);
+    LAUNCH_CHECK("k_q_probe_stats");
     return 0;
 }
 G2048_API int g2048_qtable_export(const void* table, uint64_t capacity, uint64_t* keys, float* rows, int64_t max_out,

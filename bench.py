@@ -383,7 +383,11 @@ def main():
     peak, peak_src = measured_peak()
     achieved = n * k * ALGO_BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
-    table_stats = {"capacity_slots": cap, "table_GiB": cap * 32 / 2**30, "states": int(c[6]),
+    pst = torch.zeros(3, dtype=torch.int64, device=dev)
+    assert L.g2048_qtable_probe_stats(table, cap, pst.data_ptr(), stream) == 0, L.g2048_last_error()
+    pst = pst.tolist()
+    table_stats = {"mean_probe_length": 1 + pst[1] / max(pst[0], 1), "max_probe_length": 1 + pst[2],
+                   "inserts_per_sec": world * float(c[6]) / launches * args.steps / elapsed_s, "capacity_slots": cap, "table_GiB": cap * 32 / 2**30, "states": int(c[6]),
                    "load_factor_end": int(c[6]) / cap, "dropped": int(c[7]), "lost_updates": int(c[8]),
                    "lost_update_fraction": int(c[8]) / max(int(c[0]), 1),
                    "new_state_fraction": int(c[6]) / max(int(c[0]), 1)}

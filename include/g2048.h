@@ -290,6 +290,9 @@ G2048_API int g2048_qtable_apply_targets(void* table, uint64_t capacity, const u
                                          size_t scratch_bytes, void* stream);
 /* number of states -> *count (device int64) */
 G2048_API int g2048_qtable_size(const void* table, uint64_t capacity, int64_t* count, void* stream);
+/* stats[3] (device int64): number of states, sum of their distances (in slots) from the home slot of their hash, and
+ * the largest distance; a lookup of a stored state costs 1 + distance probes, so mean probe length = 1 + sum / n. */
+G2048_API int g2048_qtable_probe_stats(const void* table, uint64_t capacity, int64_t* stats, void* stream);
 /* compact (key, row) pairs into keys[max_out], rows[max_out][4]; *count (device int64, zeroed by the caller)
  * receives the number of states (may exceed max_out: the excess is not written) */
 G2048_API int g2048_qtable_export(const void* table, uint64_t capacity, uint64_t* keys, float* rows, int64_t max_out,

@@ -323,3 +323,27 @@ def test_deterministic_update_with_very_long_runs_matches_oracle(g):
     pairs = (k.cpu().numpy().view(np.uint64) << np.uint64(2)) | a.cpu().numpy().astype(np.uint64)
     assert np.unique(pairs, return_counts=True)[1].max() > 32
     assert per_step < 0.02, per_step          # 16 ms per step at 8 M records before the cooperative kernel
+
+
+def test_probe_stats_match_a_host_recount(g):
+    """g2048_qtable_probe_stats: states, mean and max probe length recomputed on the host from the raw slots."""
+    n = 20_000
+    env = g.BatchedGame2048Env(n, "penalty", seed=3)
+    agent = g.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 0.5, capacity=1 << 18, seed=3)   # fills to a load of ~0.7
+    env.reset()
+    agent.rollout(env, 12)
+    st = agent.probe_stats()
+    keys = agent.table.view(-1, 4)[:, 0].cpu().numpy().view(np.uint64)
+    pos = np.nonzero(keys)[0].astype(np.uint64)
+    k = keys[pos.astype(np.int64)]
+    with np.errstate(over="ignore"):
+        x = k.copy()
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    mask = np.uint64((1 << 18) - 1)
+    d = (pos - (x & mask)) & mask
+    assert st["states"] == len(k) == len(agent)
+    assert st["max_probe_length"] == 1 + int(d.max())
+    assert abs(st["mean_probe_length"] - (1 + d.astype(np.float64).mean())) < 1e-9
+    assert 0.3 < st["load_factor"] < 0.95 and st["mean_probe_length"] > 1.1
