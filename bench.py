@@ -754,6 +754,27 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
         out[f"standalone_q_update_{name}"] = {"updates_per_sec": m / dt, "achieved_GBps_at_40B": gbs,
                                               "frac_of_hbm_peak": gbs / peak, "batch": m, "table_states": pool.numel()}
     L.g2048_ctx_qtable_clear(ctx)
+    # (c2) the headline workload at the other exploration rate BASELINE config 3 quotes (epsilon 0.95), fresh table
+    be = torch.zeros(n, dtype=torch.int64, device=dev)
+    ae = torch.full((n,), 0x000000000000FF01, dtype=torch.int64, device=dev)
+    se = torch.zeros(n, dtype=torch.int32, device=dev)
+    L.g2048_env_reset(be.data_ptr(), se.data_ptr(), None, None, n, SEED, 0, base, stream)
+    ce = torch.zeros(9, dtype=torch.int64, device=dev)
+    ke, launch_no = 16, [0]
+
+    def rollout_095():
+        L.g2048_rollout_qlearn(be.data_ptr(), ae.data_ptr(), se.data_ptr(), table, cap, n, ke, 0, LR, GAMMA, 0.95, SEED,
+                               launch_no[0] * ke, base, ce.data_ptr(), stream)
+        launch_no[0] += 1
+    for _ in range(3):
+        rollout_095()
+    dt = timed(rollout_095, 12)
+    cz = ce.cpu().numpy()
+    out["fused_rollout_epsilon_0.95"] = {"env_steps_per_sec": n * ke / dt, "ms_per_launch": dt * 1e3,
+                                         "new_state_fraction": float(cz[6]) / max(float(cz[0]), 1.0),
+                                         "lost_update_fraction": float(cz[8]) / max(float(cz[0]), 1.0), "dropped": int(cz[7]),
+                                         "load_factor_end": float(cz[6]) / cap}
+    L.g2048_ctx_qtable_clear(ctx)
     # (d) BASELINE config 5, env side only: 65,536 nopenalty envs feeding a DQN -- per step: select_action on
     # (placeholder) network outputs with the legal mask, env step, one-hot encode of the new boards
     m5 = 65536
