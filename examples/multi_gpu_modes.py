@@ -7,6 +7,8 @@
   exact      synchronous steps; every replica applies every rank's (state, action, target) records, which it reads
              in place from the owner's HBM over NVLink peer memory -> replicas identical to the 1-GPU result
   shared     ONE table sharded over the GPUs' HBM; the fused rollout reads and updates remote slots over NVLink
+  owner      exact synchronous steps on that shared table: records are routed to the GPU that owns the state's slot,
+             every GPU sorts and applies only its share -> same table as "exact", 1/G of the apply work per GPU
 """
 import os
 import sys
@@ -59,6 +61,22 @@ def main():
         dist.barrier()
     print(f"[rank {rank}] shared: {shared.local_size()} states in this GPU's shard, {shared.size()} in the table")
     shared.close()
+
+    # 4. exact synchronous steps on the shared table, owner computes (needs one shard per rank: world = 2^k > 1)
+    if world > 1 and world & (world - 1) == 0:
+        env = fresh()
+        shared = gdist.SharedQTable(g2048.lib(), dev, (1 << 24) // world)
+        oc = gdist.OwnerComputesQLearning(env, shared, n_total, 0.1, 0.99, 0.1)
+        for _ in range(16):
+            oc.step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        _, rows = shared.export_local()
+        t = torch.tensor([float(rows.astype("float64").sum())], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        print(f"[rank {rank}] owner: table digest {float(t):.6f} (the same number as 'exact')")
+        oc.close()
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
 
