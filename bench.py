@@ -256,7 +256,7 @@ def run_reference(args, rank, world):
     v = total / dt
     sample = (f"C oracle port, {n} envs ({per_thread_envs}/thread) x {k} steps per bench step, {threads} threads, "
               f"fresh per-thread tables each step")
-    print(json.dumps({
+    emit_result({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 boards / f32 Q rows", "data": "synthetic",
@@ -264,11 +264,34 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: keep a private copy of it for the result and point fd 1 at
+    stderr, so that native libraries that log to stdout (NCCL prints its version there) cannot get in front of it."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_result(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
 
 
 def main():
     global EPS
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
@@ -301,7 +324,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the g2048 hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g2048.init(local_rank)
     L = g2048.lib()
@@ -478,7 +500,7 @@ def main():
             "cpu_baseline": cpu_baseline(os.cpu_count() or 1) if world == 1 else None,
             "extras": extras,
         }
-        print(json.dumps(out))
+        emit_result(out)
     L.g2048_ctx_destroy(ctx)
     if world > 1:
         dist.destroy_process_group()
