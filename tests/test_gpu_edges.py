@@ -194,3 +194,43 @@ def test_c_program_drives_the_abi(L):
         run = subprocess.run([exe], capture_output=True, text=True)
         assert run.returncode == 0, run.stdout + run.stderr
         assert "fused rollout: 1048576 steps" in run.stdout
+
+
+@pytest.mark.parametrize("flavour", [0, 1])
+def test_env_step_large_batch_path_equals_small_batch_path(flavour):
+    """From 2^19 envs on g2048_env_step runs as persistent CTAs with the LUT in shared memory; the same envs stepped in
+    chunks of 2^17 (LUT through L1) must give identical boards, aux, scores, rewards, flags and max tiles."""
+    import torch
+    import g2048
+    g2048.init(0)
+    L = g2048.lib()
+    n, chunk, seed = (1 << 19) + 1234, 1 << 17, 31
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fresh():
+        b = torch.zeros(n, dtype=torch.int64, device="cuda")
+        a = torch.full((n,), 0xFF01, dtype=torch.int64, device="cuda")
+        s = torch.zeros(n, dtype=torch.int32, device="cuda")
+        assert L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, seed, 0, 0, st) == 0
+        return b, a, s
+
+    outs = []
+    for big in (True, False):
+        b, a, s = fresh()
+        r = torch.zeros(n, dtype=torch.float64, device="cuda")
+        f = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        m = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        ms = torch.zeros(n, dtype=torch.int32, device="cuda")
+        for t in range(40):
+            act = ((torch.arange(n, device="cuda") * 7 + t * 3) % 4).to(torch.uint8)
+            spans = [(0, n)] if big else [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+            for lo, hi in spans:
+                rc = L.g2048_env_step(b[lo:].data_ptr(), a[lo:].data_ptr(), s[lo:].data_ptr(), act[lo:].data_ptr(), None,
+                                      r[lo:].data_ptr(), None, f[lo:].data_ptr(), m[lo:].data_ptr(), ms[lo:].data_ptr(),
+                                      hi - lo, flavour, seed, t, lo, st)
+                assert rc == 0, L.g2048_last_error()
+        outs.append((b, a, s, r, f, m, ms))
+    for name, x, y in zip(("boards", "aux", "score", "reward", "flags", "maxlvl", "move_score"), *outs):
+        bad = (x != y).nonzero().flatten()
+        assert bad.numel() == 0, (name, bad.numel(), bad[:5].tolist(), x[bad[:5]].tolist(), y[bad[:5]].tolist())
+    assert int(outs[0][6].sum()) > 0 and int((outs[0][4] & 1).sum()) > n // 2      # merges and valid moves happened
