@@ -185,6 +185,41 @@ def test_rollout_random_is_sharding_invariant_at_1M_envs(L, ctx):
     assert np.array_equal(cb, b1[:m]) and np.array_equal(ca, a1[:m]) and np.array_equal(cs, s1[:m])
 
 
+def test_rollout_random_8M_envs_as_one_launch_or_eight_shards(L):
+    """BASELINE config 4 size: 2^23 envs (device-pointer API).  One launch == eight launches of 2^20 envs with shifted
+    env ids (what eight GPUs run), for both flavours; a sample from the LAST shard is checked against the oracle, so the
+    high env ids go through the same Philox counter path on both sides."""
+    import torch
+    n, G, k, seed = 1 << 23, 8, 24, 0x2048
+    h = n // G
+    st = torch.cuda.current_stream().cuda_stream
+    for flavour in (0, 1):
+        def fresh():
+            b = torch.zeros(n, dtype=torch.int64, device="cuda")
+            a = torch.full((n,), oracle.AUX_INIT, dtype=torch.int64, device="cuda")
+            s = torch.zeros(n, dtype=torch.int32, device="cuda")
+            ok(L, L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, seed, 0, 0, st))
+            return b, a, s
+        b1, a1, s1 = fresh()
+        start = b1[n - h:n - h + 4096].cpu().numpy().view(np.uint64).copy()
+        c1 = torch.zeros(9, dtype=torch.int64, device="cuda")
+        ok(L, L.g2048_rollout_random(b1.data_ptr(), a1.data_ptr(), s1.data_ptr(), n, k, flavour, seed, 0, 0, c1.data_ptr(), st))
+        b2, a2, s2 = fresh()
+        c2 = torch.zeros(9, dtype=torch.int64, device="cuda")
+        for r in range(G):
+            lo = r * h
+            ok(L, L.g2048_rollout_random(b2[lo:].data_ptr(), a2[lo:].data_ptr(), s2[lo:].data_ptr(), h, k, flavour, seed, 0,
+                                         lo, c2.data_ptr(), st))
+        assert torch.equal(b1, b2) and torch.equal(a1, a2) and torch.equal(s1, s2)
+        assert torch.equal(c1, c2) and int(c1[0]) == n * k
+        cb, ca, cs = start, np.full(4096, oracle.AUX_INIT, np.uint64), np.zeros(4096, np.int32)
+        oracle.rollout_random(cb, ca, cs, k, flavour, seed, 0, n - h, threads=4)
+        assert np.array_equal(cb, b1[n - h:n - h + 4096].cpu().numpy().view(np.uint64))
+        assert np.array_equal(cs, s1[n - h:n - h + 4096].cpu().numpy())
+        if flavour == 0:
+            assert np.array_equal(ca, a1[n - h:n - h + 4096].cpu().numpy().view(np.uint64))
+
+
 # ------------------------------------------------------------------------------------------ Q-table
 def export_ctx_table(L, ctx):
     n = L.g2048_ctx_qtable_size(ctx)
