@@ -1706,13 +1706,21 @@ static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* s
     CK(cudaMemsetAsync(c->counters, 0, G2048_N_COUNTERS * sizeof(long long), st));
     // Large batches go through in chunks on three streams, so that the host<->device copies of one chunk overlap
     // the kernel of another (PCIe is full duplex: H2D, D2H and compute all run at once).  Env ids are global, so
-    // the result does not depend on the chunking.
-    const int chunks = n >= (1 << 18) ? 4 : 1;
+    // the result does not depend on the chunking.  The rollout kernels run one env per thread and round with
+    // T = SMs x 1024 threads resident, so every chunk but the last is a multiple of T (no chunk adds a partly
+    // filled round); the first and the last chunk are the small ones, because their copies are the exposed ones.
+    DeviceState* D = nullptr;
+    RC(current_device_state(&D));
+    const int64_t T = (int64_t)D->sm_count * kRolloutThreads;
+    const int64_t unit = T * (n / (6 * T) > 1 ? n / (6 * T) : 1);
+    const bool pipelined = n >= (1 << 18) && n > unit;
     CK(cudaEventRecord(c->ev_start, st));
-    for (int j = 0; j < chunks; ++j) {
-        cudaStream_t ps = chunks == 1 ? st : c->pipe[j % 3];
-        int64_t lo = n * j / chunks, m = n * (j + 1) / chunks - lo;
-        if (chunks > 1) CK(cudaStreamWaitEvent(ps, c->ev_start, 0));
+    int64_t lo = 0;
+    for (int j = 0; lo < n; ++j) {
+        int64_t rem = n - lo, m = rem;
+        if (pipelined) m = j == 0 ? unit : rem >= 3 * unit ? 2 * unit : rem > unit ? unit : rem;
+        cudaStream_t ps = pipelined ? c->pipe[j % 3] : st;
+        if (pipelined) CK(cudaStreamWaitEvent(ps, c->ev_start, 0));
         CK(cudaMemcpyAsync(c->boards + lo, boards + lo, (size_t)m * 8, cudaMemcpyHostToDevice, ps));
         if (aux) CK(cudaMemcpyAsync(c->aux + lo, aux + lo, (size_t)m * 8, cudaMemcpyHostToDevice, ps));
         if (score) CK(cudaMemcpyAsync(c->score + lo, score + lo, (size_t)m * 4, cudaMemcpyHostToDevice, ps));
@@ -1728,8 +1736,9 @@ static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* s
         CK(cudaMemcpyAsync(boards + lo, c->boards + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, ps));
         if (aux) CK(cudaMemcpyAsync(aux + lo, c->aux + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, ps));
         if (score) CK(cudaMemcpyAsync(score + lo, c->score + lo, (size_t)m * 4, cudaMemcpyDeviceToHost, ps));
+        lo += m;
     }
-    if (chunks > 1)
+    if (pipelined)
         for (int j = 0; j < 3; ++j) {
             CK(cudaEventRecord(c->ev_done[j], c->pipe[j]));
             CK(cudaStreamWaitEvent(st, c->ev_done[j], 0));
