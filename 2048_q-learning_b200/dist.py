@@ -138,7 +138,7 @@ class ShardedQLearning:
             agent = engine.agent
             self.peers = PeerRecordBuffers(agent.lib, agent.device, self.pad, group)
         elif transport == "nccl":
-            dev = engine.agent.device
+            dev = getattr(engine, "device", None) or engine.agent.device
             self._mine = torch.zeros((self.pad, 2), dtype=torch.int64, device=dev)
             self._all = torch.zeros((self.world, self.pad, 2), dtype=torch.int64, device=dev)
         elif transport != "auto":
@@ -162,7 +162,7 @@ class ShardedQLearning:
         elif self.transport == "nccl":
             self.engine.emit_records(self._mine)
             if self.world > 1:
-                dist.all_gather_into_tensor(self._all, self._mine, group=self.group)
+                dist.all_gather_into_tensor(self._all.view(-1), self._mine.view(-1), group=self.group)
                 self.engine.apply_records([self._all[r] for r in range(self.world)], self.sizes)
             else:
                 self.engine.apply_records([self._mine], self.sizes)

@@ -36,15 +36,30 @@ class OracleEngine:
     def apply(self, keys, actions, deltas):
         self.tab.apply_targets_f32(keys.numpy().view(np.uint64).copy(), actions.numpy().copy(), deltas.numpy().copy(), 0.1)
 
+    # the packed 16-byte record protocol of the GPU engine (g2048_record: key | action + float32 target bits << 32)
+    device = torch.device("cpu")
 
-def _worker(rank, world, port, out):
+    def emit_records(self, records):
+        k, a, d = self.emit()
+        n = k.numel()
+        at = a.numpy().astype(np.uint64) | (d.numpy().view(np.uint32).astype(np.uint64) << np.uint64(32))
+        records[:n, 0] = k
+        records[:n, 1] = torch.from_numpy(at.view(np.int64))
+
+    def apply_records(self, lists, counts):
+        rec = np.concatenate([l[:c].numpy().view(np.uint64) for l, c in zip(lists, counts)])
+        self.tab.apply_targets_f32(rec[:, 0].copy(), (rec[:, 1] & np.uint64(3)).astype(np.uint8),
+                                   (rec[:, 1] >> np.uint64(32)).astype(np.uint32).view(np.float32).copy(), 0.1)
+
+
+def _worker(rank, world, port, out, transport="auto"):
     sys.path.insert(0, ROOT)
     import g2048
     from g2048 import dist as gdist
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     lo, hi = gdist.shard_range(N_TOTAL, rank, world)
     eng = OracleEngine(lo, hi)
-    sh = gdist.ShardedQLearning(eng, N_TOTAL)
+    sh = gdist.ShardedQLearning(eng, N_TOTAL, transport=transport)
     for _ in range(STEPS):
         sh.step()
     keys, rows = eng.tab.export()
@@ -62,11 +77,12 @@ def test_shard_range_partitions_exactly():
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_exchange_equals_single_process(tmp_path):
+@pytest.mark.parametrize("transport", ["auto", "nccl"])     # "nccl" = one gather of packed records (gloo here)
+def test_two_rank_exchange_equals_single_process(tmp_path, transport):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), transport), nprocs=2, join=True)
     sys.path.insert(0, ROOT)
     single = OracleEngine(0, N_TOTAL)
     for t in range(STEPS):
