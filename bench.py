@@ -304,6 +304,8 @@ def main():
                     help="also time BASELINE config 5: 65,536 nopenalty envs/GPU with the 197 M-parameter DQN forward in the loop")
     ap.add_argument("--exchange", action="store_true",
                     help="also time the synchronous mode with the cross-GPU record exchange (dist.ShardedQLearning)")
+    ap.add_argument("--exchange-envs", type=int, default=0,
+                    help="envs per GPU for --exchange (default min(--envs, 2^20)); BASELINE config 4 = 2^23 envs in total")
     ap.add_argument("--shared-table", action="store_true",
                     help="also time the fused rollout on ONE Q-table sharded over the GPUs' HBM (NVLink peer loads/atomics)")
     args = ap.parse_args()
@@ -441,7 +443,8 @@ def main():
 
     extras = {}
     if args.exchange:
-        sync = sync_exchange_measurement(torch, dist, g2048, dev, rank, world, min(n, 1 << 20), max_over_ranks, barrier)
+        sync = sync_exchange_measurement(torch, dist, g2048, dev, rank, world, args.exchange_envs or min(n, 1 << 20),
+                                         max_over_ranks, barrier)
         if rank == 0:
             extras["synchronous_exchange"] = sync
     if args.shared_table:
@@ -587,7 +590,7 @@ def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_
     transports = ["nccl"] + (["peer"] if world > 1 else [])
     for transport in transports:
         env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
-        agent = g2048.BatchedQLearningAgent(1000, 4, LR, GAMMA, EPS, capacity=1 << 28, device=dev.index, seed=SEED)
+        agent = g2048.BatchedQLearningAgent(1000, 4, LR, GAMMA, EPS, capacity=1 << 29, device=dev.index, seed=SEED)
         env.reset()
         sh = gdist.ShardedQLearning(gdist.TorchEngine(env, agent), n * world, transport=transport)
         for _ in range(3):
@@ -619,7 +622,7 @@ def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_
         # owner computes: ONE table sharded over the GPUs, every GPU sorts/applies only the records for its shard
         env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
         env.reset()
-        shared = gdist.SharedQTable(g2048.lib(), dev, (1 << 28) // world)
+        shared = gdist.SharedQTable(g2048.lib(), dev, (1 << 29) // world)
         oc = gdist.OwnerComputesQLearning(env, shared, n * world, LR, GAMMA, EPS)
         for _ in range(3):
             oc.step()
