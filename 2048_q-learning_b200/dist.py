@@ -315,7 +315,11 @@ class OwnerComputesQLearning:
 
     HEAD = 512                                   # flags (256 B) + 2 x 16 counters
 
-    def __init__(self, env, shared: SharedQTable, n_total: int, lr: float, gamma: float, eps: float, group=None):
+    def __init__(self, env, shared: SharedQTable, n_total: int, lr: float, gamma: float, eps: float, group=None,
+                 window: int = 1):
+        """window = K > 1: the table's values stay frozen for K env steps (new states are still inserted, as zero
+        rows), the records of all K steps are then exchanged and applied at once in (step, global env) order -- the
+        "exchange every K steps" form: one barrier pair, one sort and one host read per K steps."""
         import ctypes
         from ._lib import check
         self._check, self._ct = check, ctypes
@@ -325,11 +329,11 @@ class OwnerComputesQLearning:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if shared.n_shards != self.world:
             raise ValueError("one shard per rank")
-        self.n_total = int(n_total)
-        self.idx_bits = max(1, (self.n_total - 1).bit_length())
+        self.n_total, self.window = int(n_total), int(window)
+        self.idx_bits = max(1, (self.n_total * self.window - 1).bit_length())
         self.lo, _ = shard_range(self.n_total, self.rank, self.world)
         self.cap = max(hi - lo for lo, hi in (shard_range(self.n_total, r, self.world) for r in range(self.world)))
-        self.list_bytes = ((self.cap * 16 + 255) // 256) * 256
+        self.list_bytes = ((self.cap * self.window * 16 + 255) // 256) * 256
         nbytes = self.HEAD + 2 * self.world * self.list_bytes
         mine, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
         with torch.cuda.device(self.device):
@@ -349,7 +353,7 @@ class OwnerComputesQLearning:
             self._flags = (ctypes.c_void_p * self.world)(*self.base)
             self.timed_out = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._scratch = None
-        self.epoch, self.t = 0, 0
+        self.epoch, self.t, self.k = 0, 0, 0      # barrier epoch, window number, step inside the window
         dist.barrier(group=group)
 
     # layout helpers: counts[slot][j] and list[slot][j] inside rank r's buffer
@@ -366,31 +370,44 @@ class OwnerComputesQLearning:
                     "g2048_peer_barrier")
 
     def step(self):
+        """One env step of every env of this rank; returns the number of records this rank applied to its shard (0
+        inside a window)."""
         ct, env, sh, slot = self._ct, self.env, self.shared, self.t & 1
         st = torch.cuda.current_stream().cuda_stream
+        total = 0
         with torch.cuda.device(self.device):
-            self._check(self.lib.g2048_peer_memset(self._counts(self.rank, slot), 0, 128, st), "g2048_peer_memset")
+            if self.k == 0:
+                self._check(self.lib.g2048_peer_memset(self._counts(self.rank, slot), 0, 128, st), "g2048_peer_memset")
             lists = (ct.c_void_p * self.world)(*[self._list(self.rank, slot, j) for j in range(self.world)])
             self._check(self.lib.g2048_qlearn_emit_owned(
                 env.boards.data_ptr(), env.aux.data_ptr(), env.score.data_ptr(), sh._arr, sh.n_shards, sh.slots_per_shard,
-                env.n, env.flavour, self.gamma, float(self.eps), env.seed, env.step_idx, env.env_id_base, self.lo,
-                self.idx_bits, env.counters.data_ptr(), lists, self._counts(self.rank, slot), st), "g2048_qlearn_emit_owned")
+                env.n, env.flavour, self.gamma, float(self.eps), env.seed, env.step_idx, env.env_id_base,
+                self.k * self.n_total + self.lo, self.idx_bits, env.counters.data_ptr(), lists,
+                self._counts(self.rank, slot), st), "g2048_qlearn_emit_owned")
             env.step_idx += 1
-            self._barrier()                                     # every rank's records and counts are written
-            src = (ct.c_void_p * self.world)(*[self._counts(r, slot) + 8 * self.rank for r in range(self.world)])
-            host = (ct.c_uint64 * self.world)()
-            self._check(self.lib.g2048_peer_read_u64(src, self.world, host, st), "g2048_peer_read_u64")
-            counts = (ct.c_int64 * self.world)(*[int(x) for x in host])
-            total = sum(int(x) for x in host)
-            need = int(self.lib.g2048_qlearn_scratch_bytes(max(total, 1)))
-            if self._scratch is None or self._scratch.numel() < need:
-                self._scratch = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
-            mine = (ct.c_void_p * self.world)(*[self._list(r, slot, self.rank) for r in range(self.world)])
-            self._check(self.lib.g2048_qtable_apply_owned(sh.ptrs[self.rank], sh.slots_per_shard, mine, counts, self.world,
-                                                          self.idx_bits, self.lr, self._scratch.data_ptr(),
-                                                          self._scratch.numel(), st), "g2048_qtable_apply_owned")
-            self._barrier()                                     # all shards updated before anyone reads them again
-        self.t += 1
+            self.k += 1
+            if self.k == self.window:
+                total = self._exchange_and_apply(slot, st)
+                self.k = 0
+                self.t += 1
+        return total
+
+    def _exchange_and_apply(self, slot, st):
+        ct, sh = self._ct, self.shared
+        self._barrier()                                     # every rank's records and counts are written
+        src = (ct.c_void_p * self.world)(*[self._counts(r, slot) + 8 * self.rank for r in range(self.world)])
+        host = (ct.c_uint64 * self.world)()
+        self._check(self.lib.g2048_peer_read_u64(src, self.world, host, st), "g2048_peer_read_u64")
+        counts = (ct.c_int64 * self.world)(*[int(x) for x in host])
+        total = sum(int(x) for x in host)
+        need = int(self.lib.g2048_qlearn_scratch_bytes(max(total, 1)))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
+        mine = (ct.c_void_p * self.world)(*[self._list(r, slot, self.rank) for r in range(self.world)])
+        self._check(self.lib.g2048_qtable_apply_owned(sh.ptrs[self.rank], sh.slots_per_shard, mine, counts, self.world,
+                                                      self.idx_bits, self.lr, self._scratch.data_ptr(),
+                                                      self._scratch.numel(), st), "g2048_qtable_apply_owned")
+        self._barrier()                                     # all shards updated before anyone reads them again
         return total
 
     def close(self):

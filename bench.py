@@ -645,6 +645,26 @@ def sync_exchange_measurement(torch, dist, g2048, dev, rank, world, n, max_over_
         out["owner_computes"] = {"env_steps_per_sec": world * n * steps / dt, "ms_per_step": dt / steps * 1e3,
                                  "table_digest_sum_and_count_of_nonzero_rows": t.tolist(),
                                  "note": "one sharded table; digest = sum over all shards, to compare with one replica's"}
+        # the same with the exchange every 16 steps (values frozen inside a window)
+        env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
+        env.reset()
+        shared = gdist.SharedQTable(g2048.lib(), dev, (1 << 29) // world)
+        oc = gdist.OwnerComputesQLearning(env, shared, n * world, LR, GAMMA, EPS, window=16)
+        for _ in range(16):
+            oc.step()
+        barrier()
+        e0.record()
+        for _ in range(32):
+            oc.step()
+        e1.record()
+        barrier()
+        dt = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+        oc.close()
+        shared.close()
+        del env
+        torch.cuda.empty_cache()
+        out["owner_computes_window_16"] = {"env_steps_per_sec": world * n * 32 / dt, "ms_per_step": dt / 32 * 1e3,
+                                           "note": "exchange + apply once per 16 env steps"}
     if "peer" in out:
         out["transports_agree"] = (out["peer"]["replica_digests_sum_and_count_of_nonzero_rows"] ==
                                    out["nccl"]["replica_digests_sum_and_count_of_nonzero_rows"])

@@ -315,7 +315,22 @@ def test_owner_computes_step_equals_the_single_table_deterministic_step():
                                      SEED, 0, 0, 1 << 20, 8, None, arr, counts[0].data_ptr(), st) == -1
 
 
-def _owner_worker(rank, world, port, out):
+def windowed_single_process_result(g, n, steps, window):
+    """Reference for the K-step window: K steps on frozen values (records only), then all records applied in
+    (step, env) order -- on ONE table in one process."""
+    import torch
+    env = g.BatchedGame2048Env(n, "penalty", seed=SEED)
+    agent = g.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 0.4, capacity=CAP, seed=SEED)
+    env.reset()
+    for _ in range(steps // window):
+        recs = [agent.step_sync(env, mode="deterministic", apply=False, records=True) for _ in range(window)]
+        agent.apply_targets(torch.cat([r[0] for r in recs]), torch.cat([r[1] for r in recs]), torch.cat([r[2] for r in recs]))
+    keys, rows = agent.export()
+    nz = np.abs(rows).sum(1) > 0
+    return np_boards(env.boards).copy(), keys[nz], rows[nz]
+
+
+def _owner_worker(rank, world, port, out, window=1):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -327,8 +342,9 @@ def _owner_worker(rank, world, port, out):
     env = g2048.BatchedGame2048Env(hi - lo, "penalty", seed=SEED, env_id_base=lo)
     env.reset()
     shared = gdist.SharedQTable(g2048.lib(), torch.device("cuda", 0), CAP // world)
-    oc = gdist.OwnerComputesQLearning(env, shared, N_TOTAL, 0.1, 0.99, 0.4)
-    handled = [oc.step() for _ in range(STEPS)]
+    oc = gdist.OwnerComputesQLearning(env, shared, N_TOTAL, 0.1, 0.99, 0.4, window=window)
+    steps = STEPS if window == 1 else 12
+    handled = [oc.step() for _ in range(steps)]
     torch.cuda.synchronize()
     dist.barrier()
     keys, rows = shared.export_local()
@@ -353,6 +369,28 @@ def test_two_processes_owner_computes_through_ipc_peer_memory(tmp_path):
     for x in d:
         assert np.array_equal(x["boards"], boards1[int(x["lo"]):int(x["hi"])])
     assert np.array_equal(d[0]["handled"] + d[1]["handled"], np.full(STEPS, N_TOTAL))
+    keys = np.concatenate([d[0]["keys"], d[1]["keys"]])
+    rows = np.concatenate([d[0]["rows"], d[1]["rows"]])
+    order = np.argsort(keys)
+    assert np.array_equal(keys[order], keys1) and np.array_equal(rows[order], rows1)
+
+
+@pytest.mark.timeout(600)
+def test_two_processes_owner_computes_with_a_4_step_window(tmp_path):
+    """Exchange every K = 4 steps: values frozen inside the window, all 4 x N records applied at once in (step, env)
+    order by their owners -- equal to the single-table, single-process run of the same rule."""
+    import torch.multiprocessing as mp
+    import g2048
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_owner_worker, args=(2, port, str(tmp_path), 4), nprocs=2, join=True)
+    boards1, keys1, rows1 = windowed_single_process_result(g2048, N_TOTAL, 12, 4)
+    d = [np.load(tmp_path / f"owner{r}.npz") for r in range(2)]
+    for x in d:
+        assert np.array_equal(x["boards"], boards1[int(x["lo"]):int(x["hi"])])
+    handled = d[0]["handled"] + d[1]["handled"]
+    assert handled.tolist() == [0, 0, 0, 4 * N_TOTAL] * 3
     keys = np.concatenate([d[0]["keys"], d[1]["keys"]])
     rows = np.concatenate([d[0]["rows"], d[1]["rows"]])
     order = np.argsort(keys)
