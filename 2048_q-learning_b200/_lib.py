@@ -75,7 +75,8 @@ _SIG = {
     "g2048_qtable_lookup_sharded": (i32, [vp, i32, u64, vp, i64, vp, vp, i32, vp]),
     "g2048_qlearn_emit": (i32, [vp, vp, vp, vp, u64, i64, i32, f32, f64, u64, u64, u64, vp, vp, vp]),
     "g2048_qtable_apply_records": (i32, [vp, u64, vp, vp, i32, f32, i32, vp, sz, vp]),
-    "g2048_qlearn_emit_owned": (i32, [vp, vp, vp, vp, i32, u64, i64, i32, f32, f64, u64, u64, u64, u64, i32, vp, vp, vp, vp]),
+    "g2048_qlearn_emit_owned": (i32, [vp, vp, vp, vp, i32, u64, i64, i32, f32, f64, u64, u64, u64, u64, i32, vp, vp, vp, vp,
+                                      vp, i32, vp]),
     "g2048_qtable_apply_owned": (i32, [vp, u64, vp, vp, i32, i32, f32, vp, sz, vp]),
     "g2048_peer_read_u64": (i32, [vp, i32, vp, vp]),
     "g2048_peer_memset": (i32, [vp, i32, sz, vp]),

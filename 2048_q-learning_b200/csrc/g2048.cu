@@ -459,7 +459,7 @@ template <int FLAVOUR>
 __global__ void __launch_bounds__(256)
 k_qlearn_emit_owned(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ ShardedTable table, long long n,
                     float gamma, u64 eps_thresh, u64 seed, u64 t, u64 id_base, u64 rec_base, long long* counters,
-                    const __grid_constant__ OwnedLists out) {
+                    const __grid_constant__ OwnedLists out, u32* carry_slot, float4* carry_row, int use_carry) {
     __shared__ Slot* shard_base[G2048_MAX_PEERS];
     __shared__ ulonglong2* list_base[G2048_MAX_PEERS];
     if (threadIdx.x < G2048_MAX_PEERS) list_base[threadIdx.x] = out.list[threadIdx.x];
@@ -478,21 +478,39 @@ k_qlearn_emit_owned(Tables T, u64* boards, u64* aux, int* score, const __grid_co
             env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
             u64 id = id_base + (u64)i;
             float4 row, row2;
-            u32 slot = table_find<true>(tab, e.board, row, c.inserts);
-            c.dropped += (slot == kNoSlot);
+            u32 slot;
+            if (use_carry) {   // inside a window the values are frozen: (slot, row) of s are those found for s' one step ago
+                slot = carry_slot[i];
+                row = carry_row[i];
+            } else {
+                slot = table_find<true>(tab, e.board, row, c.inserts);
+                c.dropped += (slot == kNoSlot);
+            }
             Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
             int a = choose_action(row, x, eps_thresh);
+            const u64 s_board = e.board;
             StepOut o;
             philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
             c.add(o);
-            u32 slot2 = table_find<true>(tab, e.board, row2, c.inserts);
-            c.dropped += (slot2 == kNoSlot);
+            u32 slot2 = slot;
+            row2 = row;
+            if (e.board != s_board) {   // an invalid move leaves s' == s: nothing to look up
+                slot2 = table_find<true>(tab, e.board, row2, c.inserts);
+                c.dropped += (slot2 == kNoSlot);
+            }
             target = td_target(gamma, (float)o.reward, max4(row2), o.done);
             if (slot != kNoSlot) {
                 owner = (int)((u64)slot >> tab.shift);
                 key = (((((u64)slot & tab.low) << 2) | (u64)a) << out.idx_bits) | (rec_base + (u64)i);
             }
-            if (o.done) philox_autoreset(e, seed, id, t);
+            if (o.done) {
+                philox_autoreset(e, seed, id, t);
+                if (carry_slot) {   // the next step continues from the fresh board: find it now
+                    slot2 = table_find<true>(tab, e.board, row2, c.inserts);
+                    c.dropped += (slot2 == kNoSlot);
+                }
+            }
+            if (carry_slot) { carry_slot[i] = slot2; carry_row[i] = row2; }
             boards[i] = e.board;
             if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
             if (score) score[i] = e.score;
@@ -1339,10 +1357,11 @@ G2048_API int g2048_qlearn_emit_owned(uint64_t* boards, uint64_t* aux, int32_t* 
                                       int n_shards, uint64_t slots_per_shard, int64_t n, int flavour, float gamma,
                                       double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base,
                                       uint64_t record_index_base, int idx_bits, int64_t* counters,
-                                      g2048_record* const* owner_lists, uint64_t* owner_counts, void* stream) {
+                                      g2048_record* const* owner_lists, uint64_t* owner_counts, uint32_t* carry_slot,
+                                      float* carry_row, int use_carry, void* stream) {
     DEVSTATE();
     if (n < 0 || (n && !boards) || (flavour != 0 && flavour != 1) || !owner_lists || !owner_counts || idx_bits < 1 ||
-        idx_bits > 40)
+        idx_bits > 40 || (!carry_slot != !carry_row) || (use_carry && !carry_slot) || ((uintptr_t)carry_row & 15))
         return fail(G2048_ERR_ARG, "g2048_qlearn_emit_owned: bad arguments");
     ShardedTable t;
     int rc = make_sharded(shards, n_shards, slots_per_shard, t, "g2048_qlearn_emit_owned: bad shard list");
@@ -1361,7 +1380,7 @@ G2048_API int g2048_qlearn_emit_owned(uint64_t* boards, uint64_t* aux, int32_t* 
 #define EMIT(F)                                                                                                       \
     k_qlearn_emit_owned<F><<<g, 256, 0, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, t, n, gamma,           \
                                                      eps_threshold(eps), seed, step_idx, env_id_base, record_index_base, \
-                                                     (long long*)counters, out)
+                                                     (long long*)counters, out, carry_slot, (float4*)carry_row, use_carry)
     if (flavour == 0) EMIT(0); else EMIT(1);
 #undef EMIT
     LAUNCH_CHECK("k_qlearn_emit_owned");

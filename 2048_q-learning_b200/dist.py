@@ -353,6 +353,8 @@ class OwnerComputesQLearning:
             self._flags = (ctypes.c_void_p * self.world)(*self.base)
             self.timed_out = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._scratch = None
+            self._carry_slot = torch.zeros(env.n, dtype=torch.int32, device=self.device) if self.window > 1 else None
+            self._carry_row = torch.zeros((env.n, 4), dtype=torch.float32, device=self.device) if self.window > 1 else None
         self.epoch, self.t, self.k = 0, 0, 0      # barrier epoch, window number, step inside the window
         dist.barrier(group=group)
 
@@ -383,7 +385,9 @@ class OwnerComputesQLearning:
                 env.boards.data_ptr(), env.aux.data_ptr(), env.score.data_ptr(), sh._arr, sh.n_shards, sh.slots_per_shard,
                 env.n, env.flavour, self.gamma, float(self.eps), env.seed, env.step_idx, env.env_id_base,
                 self.k * self.n_total + self.lo, self.idx_bits, env.counters.data_ptr(), lists,
-                self._counts(self.rank, slot), st), "g2048_qlearn_emit_owned")
+                self._counts(self.rank, slot), None if self._carry_slot is None else self._carry_slot.data_ptr(),
+                None if self._carry_row is None else self._carry_row.data_ptr(), int(self.k > 0), st),
+                "g2048_qlearn_emit_owned")
             env.step_idx += 1
             self.k += 1
             if self.k == self.window:

@@ -241,12 +241,18 @@ G2048_API int g2048_qtable_apply_records(void* table, uint64_t capacity, const g
  * local or peer memory; counts[] on the HOST, e.g. from g2048_peer_read_u64) and applies them to ITS shard, record
  * after record in global env order: q <- q + lr (target - q) (main.py:43).  The result equals the single-GPU
  * deterministic step bit for bit, and every GPU sorts only its share of the records.  A second barrier must separate
- * the apply from the next emit (which reads remote shards). */
+ * the apply from the next emit (which reads remote shards).
+ * Exchange every K steps: call emit K times (record_index_base = k * total envs + first env of the rank, idx_bits for
+ * K * total envs, counts zeroed once) before the barrier and the apply; the table's values are then frozen for the K
+ * steps.  carry_slot[n] / carry_row[n][4] (device, both or neither) receive the slot and row of the state every env
+ * continues from; with use_carry = 1 (steps 2..K of a window) the kernel takes them from there instead of looking the
+ * state up again -- one remote request less per env step. */
 G2048_API int g2048_qlearn_emit_owned(uint64_t* boards, uint64_t* aux, int32_t* score, const void* const* shards,
                                       int n_shards, uint64_t slots_per_shard, int64_t n, int flavour, float gamma,
                                       double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base,
                                       uint64_t record_index_base, int idx_bits, int64_t* counters,
-                                      g2048_record* const* owner_lists, uint64_t* owner_counts, void* stream);
+                                      g2048_record* const* owner_lists, uint64_t* owner_counts, uint32_t* carry_slot,
+                                      float* carry_row, int use_carry, void* stream);
 G2048_API int g2048_qtable_apply_owned(void* shard, uint64_t slots_per_shard, const g2048_record* const* lists,
                                        const int64_t* counts, int n_lists, int idx_bits, float lr, void* scratch,
                                        size_t scratch_bytes, void* stream);

@@ -290,7 +290,7 @@ def test_owner_computes_step_equals_the_single_table_deterministic_step():
             arr = (ctypes.c_void_p * G)(*[x.data_ptr() for x in lists[r]])
             rc = L.g2048_qlearn_emit_owned(envs[r].boards.data_ptr(), envs[r].aux.data_ptr(), envs[r].score.data_ptr(),
                                            shared._arr, G, slots, sizes[r], 0, 0.99, 0.4, SEED, t, lo[r], lo[r], idx_bits,
-                                           envs[r].counters.data_ptr(), arr, counts[r].data_ptr(), st)
+                                           envs[r].counters.data_ptr(), arr, counts[r].data_ptr(), None, None, 0, st)
             assert rc == 0, L.g2048_last_error()
         host = torch.stack(counts).cpu().numpy()                 # [rank][owner]
         assert host.sum() == n
@@ -312,7 +312,7 @@ def test_owner_computes_step_equals_the_single_table_deterministic_step():
     # misuse: record index that does not fit idx_bits
     arr = (ctypes.c_void_p * G)(*[x.data_ptr() for x in lists[0]])
     assert L.g2048_qlearn_emit_owned(envs[0].boards.data_ptr(), None, None, shared._arr, G, slots, sizes[0], 0, 0.99, 0.4,
-                                     SEED, 0, 0, 1 << 20, 8, None, arr, counts[0].data_ptr(), st) == -1
+                                     SEED, 0, 0, 1 << 20, 8, None, arr, counts[0].data_ptr(), None, None, 0, st) == -1
 
 
 def windowed_single_process_result(g, n, steps, window):
