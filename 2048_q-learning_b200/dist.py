@@ -396,6 +396,16 @@ class OwnerComputesQLearning:
                 self.t += 1
         return total
 
+    def flush(self):
+        """Apply the records of a partly filled window now (every rank must call it at the same step)."""
+        total = 0
+        if self.k:
+            with torch.cuda.device(self.device):
+                total = self._exchange_and_apply(self.t & 1, torch.cuda.current_stream().cuda_stream)
+            self.k = 0
+            self.t += 1
+        return total
+
     def _exchange_and_apply(self, slot, st):
         ct, sh = self._ct, self.shared
         self._barrier()                                     # every rank's records and counts are written
@@ -415,6 +425,7 @@ class OwnerComputesQLearning:
         return total
 
     def close(self):
+        self.flush()
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
             v = int(self.timed_out.item())
