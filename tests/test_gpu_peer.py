@@ -322,8 +322,8 @@ def windowed_single_process_result(g, n, steps, window):
     env = g.BatchedGame2048Env(n, "penalty", seed=SEED)
     agent = g.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 0.4, capacity=CAP, seed=SEED)
     env.reset()
-    for _ in range(steps // window):
-        recs = [agent.step_sync(env, mode="deterministic", apply=False, records=True) for _ in range(window)]
+    for w in range(0, steps, window):
+        recs = [agent.step_sync(env, mode="deterministic", apply=False, records=True) for _ in range(min(window, steps - w))]
         agent.apply_targets(torch.cat([r[0] for r in recs]), torch.cat([r[1] for r in recs]), torch.cat([r[2] for r in recs]))
     keys, rows = agent.export()
     nz = np.abs(rows).sum(1) > 0
@@ -343,8 +343,9 @@ def _owner_worker(rank, world, port, out, window=1):
     env.reset()
     shared = gdist.SharedQTable(g2048.lib(), torch.device("cuda", 0), CAP // world)
     oc = gdist.OwnerComputesQLearning(env, shared, N_TOTAL, 0.1, 0.99, 0.4, window=window)
-    steps = STEPS if window == 1 else 12
+    steps = STEPS if window == 1 else 14
     handled = [oc.step() for _ in range(steps)]
+    handled.append(oc.flush())                       # the partly filled last window (a no-op for window = 1)
     torch.cuda.synchronize()
     dist.barrier()
     keys, rows = shared.export_local()
@@ -368,7 +369,7 @@ def test_two_processes_owner_computes_through_ipc_peer_memory(tmp_path):
     d = [np.load(tmp_path / f"owner{r}.npz") for r in range(2)]
     for x in d:
         assert np.array_equal(x["boards"], boards1[int(x["lo"]):int(x["hi"])])
-    assert np.array_equal(d[0]["handled"] + d[1]["handled"], np.full(STEPS, N_TOTAL))
+    assert np.array_equal(d[0]["handled"] + d[1]["handled"], np.array([N_TOTAL] * STEPS + [0]))
     keys = np.concatenate([d[0]["keys"], d[1]["keys"]])
     rows = np.concatenate([d[0]["rows"], d[1]["rows"]])
     order = np.argsort(keys)
@@ -385,12 +386,12 @@ def test_two_processes_owner_computes_with_a_4_step_window(tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_owner_worker, args=(2, port, str(tmp_path), 4), nprocs=2, join=True)
-    boards1, keys1, rows1 = windowed_single_process_result(g2048, N_TOTAL, 12, 4)
+    boards1, keys1, rows1 = windowed_single_process_result(g2048, N_TOTAL, 14, 4)
     d = [np.load(tmp_path / f"owner{r}.npz") for r in range(2)]
     for x in d:
         assert np.array_equal(x["boards"], boards1[int(x["lo"]):int(x["hi"])])
     handled = d[0]["handled"] + d[1]["handled"]
-    assert handled.tolist() == [0, 0, 0, 4 * N_TOTAL] * 3
+    assert handled.tolist() == [0, 0, 0, 4 * N_TOTAL] * 3 + [0, 0, 2 * N_TOTAL]
     keys = np.concatenate([d[0]["keys"], d[1]["keys"]])
     rows = np.concatenate([d[0]["rows"], d[1]["rows"]])
     order = np.argsort(keys)
