@@ -234,7 +234,7 @@ G2048_API int g2048_qtable_apply_records(void* table, uint64_t capacity, const g
 /* The exact synchronous step on ONE table sharded over the GPUs (see g2048_rollout_qlearn_sharded for the shard
  * list), owner computes: g2048_qlearn_emit_owned advances the envs like g2048_qlearn_emit, looking s and s' up
  * wherever their slots live, and appends the record of each transition to owner_lists[j] (HOST array of n_shards
- * device pointers, room for n records each) of the GPU j that owns the slot of s; owner_counts[j] (device, zeroed by
+ * device pointers, room for n records each -- K * n when K steps are exchanged at once) of the GPU j that owns the slot of s; owner_counts[j] (device, zeroed by
  * the caller) counts them.  A record holds ((owner-local slot * 4 + action) << idx_bits) | (record_index_base + i)
  * and the float32 target; idx_bits >= log2(total envs of the job), record_index_base = first global env index of
  * this rank.  After a barrier, g2048_qtable_apply_owned on GPU j sorts the lists every rank wrote for j (read in place,
