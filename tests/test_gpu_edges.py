@@ -234,3 +234,66 @@ def test_env_step_large_batch_path_equals_small_batch_path(flavour):
         bad = (x != y).nonzero().flatten()
         assert bad.numel() == 0, (name, bad.numel(), bad[:5].tolist(), x[bad[:5]].tolist(), y[bad[:5]].tolist())
     assert int(outs[0][6].sum()) > 0 and int((outs[0][4] & 1).sum()) > n // 2      # merges and valid moves happened
+
+
+def test_move_properties_at_1M_boards_on_the_gpu():
+    """BASELINE size, size-independent properties checked on the GPU's own outputs (no oracle in the loop): tile-sum
+    conservation, score > 0 iff a tile disappeared, the four directions as mirror images / transposes of one another,
+    legal mask == the four trial moves, all on 2^20 random boards of every density."""
+    import torch
+    import g2048
+    g2048.init(0)
+    L = g2048.lib()
+    n = 1 << 20
+    st = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    lv = torch.randint(1, 12, (n, 16), device="cuda", generator=gen)
+    p_zero = torch.rand((n, 1), device="cuda", generator=gen)
+    lv = torch.where(torch.rand((n, 16), device="cuda", generator=gen) < p_zero, torch.zeros_like(lv), lv)
+    lv[:, 0] = torch.where(lv.sum(1) == 0, torch.ones_like(lv[:, 0]), lv[:, 0])
+
+    def pack(levels):
+        b = torch.zeros(levels.shape[0], dtype=torch.int64, device="cuda")
+        for j in range(16):
+            b |= levels[:, j] << (4 * j)
+        return b
+
+    def unpack(b):
+        return torch.stack([(b >> (4 * j)) & 15 for j in range(16)], dim=1)
+
+    def mirror(b):
+        return pack(unpack(b).view(-1, 4, 4).flip(2).reshape(-1, 16))
+
+    def transpose(b):
+        return pack(unpack(b).view(-1, 4, 4).transpose(1, 2).reshape(-1, 16))
+
+    def tile_sum(b):
+        u = unpack(b)
+        return torch.where(u > 0, torch.ones_like(u) << u, torch.zeros_like(u)).sum(1)
+
+    def move(b, action):
+        a = torch.full((n,), action, dtype=torch.uint8, device="cuda")
+        out = torch.empty_like(b)
+        moved = torch.empty(n, dtype=torch.uint8, device="cuda")
+        score = torch.empty(n, dtype=torch.int32, device="cuda")
+        assert L.g2048_move_trial(b.data_ptr(), a.data_ptr(), out.data_ptr(), moved.data_ptr(), score.data_ptr(), n, st) == 0
+        return out, moved, score
+
+    boards = pack(lv)
+    mask = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert L.g2048_legal_mask(boards.data_ptr(), mask.data_ptr(), n, st) == 0
+    left, mv_l, sc_l = move(boards, 0)
+    for action in range(4):
+        out, moved, score = move(boards, action)
+        assert torch.equal(tile_sum(out), tile_sum(boards))
+        fewer = (unpack(out) > 0).sum(1) < (unpack(boards) > 0).sum(1)
+        assert torch.equal(score > 0, fewer) and torch.equal(moved != 0, out != boards)
+        assert torch.equal((mask >> action) & 1, moved)
+    right, mv_r, sc_r = move(mirror(boards), 2)
+    assert torch.equal(mirror(right), left) and torch.equal(mv_r, mv_l) and torch.equal(sc_r, sc_l)
+    up, mv_u, sc_u = move(transpose(boards), 1)
+    assert torch.equal(transpose(up), left) and torch.equal(mv_u, mv_l) and torch.equal(sc_u, sc_l)
+    down, mv_d, sc_d = move(transpose(mirror(boards)), 3)
+    assert torch.equal(mirror(transpose(down)), left) and torch.equal(mv_d, mv_l) and torch.equal(sc_d, sc_l)
+    full = (unpack(boards) > 0).all(1)
+    assert int((full & (mask == 0)).sum()) > 0 and int((mask == 15).sum()) > 0
