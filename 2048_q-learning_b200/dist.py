@@ -30,6 +30,42 @@ def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _share_device_memory(lib, device, nbytes: int, group=None):
+    """Allocate `nbytes` of zeroed device memory on this rank, exchange the CUDA-IPC handles through the process group
+    (any backend) and map every peer's allocation.  Returns (own pointer, [pointer of rank r's allocation for all r],
+    [pointers that must be g2048_peer_close'd])."""
+    import ctypes
+    from ._lib import check
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+    with torch.cuda.device(device):
+        check(lib.g2048_peer_alloc(nbytes, ctypes.byref(mine), handle), "g2048_peer_alloc")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        base, opened = [], []
+        for r in range(world):
+            if r == rank:
+                base.append(mine.value)
+                continue
+            p = ctypes.c_void_p()
+            check(lib.g2048_peer_open((ctypes.c_ubyte * 64)(*handles[r]), ctypes.byref(p)), "g2048_peer_open")
+            base.append(p.value)
+            opened.append(p.value)
+    dist.barrier(group=group)          # every rank has mapped every buffer before anyone touches them
+    return mine.value, base, opened
+
+
+def _unshare_device_memory(lib, device, mine, opened, group=None):
+    with torch.cuda.device(device):
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=group)   # nobody unmaps while a peer may still read
+        for p in opened:
+            lib.g2048_peer_close(p)
+        if mine:
+            lib.g2048_peer_free(mine)
+
+
 class TorchEngine:
     """The GPU engine: BatchedGame2048Env + BatchedQLearningAgent of this rank."""
 
@@ -65,26 +101,11 @@ class PeerRecordBuffers:
             raise ValueError("peer exchange supports up to 16 GPUs of one box")
         self.slot_bytes = ((self.n_max * 16 + 255) // 256) * 256
         nbytes = self.FLAG_BYTES + 2 * self.slot_bytes
-        mine, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        self._mine, self.base, self._opened = _share_device_memory(lib, device, nbytes, group)
+        self._flags = (ctypes.c_void_p * self.world)(*self.base)
         with torch.cuda.device(device):
-            self._check(lib.g2048_peer_alloc(nbytes, ctypes.byref(mine), handle), "g2048_peer_alloc")
-            allh = [None] * self.world      # 64-byte handles through the control plane (any backend)
-            dist.all_gather_object(allh, bytes(handle), group=group)
-            self.base, self._opened = [], []
-            for r in range(self.world):
-                if r == self.rank:
-                    self.base.append(mine.value)
-                    continue
-                p = ctypes.c_void_p()
-                buf = (ctypes.c_ubyte * 64)(*allh[r])
-                self._check(lib.g2048_peer_open(buf, ctypes.byref(p)), "g2048_peer_open")
-                self.base.append(p.value)
-                self._opened.append(p.value)
-            self._mine = mine.value
-            self._flags = (ctypes.c_void_p * self.world)(*self.base)
             self.timed_out = torch.zeros(1, dtype=torch.int32, device=device)
         self.epoch = 0
-        dist.barrier(group=group)          # every rank has mapped every buffer before anyone signals
 
     def _check(self, rc, what):
         from ._lib import check
@@ -107,16 +128,8 @@ class PeerRecordBuffers:
             raise RuntimeError(f"peer barrier timed out waiting for rank {v - 1}")
 
     def close(self):
-        with torch.cuda.device(self.device):
-            torch.cuda.synchronize()
-            if dist.is_initialized():
-                dist.barrier(group=self.group)   # nobody unmaps while a peer may still read
-            for p in self._opened:
-                self.lib.g2048_peer_close(p)
-            self._opened = []
-            if self._mine:
-                self.lib.g2048_peer_free(self._mine)
-                self._mine = None
+        _unshare_device_memory(self.lib, self.device, self._mine, self._opened, self.group)
+        self._mine, self._opened = None, []
 
 
 class ShardedQLearning:
@@ -202,24 +215,8 @@ class SharedQTable:
             self._local = self.ptrs            # all shards are local
         else:
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-            nbytes = self.slots_per_shard * 32
-            mine, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
-            with torch.cuda.device(device):
-                check(lib.g2048_peer_alloc(nbytes, ctypes.byref(mine), handle), "g2048_peer_alloc")
-                allh = [None] * self.world
-                dist.all_gather_object(allh, bytes(handle), group=group)
-                self.ptrs = []
-                for r in range(self.world):
-                    if r == self.rank:
-                        self.ptrs.append(mine.value)
-                        continue
-                    p = ctypes.c_void_p()
-                    check(lib.g2048_peer_open((ctypes.c_ubyte * 64)(*allh[r]), ctypes.byref(p)), "g2048_peer_open")
-                    self.ptrs.append(p.value)
-                    self._opened.append(p.value)
-            self._mine = mine.value
-            self._local = [mine.value]
-            dist.barrier(group=group)
+            self._mine, self.ptrs, self._opened = _share_device_memory(lib, device, self.slots_per_shard * 32, group)
+            self._local = [self._mine]
         m = len(self.ptrs)
         if m & (m - 1) or m * self.slots_per_shard > (1 << 31):
             raise ValueError("number of shards must be a power of two and the table at most 2^31 slots")
@@ -294,16 +291,9 @@ class SharedQTable:
         return k[order], r[order]
 
     def close(self):
-        with torch.cuda.device(self.device):
-            torch.cuda.synchronize()
-            if self.world > 1 and dist.is_initialized():
-                dist.barrier(group=self.group)
-            for p in self._opened:
-                self.lib.g2048_peer_close(p)
-            self._opened = []
-            if self._mine:
-                self.lib.g2048_peer_free(self._mine)
-                self._mine = None
+        if self._mine or self._opened:
+            _unshare_device_memory(self.lib, self.device, self._mine, self._opened, self.group)
+        self._mine, self._opened = None, []
 
 
 class OwnerComputesQLearning:
@@ -335,28 +325,14 @@ class OwnerComputesQLearning:
         self.cap = max(hi - lo for lo, hi in (shard_range(self.n_total, r, self.world) for r in range(self.world)))
         self.list_bytes = ((self.cap * self.window * 16 + 255) // 256) * 256
         nbytes = self.HEAD + 2 * self.world * self.list_bytes
-        mine, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        self._mine, self.base, self._opened = _share_device_memory(self.lib, self.device, nbytes, group)
         with torch.cuda.device(self.device):
-            check(self.lib.g2048_peer_alloc(nbytes, ctypes.byref(mine), handle), "g2048_peer_alloc")
-            allh = [None] * self.world
-            dist.all_gather_object(allh, bytes(handle), group=group)
-            self.base, self._opened = [], []
-            for r in range(self.world):
-                if r == self.rank:
-                    self.base.append(mine.value)
-                    continue
-                p = ctypes.c_void_p()
-                check(self.lib.g2048_peer_open((ctypes.c_ubyte * 64)(*allh[r]), ctypes.byref(p)), "g2048_peer_open")
-                self.base.append(p.value)
-                self._opened.append(p.value)
-            self._mine = mine.value
             self._flags = (ctypes.c_void_p * self.world)(*self.base)
             self.timed_out = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._scratch = None
             self._carry_slot = torch.zeros(env.n, dtype=torch.int32, device=self.device) if self.window > 1 else None
             self._carry_row = torch.zeros((env.n, 4), dtype=torch.float32, device=self.device) if self.window > 1 else None
         self.epoch, self.t, self.k = 0, 0, 0      # barrier epoch, window number, step inside the window
-        dist.barrier(group=group)
 
     # layout helpers: counts[slot][j] and list[slot][j] inside rank r's buffer
     def _counts(self, r, slot):
@@ -429,13 +405,8 @@ class OwnerComputesQLearning:
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
             v = int(self.timed_out.item())
-            dist.barrier(group=self.group)
-            for p in self._opened:
-                self.lib.g2048_peer_close(p)
-            self._opened = []
-            if self._mine:
-                self.lib.g2048_peer_free(self._mine)
-                self._mine = None
+        _unshare_device_memory(self.lib, self.device, self._mine, self._opened, self.group)
+        self._mine, self._opened = None, []
         if v:
             raise RuntimeError(f"peer barrier timed out waiting for rank {v - 1}")
 
