@@ -196,8 +196,9 @@ def test_c_program_drives_the_abi(L):
         assert "fused rollout: 1048576 steps" in run.stdout
 
 
+@pytest.mark.parametrize("replay", [False, True])
 @pytest.mark.parametrize("flavour", [0, 1])
-def test_env_step_large_batch_path_equals_small_batch_path(flavour):
+def test_env_step_large_batch_path_equals_small_batch_path(flavour, replay):
     """From 2^19 envs on g2048_env_step runs as persistent CTAs with the LUT in shared memory; the same envs stepped in
     chunks of 2^17 (LUT through L1) must give identical boards, aux, scores, rewards, flags and max tiles."""
     import torch
@@ -221,11 +222,17 @@ def test_env_step_large_batch_path_equals_small_batch_path(flavour):
         f = torch.zeros(n, dtype=torch.uint8, device="cuda")
         m = torch.zeros(n, dtype=torch.uint8, device="cuda")
         ms = torch.zeros(n, dtype=torch.int32, device="cuda")
+        gen = torch.Generator(device="cuda").manual_seed(5)
         for t in range(40):
             act = ((torch.arange(n, device="cuda") * 7 + t * 3) % 4).to(torch.uint8)
+            # recorded draws (spawn cell, is-4, and the nopenalty full-board pair): 4 bytes per env, same for both paths
+            draws = torch.randint(0, 16, (n, 4), device="cuda", generator=gen).to(torch.uint8)
+            draws[:, 1] = (draws[:, 1] == 0).to(torch.uint8)
+            draws[:, 3] = (draws[:, 3] == 0).to(torch.uint8)
             spans = [(0, n)] if big else [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
             for lo, hi in spans:
-                rc = L.g2048_env_step(b[lo:].data_ptr(), a[lo:].data_ptr(), s[lo:].data_ptr(), act[lo:].data_ptr(), None,
+                rc = L.g2048_env_step(b[lo:].data_ptr(), a[lo:].data_ptr(), s[lo:].data_ptr(), act[lo:].data_ptr(),
+                                      draws[lo:].data_ptr() if replay else None,
                                       r[lo:].data_ptr(), None, f[lo:].data_ptr(), m[lo:].data_ptr(), ms[lo:].data_ptr(),
                                       hi - lo, flavour, seed, t, lo, st)
                 assert rc == 0, L.g2048_last_error()
