@@ -19,8 +19,8 @@ def np_boards(t):
     return t.detach().cpu().numpy().view(np.uint64)
 
 
-def single_process_result(g, n, steps):
-    env = g.BatchedGame2048Env(n, "penalty", seed=SEED)
+def single_process_result(g, n, steps, flavour="penalty"):
+    env = g.BatchedGame2048Env(n, flavour, seed=SEED)
     agent = g.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 0.4, capacity=CAP, seed=SEED)
     env.reset()
     for _ in range(steps):
@@ -260,7 +260,8 @@ def test_two_processes_learn_one_table_through_peer_memory(tmp_path):
 
 
 # ---------------------------------------------------------------- exact synchronous step, owner computes
-def test_owner_computes_step_equals_the_single_table_deterministic_step():
+@pytest.mark.parametrize("flavour,code", [("penalty", 0), ("nopenalty", 1)])
+def test_owner_computes_step_equals_the_single_table_deterministic_step(flavour, code):
     """Virtual ranks in one process through the raw C ABI: 2 env shards (ragged), a table of 2 shards; every owner sorts
     and applies only the records for its shard.  Boards and table content equal the single-GPU deterministic run."""
     import ctypes
@@ -270,13 +271,13 @@ def test_owner_computes_step_equals_the_single_table_deterministic_step():
     L = g2048.lib()
     sizes, G, steps, slots = [1700, 1301], 2, 14, 1 << 17
     n = sum(sizes)
-    boards1, keys1, rows1 = single_process_result(g2048, n, steps)       # capacity CAP = 2 * slots
+    boards1, keys1, rows1 = single_process_result(g2048, n, steps, flavour)       # capacity CAP = 2 * slots
     assert CAP == G * slots
     lo = [0, sizes[0]]
     idx_bits = (n - 1).bit_length()
     shards = [torch.zeros(slots * 4, dtype=torch.int64, device="cuda") for _ in range(G)]
     shared = gdist.SharedQTable(L, torch.device("cuda", 0), slots, shards=shards)
-    envs = [g2048.BatchedGame2048Env(sizes[r], "penalty", seed=SEED, env_id_base=lo[r]) for r in range(G)]
+    envs = [g2048.BatchedGame2048Env(sizes[r], flavour, seed=SEED, env_id_base=lo[r]) for r in range(G)]
     for e in envs:
         e.reset()
     lists = [[torch.zeros((max(sizes), 2), dtype=torch.int64, device="cuda") for _ in range(G)] for _ in range(G)]
@@ -289,7 +290,7 @@ def test_owner_computes_step_equals_the_single_table_deterministic_step():
             counts[r].zero_()
             arr = (ctypes.c_void_p * G)(*[x.data_ptr() for x in lists[r]])
             rc = L.g2048_qlearn_emit_owned(envs[r].boards.data_ptr(), envs[r].aux.data_ptr(), envs[r].score.data_ptr(),
-                                           shared._arr, G, slots, sizes[r], 0, 0.99, 0.4, SEED, t, lo[r], lo[r], idx_bits,
+                                           shared._arr, G, slots, sizes[r], code, 0.99, 0.4, SEED, t, lo[r], lo[r], idx_bits,
                                            envs[r].counters.data_ptr(), arr, counts[r].data_ptr(), None, None, 0, st)
             assert rc == 0, L.g2048_last_error()
         host = torch.stack(counts).cpu().numpy()                 # [rank][owner]
