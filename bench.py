@@ -16,6 +16,12 @@ Prints ONE JSON line (rank 0).  `value`: device-resident throughput (CUDA events
 host<->device copies inside the timed region; `roofline`: the fused kernel against the measured HBM peak
 (32 algorithmic bytes per env step); `cpu_baseline`: the C oracle port on the host cores (bounded sample).
 `--impl reference` times that CPU port as the reference arm.
+
+Optional side measurements (extras of the same line): --exchange [--exchange-envs M] the exact synchronous mode across
+GPUs (replicated tables over NCCL / NVLink peer memory, owner-computes on one sharded table, every step and every 16
+steps); --shared-table the fused rollout on ONE table sharded over the GPUs' HBM; --dqn BASELINE config 5 (197 M-parameter
+network in the loop, data-parallel replay step); --eps the other exploration rate; --no-extras skips the explanatory
+single-GPU measurements (random rollout, single-step API, stand-alone update, DQN feed, live HBM random-access peaks).
 """
 from __future__ import annotations
 
