@@ -351,6 +351,60 @@ def record_seeded(steps: int = 400, episodes: int = 20):
     return out
 
 
+def record_dqn(n_boards: int = 512, n_cases: int = 3000):
+    """The action-selection path of the reference's DQN agent, executed from its own source (ref_shim.load_dqn_agent):
+    encode_state (Dqn8TestNOPERCNN.py:271-277) on random boards, and act / act_ripetitive (:312-336) + update_epsilon
+    (:341-343) on a stand-in object whose `model.predict` returns prescribed Q-values.  epsilon_start = 0 puts every
+    call on the greedy branch, which is the deterministic part (argmax, ties, restriction to the legal moves, the
+    fallback without legal moves); the exploring branch draws from MT19937 and is checked statistically elsewhere."""
+    mod = ref_shim.load_dqn_agent()
+    A = mod.DQNAgent
+    rs = np.random.RandomState(77)
+    lv = rs.randint(0, 16, size=(n_boards, 16))
+    lv = np.where(rs.random_sample((n_boards, 16)) < rs.random_sample((n_boards, 1)), 0, lv)
+    tiles = np.where(lv > 0, 1 << lv, 0).astype(np.int64).reshape(n_boards, 4, 4)
+    enc = np.concatenate([np.asarray(A.encode_state(None, b)) for b in tiles]).astype(np.float32)
+
+    class Model:
+        q = None
+
+        def predict(self, x, verbose=0):
+            return Model.q[None, :]
+
+    class Stand:
+        pass
+    me = Stand()
+    me.epsilon_start, me.epsilon_min, me.epsilon_decay, me.epsilon, me.step_counter, me.action_space = 0.0, 0.0, 0.9999, 0.0, 0, 4
+    me.model = Model()
+    me.encode_state = lambda b: A.encode_state(me, b)
+    me.update_epsilon = lambda: A.update_epsilon(me)
+    q = rs.standard_normal((n_cases, 4)).astype(np.float32)
+    q[::3, 1] = q[::3, 3]          # ties
+    q[::5, 0] = q[::5, 2]
+    q[::11] = q[::11, :1]          # all four equal
+    legal = rs.randint(0, 16, n_cases).astype(np.uint8)
+    legal[::13] = 0                # no legal move at all
+    act, act_rip = np.zeros(n_cases, np.uint8), np.zeros(n_cases, np.uint8)
+    np.random.seed(5)              # the draws only decide "explore?": rand() <= 0 never holds
+    for i in range(n_cases):
+        Model.q = q[i]
+        board = tiles[i % n_boards]
+        act[i] = int(A.act(me, board))
+        moves = [a for a in range(4) if (int(legal[i]) >> a) & 1]
+        act_rip[i] = int(A.act_ripetitive(me, board, moves))
+    assert me.step_counter == n_cases                         # act() counts steps (:316), act_ripetitive does not
+    # update_epsilon with the reference's default constants (:249): epsilon(step) for a few step counts
+    me.epsilon_start, me.epsilon_min = 0.9, 0.001
+    steps = np.array([0, 1, 10, 1000, 10_000, 50_000, 67_000, 68_100, 100_000], np.int64)
+    eps = []
+    for st in steps:
+        me.step_counter = int(st)
+        A.update_epsilon(me)
+        eps.append(me.epsilon)
+    return {"tiles": tiles, "onehot": enc, "q": q, "legal": legal, "act": act, "act_ripetitive": act_rip,
+            "eps_steps": steps, "eps": np.array(eps, np.float64)}
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit(f"reference not found under {ref_shim.REF_ROOT}")
@@ -367,6 +421,10 @@ def main():
     path = os.path.join(OUT_DIR, "compat_seeded.npz")
     np.savez_compressed(path, **sd)
     print(f"{path}: {len(sd['loop_actions'])} loop steps, {os.path.getsize(path) / 1e3:.0f} kB")
+    dq = record_dqn()
+    path = os.path.join(OUT_DIR, "dqn_agent.npz")
+    np.savez_compressed(path, **dq)
+    print(f"{path}: {len(dq['tiles'])} encoded boards, {len(dq['q'])} action selections, {os.path.getsize(path) / 1e3:.0f} kB")
     q = record_qlearn()
     path = os.path.join(OUT_DIR, "qlearn_ref.npz")
     np.savez_compressed(path, **q)

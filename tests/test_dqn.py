@@ -169,3 +169,31 @@ def test_train_dqn_driver_cadence(tmp_path):
     other = dqn.BatchedDQNAgent(width=16, hidden=32, memory_size=1 << 14, batch_size=64)
     other.load_agent_state(str(tmp_path / "saves" / saves[-1]))
     assert other.nb_entries > 0 and other.step_counter > 0
+
+
+@pytest.mark.gpu
+def test_encode_and_greedy_action_selection_match_the_reference_agent(golden):
+    """g2048_encode_onehot and the greedy branch of g2048_select_action against goldens recorded from the reference's
+    own DQNAgent.encode_state / act / act_ripetitive (Dqn8TestNOPERCNN.py:271-277, :312-336): argmax with ties, the
+    restriction to the legal moves, and the fallback when no move is legal."""
+    import g2048
+    g2048.init(0)
+    L = g2048.lib()
+    g = golden("dqn_agent")
+    st = torch.cuda.current_stream().cuda_stream
+    boards, bad = oracle.pack_i64(g["tiles"])
+    assert bad == 0
+    b = torch.from_numpy(boards.view(np.int64)).cuda()
+    for code, dtype in ((0, torch.float32), (1, torch.bfloat16)):
+        out = torch.empty((len(boards), 16, 4, 4), dtype=dtype, device="cuda")
+        assert L.g2048_encode_onehot(b.data_ptr(), out.data_ptr(), len(boards), code, st) == 0
+        assert np.array_equal(out.float().cpu().numpy(), g["onehot"])
+    n = len(g["q"])
+    q = torch.from_numpy(g["q"]).cuda()
+    legal = torch.from_numpy(g["legal"]).cuda()
+    a = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert L.g2048_select_action(q.data_ptr(), None, a.data_ptr(), n, 0.0, 1, 0, 0, st) == 0
+    assert np.array_equal(a.cpu().numpy(), g["act"])
+    assert L.g2048_select_action(q.data_ptr(), legal.data_ptr(), a.data_ptr(), n, 0.0, 1, 0, 0, st) == 0
+    assert np.array_equal(a.cpu().numpy(), g["act_ripetitive"])
+    assert (g["act"] != g["act_ripetitive"]).sum() > 100          # the legal-move restriction matters in the sample

@@ -133,3 +133,23 @@ def test_batch_update_n1_is_sequential_update(golden):
     k64, r64 = tab64.export()
     assert np.array_equal(k64, keys)
     np.testing.assert_allclose(rows, r64, rtol=1e-5, atol=1e-5)
+
+
+def test_dqn_encode_state_and_epsilon_follow_the_reference_agent(golden):
+    """Golden recorded by running the reference's own DQNAgent.encode_state / update_epsilon source
+    (Dqn8TestNOPERCNN.py:271-277, :341-343; oracle/make_golden.py:record_dqn, TF ops stubbed with numpy)."""
+    g = golden("dqn_agent")
+    boards, bad = oracle.pack_i64(g["tiles"])
+    assert bad == 0
+    assert np.array_equal(oracle.encode_onehot(boards), g["onehot"])
+    assert g["onehot"].sum() == 16 * len(boards) and g["onehot"][:, 15].sum() > 0        # 32768 tiles are in the sample
+
+    from g2048 import dqn
+
+    class Stand:
+        epsilon_start, epsilon_min, epsilon_decay, epsilon, step_counter = 0.9, 0.001, 0.9999, 0.9, 0
+    me = Stand()
+    for step, want in zip(g["eps_steps"], g["eps"]):
+        me.step_counter = int(step)
+        dqn.BatchedDQNAgent.update_epsilon(me)
+        assert me.epsilon == want                      # float64, same expression: bit-equal
