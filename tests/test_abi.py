@@ -84,3 +84,38 @@ def test_header_compiles_as_c_and_links():
         run = subprocess.run([exe], capture_output=True, text=True)
         if ctypes.CDLL(g2048.build()).g2048_device_count() == 0:
             assert run.returncode == 2 and "no CPU fallback" in run.stderr      # refuses loudly without a GPU
+
+
+def test_ctypes_signatures_agree_with_the_header():
+    """Every prototype of include/g2048.h against the ctypes table of _lib.py: same number of arguments, pointers bound
+    as void pointers, 64-bit integers as 64-bit, floats/doubles as such, and the same kind of return value."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "g2048.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith("#"))
+    protos = re.findall(r"G2048_API\s+([^;{]+?)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) == len(g2048.declared_symbols())
+
+    def kind(decl):
+        decl = " ".join(decl.split())
+        if "*" in decl:
+            return "ptr"
+        base = decl.rsplit(" ", 1)[0] if " " in decl else decl
+        base = base.replace("const ", "").strip()
+        return {"int": "i32", "int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64", "size_t": "u64",
+                "float": "f32", "double": "f64", "void": "void"}[base]
+
+    ctype_kind = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "i32", ctypes.c_int32: "i32",
+                  ctypes.c_uint32: "u32", ctypes.c_int64: "i64", ctypes.c_uint64: "u64", ctypes.c_size_t: "u64",
+                  ctypes.c_float: "f32", ctypes.c_double: "f64", None: "void"}
+    for ret_and_name, params in protos:
+        parts = ret_and_name.split()
+        name = parts[-1].lstrip("*")
+        ret = " ".join(parts[:-1]) + ("*" if parts[-1].startswith("*") or parts[-2].endswith("*") else "")
+        restype, argtypes = _lib._SIG[name]
+        plist = [p for p in (q.strip() for q in params.split(",")) if p and p != "void"]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+        for i, (p, a) in enumerate(zip(plist, argtypes)):
+            assert kind(p + " x" if " " not in p else p) == ctype_kind[a], (name, i, p, a)
+        assert kind(ret + " x") == ctype_kind[restype], (name, ret, restype)
