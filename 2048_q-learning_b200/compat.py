@@ -321,8 +321,9 @@ class QLearningAgent:
         s, s2 = np.array([pack_tiles(state)], np.uint64), np.array([pack_tiles(next_state)], np.uint64)
         a, d = np.array([int(action)], np.uint8), np.array([1 if done else 0], np.uint8)
         r = np.array([reward], np.float32)
+        # one record: the atomic path is the same arithmetic as the deterministic one, without the sort launches
         check(self._be.lib.g2048_ctx_qtable_update(self._be.ctx, _vp(s), _vp(a), _vp(r), _vp(s2), _vp(d), 1,
-                                                   float(self.lr), float(self.gamma), 1), "qtable_update")
+                                                   float(self.lr), float(self.gamma), 0), "qtable_update")
 
     def decay_exploration(self, current_epoch):
         epsilon_schedule_step(self, current_epoch)
