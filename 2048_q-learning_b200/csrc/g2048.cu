@@ -1533,7 +1533,7 @@ G2048_API int g2048_qtable_apply_targets(void* table, uint64_t capacity, const u
     k_keys_to_records<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((Slot*)table, capacity - 1, (const u64*)keys, a,
                                                                              n, sc.key_in);
     LAUNCH_CHECK("k_keys_to_records");
-    CK(cudaMemcpyAsync(sc.val_in, target, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, S(stream)));
+    CK(cudaMemcpyAsync(sc.val_in, target, (size_t)n * sizeof(float), cudaMemcpyDefault, S(stream)));
     return apply_records(D, (Slot*)table, capacity, sc, n, lr, mode, S(stream));
 }
 G2048_API int g2048_qtable_size(const void* table, uint64_t capacity, int64_t* count, void* stream) {
@@ -1584,7 +1584,13 @@ struct g2048_ctx {
     long long* counters = nullptr;  // G2048_N_COUNTERS + 1 (export/size count)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // Contexts for a handful of envs (the N = 1 drop-in adapters) stage through ONE block of pinned host memory that
+    // the kernels read and write directly (mapped under unified addressing): a call then costs its kernel and one
+    // stream synchronisation instead of about ten small copies from pageable memory.
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
 };
+constexpr int64_t kTinyCtxEnvs = 64;
 
 G2048_API g2048_ctx* g2048_ctx_create(int device, int64_t max_envs, uint64_t table_capacity) {
     if (max_envs <= 0 || (table_capacity && !pow2(table_capacity))) { fail(G2048_ERR_ARG, "g2048_ctx_create: bad arguments"); return nullptr; }
@@ -1598,16 +1604,32 @@ G2048_API g2048_ctx* g2048_ctx_create(int device, int64_t max_envs, uint64_t tab
     for (int j = 0; ok && j < 3; ++j)
         ok = cudaStreamCreateWithFlags(&c->pipe[j], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_done[j], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok &&
+    if (ok && max_envs <= kTinyCtxEnvs) {
+        const size_t slot = align256(m * 16);            // every staging buffer fits one slot (rows: 16 B per env)
+        c->arena_bytes = 13 * slot;
+        ok = cudaHostAlloc(&c->arena, c->arena_bytes, cudaHostAllocDefault) == cudaSuccess;
+        if (ok) {
+            char* p = (char*)c->arena;
+            memset(p, 0, c->arena_bytes);
+            auto take = [&]() { char* q = p; p += slot; return (void*)q; };
+            c->boards = (u64*)take(); c->aux = (u64*)take(); c->keys2 = (u64*)take();
+            c->score = (int*)take(); c->move_score = (int*)take();
+            c->bytes_a = (uint8_t*)take(); c->bytes_b = (uint8_t*)take(); c->flags = (uint8_t*)take();
+            c->maxlvl = (uint8_t*)take(); c->draws = (uint8_t*)take();
+            c->rew64 = (double*)take(); c->rows = (float*)take(); c->rew32 = (float*)take();
+        }
+    } else {
+        ok = ok &&
               cudaMalloc(&c->boards, m * 8) == cudaSuccess && cudaMalloc(&c->aux, m * 8) == cudaSuccess &&
               cudaMalloc(&c->keys2, m * 8) == cudaSuccess && cudaMalloc(&c->score, m * 4) == cudaSuccess &&
               cudaMalloc(&c->move_score, m * 4) == cudaSuccess && cudaMalloc(&c->bytes_a, m) == cudaSuccess &&
               cudaMalloc(&c->bytes_b, m) == cudaSuccess && cudaMalloc(&c->flags, m) == cudaSuccess &&
               cudaMalloc(&c->maxlvl, m) == cudaSuccess && cudaMalloc(&c->draws, m * 4) == cudaSuccess &&
               cudaMalloc(&c->rew64, m * 8) == cudaSuccess && cudaMalloc(&c->rows, m * 16) == cudaSuccess &&
-              cudaMalloc(&c->rew32, m * 4) == cudaSuccess &&
-              cudaMalloc(&c->counters, (G2048_N_COUNTERS + 1) * sizeof(long long)) == cudaSuccess &&
-              cudaMalloc(&c->scratch, c->scratch_bytes) == cudaSuccess;
+              cudaMalloc(&c->rew32, m * 4) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&c->counters, (G2048_N_COUNTERS + 1) * sizeof(long long)) == cudaSuccess &&
+         cudaMalloc(&c->scratch, c->scratch_bytes) == cudaSuccess;
     if (ok && table_capacity) {
         ok = cudaMalloc(&c->table, g2048_qtable_bytes(table_capacity)) == cudaSuccess &&
              cudaMemsetAsync(c->table, 0, g2048_qtable_bytes(table_capacity), c->stream) == cudaSuccess &&
@@ -1623,8 +1645,13 @@ G2048_API g2048_ctx* g2048_ctx_create(int device, int64_t max_envs, uint64_t tab
 G2048_API void g2048_ctx_destroy(g2048_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->boards, c->aux, c->keys2, c->score, c->move_score, c->bytes_a, c->bytes_b, c->flags, c->maxlvl,
-                    c->draws, c->rew64, c->rows, c->rew32, c->counters, c->scratch, c->table};
+    void* staging[] = {c->boards, c->aux, c->keys2, c->score, c->move_score, c->bytes_a, c->bytes_b, c->flags, c->maxlvl,
+                       c->draws, c->rew64, c->rows, c->rew32};
+    if (c->arena) cudaFreeHost(c->arena);
+    else
+        for (void* p : staging)
+            if (p) cudaFree(p);
+    void* ptrs[] = {c->counters, c->scratch, c->table};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1646,10 +1673,25 @@ G2048_API void* g2048_ctx_stream(g2048_ctx* c) { return c ? (void*)c->stream : n
     CK(cudaSetDevice(c->device));                                                                \
     cudaStream_t st = c->stream;                                                                 \
     (void)st
-#define H2D(dst, src, bytes) \
-    if (src) CK(cudaMemcpyAsync(dst, src, (size_t)(bytes), cudaMemcpyHostToDevice, st))
-#define D2H(dst, src, bytes) \
-    if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(bytes), cudaMemcpyDeviceToHost, st))
+static inline bool in_arena(const g2048_ctx* c, const void* p) {
+    return c->arena && (const char*)p >= (const char*)c->arena && (const char*)p < (const char*)c->arena + c->arena_bytes;
+}
+// host -> staging: a plain memcpy into the pinned arena (nothing is in flight: every call ends with a synchronise)
+static inline int ctx_h2d(g2048_ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (!src || !bytes) return 0;
+    if (in_arena(c, dst)) { memcpy(dst, src, bytes); return 0; }
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+// staging -> host: from the arena once the kernels have finished, else an asynchronous copy
+static inline int ctx_d2h(g2048_ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (!dst || !bytes) return 0;
+    if (in_arena(c, src)) { CK(cudaStreamSynchronize(st)); memcpy(dst, src, bytes); return 0; }
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+#define H2D(dst, src, bytes) RC(ctx_h2d(c, dst, src, (size_t)(bytes), st))
+#define D2H(dst, src, bytes) RC(ctx_d2h(c, dst, src, (size_t)(bytes), st))
 #define RC(expr)              \
     do {                      \
         int rc_ = (expr);     \
@@ -1740,9 +1782,9 @@ static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* s
         if (pipelined) m = j == 0 ? unit : rem >= 3 * unit ? 2 * unit : rem > unit ? unit : rem;
         cudaStream_t ps = pipelined ? c->pipe[j % 3] : st;
         if (pipelined) CK(cudaStreamWaitEvent(ps, c->ev_start, 0));
-        CK(cudaMemcpyAsync(c->boards + lo, boards + lo, (size_t)m * 8, cudaMemcpyHostToDevice, ps));
-        if (aux) CK(cudaMemcpyAsync(c->aux + lo, aux + lo, (size_t)m * 8, cudaMemcpyHostToDevice, ps));
-        if (score) CK(cudaMemcpyAsync(c->score + lo, score + lo, (size_t)m * 4, cudaMemcpyHostToDevice, ps));
+        CK(cudaMemcpyAsync(c->boards + lo, boards + lo, (size_t)m * 8, cudaMemcpyDefault, ps));
+        if (aux) CK(cudaMemcpyAsync(c->aux + lo, aux + lo, (size_t)m * 8, cudaMemcpyDefault, ps));
+        if (score) CK(cudaMemcpyAsync(c->score + lo, score + lo, (size_t)m * 4, cudaMemcpyDefault, ps));
         uint64_t* db = (uint64_t*)c->boards + lo;
         uint64_t* da = aux ? (uint64_t*)c->aux + lo : nullptr;
         int32_t* ds = score ? c->score + lo : nullptr;
@@ -1752,9 +1794,9 @@ static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* s
         else
             RC(g2048_rollout_random(db, da, ds, m, k_steps, flavour, seed, step_base, env_id_base + (uint64_t)lo,
                                     (int64_t*)c->counters, ps));
-        CK(cudaMemcpyAsync(boards + lo, c->boards + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, ps));
-        if (aux) CK(cudaMemcpyAsync(aux + lo, c->aux + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, ps));
-        if (score) CK(cudaMemcpyAsync(score + lo, c->score + lo, (size_t)m * 4, cudaMemcpyDeviceToHost, ps));
+        CK(cudaMemcpyAsync(boards + lo, c->boards + lo, (size_t)m * 8, cudaMemcpyDefault, ps));
+        if (aux) CK(cudaMemcpyAsync(aux + lo, c->aux + lo, (size_t)m * 8, cudaMemcpyDefault, ps));
+        if (score) CK(cudaMemcpyAsync(score + lo, c->score + lo, (size_t)m * 4, cudaMemcpyDefault, ps));
         lo += m;
     }
     if (pipelined)
