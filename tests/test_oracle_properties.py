@@ -98,3 +98,58 @@ def test_pack_unpack_round_trip_and_row_table(boards):
     rows = rows[rows != 0]
     out, _, _ = oracle.move(rows, np.zeros(len(rows), np.uint8))
     assert np.array_equal(out, res[rows.astype(np.int64)].astype(np.uint64))
+
+
+# ---------------------------------------------------------------- the batched Q-update, restated independently
+def test_batched_update_is_the_reference_rule_applied_in_batch_order():
+    """update_q_value (main.py:40-43) for a batch, as this build defines it: all targets from the
+    table as it is BEFORE the batch, then every (state, action) receives its targets one after another in batch order,
+    q <- q + lr (target - q), every operation rounded to float32.  A literal numpy/dict restatement must give the
+    oracle's table bit for bit -- with heavy collisions (a pool of 40 states, 5,000 transitions)."""
+    rng = np.random.RandomState(11)
+    pool = rng.randint(1, 1 << 40, size=40).astype(np.uint64)
+    lr, gamma = np.float32(0.1), np.float32(0.99)
+    tab = oracle.QTable(1 << 12, f32=True)
+    ref = {}                                               # key -> float32[4]
+    for batch in range(6):
+        n = 5000
+        s, s2 = pool[rng.randint(0, 40, n)], pool[rng.randint(0, 40, n)]
+        a = rng.randint(0, 4, n).astype(np.uint8)
+        r = rng.standard_normal(n).astype(np.float32)
+        done = (rng.random_sample(n) < 0.1).astype(np.uint8)
+        tab.update_batch_f32(s, a, r, s2, done, float(lr), float(gamma))
+        snap = {k: v.copy() for k, v in ref.items()}
+        zero = np.zeros(4, np.float32)
+        target = np.empty(n, np.float32)
+        for i in range(n):
+            best = np.float32(snap.get(int(s2[i]), zero).max())
+            g = np.float32(gamma * best)
+            target[i] = np.float32(r[i] + (np.float32(0) if done[i] else g))
+        for i in range(n):
+            row = ref.setdefault(int(s[i]), np.zeros(4, np.float32))
+            ref.setdefault(int(s2[i]), np.zeros(4, np.float32))            # reading a state creates its zero row
+            q = row[a[i]]
+            row[a[i]] = np.float32(q + np.float32(lr * np.float32(target[i] - q)))
+    keys, rows = tab.export()
+    want_keys = np.array(sorted(ref), np.uint64)
+    assert np.array_equal(keys, want_keys)
+    want = np.stack([ref[int(k)] for k in want_keys])
+    assert np.array_equal(rows.astype(np.float32), want)
+    assert np.isfinite(want).all() and np.abs(want).max() < 10      # a contraction: no blow-up under 125 hits per value
+
+
+def test_apply_targets_is_order_sensitive_and_sequential():
+    """apply_targets: the records of one (state, action) are applied in the order given -- reversing them changes the
+    float32 result, and the result always lies between the old value and the extreme targets."""
+    key = np.full(64, 12345, np.uint64)
+    a = np.zeros(64, np.uint8)
+    t = np.linspace(-3, 5, 64).astype(np.float32)
+    one, two = oracle.QTable(1 << 8, f32=True), oracle.QTable(1 << 8, f32=True)
+    one.apply_targets_f32(key, a, t, 0.1)
+    two.apply_targets_f32(key, a, t[::-1].copy(), 0.1)
+    q1, q2 = one.export()[1][0, 0], two.export()[1][0, 0]
+    assert q1 != q2 and -3 <= min(q1, q2) and max(q1, q2) <= 5
+    q = np.float32(0)
+    for x in t:
+        q = np.float32(q + np.float32(np.float32(0.1) * np.float32(x - q)))
+    assert q1 == q
