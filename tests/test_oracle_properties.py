@@ -153,3 +153,29 @@ def test_apply_targets_is_order_sensitive_and_sequential():
     for x in t:
         q = np.float32(q + np.float32(np.float32(0.1) * np.float32(x - q)))
     assert q1 == q
+
+
+@pytest.mark.parametrize("flavour", [oracle.FLAVOUR_PENALTY, oracle.FLAVOUR_NOPENALTY])
+def test_synchronous_step_is_choose_then_step_then_batch_update(flavour):
+    """orc_qlearn_step_sync (what the GPU's synchronous modes are compared with) == the three reference calls of the
+    loop main.py:91-101 composed from the separately pinned pieces: choose_action for every env on the table as it is,
+    env.step with the same Philox draws, then update_q_value for the whole batch (targets from the pre-step table,
+    applied in env order).  Fresh boards, 25 steps (no game ends that early, so no reset is involved)."""
+    n, seed, base, eps, lr, gamma = 700, 31, 1000, 0.35, 0.1, 0.99
+    b1 = np.zeros(n, np.uint64)
+    oracle.env_reset(b1, None, None, None, seed=seed, episode_idx=0, env_id_base=base)
+    a1, s1 = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+    b2, a2, s2 = b1.copy(), a1.copy(), s1.copy()
+    t1, t2 = oracle.QTable(1 << 16, f32=True), oracle.QTable(1 << 16, f32=True)
+    for t in range(25):
+        oracle.qlearn_step_sync(b1, a1, s1, t1, lr, gamma, eps, flavour, seed, t, base)
+        state = b2.copy()
+        actions = t2.choose_action(state, oracle.eps_threshold(eps), seed, t, base)
+        reward, flags, _, _ = oracle.env_step(b2, a2, s2, actions, None, flavour, seed, t, base)
+        done = (flags >> 2) & 1
+        assert done.sum() == 0
+        t2.update_batch_f32(state, actions, reward.astype(np.float32), b2.copy(), done.astype(np.uint8), lr, gamma)
+        assert np.array_equal(b1, b2) and np.array_equal(a1, a2) and np.array_equal(s1, s2), t
+    (k1, r1), (k2, r2) = t1.export(), t2.export()
+    assert np.array_equal(k1, k2) and np.array_equal(r1, r2)
+    assert len(k1) > 2000 and np.abs(r1).sum() > 0
