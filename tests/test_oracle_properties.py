@@ -179,3 +179,25 @@ def test_synchronous_step_is_choose_then_step_then_batch_update(flavour):
     (k1, r1), (k2, r2) = t1.export(), t2.export()
     assert np.array_equal(k1, k2) and np.array_equal(r1, r2)
     assert len(k1) > 2000 and np.abs(r1).sum() > 0
+
+
+@pytest.mark.parametrize("flavour", [oracle.FLAVOUR_PENALTY, oracle.FLAVOUR_NOPENALTY])
+def test_sequential_rollout_of_one_env_is_the_reference_loop_step_by_step(flavour):
+    """orc_rollout_qlearn_seq with one env (the oracle behind smoke() and the N = 1 GPU parity test) == the loop of
+    main.py:91-101 made of single calls: choose_action, env.step, update_q_value, one transition at a time."""
+    seed, base, eps, lr, gamma, steps = 9, 5, 0.3, 0.1, 0.99, 120
+    b1 = np.zeros(1, np.uint64)
+    oracle.env_reset(b1, None, None, None, seed=seed, episode_idx=0, env_id_base=base)
+    a1, s1 = np.full(1, oracle.AUX_INIT, np.uint64), np.zeros(1, np.int32)
+    b2, a2, s2 = b1.copy(), a1.copy(), s1.copy()
+    t1, t2 = oracle.QTable(1 << 12, f32=True), oracle.QTable(1 << 12, f32=True)
+    oracle.rollout_qlearn_seq(b1, a1, s1, t1, steps, lr, gamma, eps, flavour, seed, 0, base)
+    for t in range(steps):
+        state = b2.copy()
+        action = t2.choose_action(state, oracle.eps_threshold(eps), seed, t, base)
+        reward, flags, _, _ = oracle.env_step(b2, a2, s2, action, None, flavour, seed, t, base)
+        assert not (flags[0] >> 2) & 1, "the game must not end inside this test (no reset path in the composition)"
+        t2.update_batch_f32(state, action, reward.astype(np.float32), b2.copy(), np.zeros(1, np.uint8), lr, gamma)
+    assert np.array_equal(b1, b2) and np.array_equal(a1, a2) and np.array_equal(s1, s2)
+    (k1, r1), (k2, r2) = t1.export(), t2.export()
+    assert np.array_equal(k1, k2) and np.array_equal(r1, r2) and len(k1) > 50
