@@ -33,6 +33,7 @@ OUT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"
 N_ENVS = 96
 N_STEPS = 384
 PEN_SAT = 25
+SEED_OFFSET = 0      # the committed goldens use 0; tests/test_oracle_live_reference.py records fresh trajectories with others
 
 
 def pack_board(tiles) -> int:
@@ -168,8 +169,8 @@ def record_env(flavour: str):
         with DrawRecorder() as rec:
             for i in range(E):
                 kind, tele = env_kind(i)
-                np.random.seed(1000 + i)
-                rs = np.random.RandomState(2000 + i)
+                np.random.seed(1000 + SEED_OFFSET + i)
+                rs = np.random.RandomState(2000 + SEED_OFFSET + i)
                 env = mod.Game2048_env()
                 rec.take()
                 episode = 0

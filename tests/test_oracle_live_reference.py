@@ -1,0 +1,37 @@
+"""Where the reference checkout is present (the build container; never the GPU box): run the UNMODIFIED reference
+envs live on trajectories that are NOT in the committed goldens (other seeds), record their draws with
+oracle/make_golden.py's recorder and replay them through the oracle -- boards, flags, scores, aux state and the
+float64 reward bits must be identical.  Skipped when /root/reference does not exist."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from test_oracle_golden import oracle_step, replay_env
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_shim  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+
+
+def recorder(offset, n_envs, n_steps):
+    spec = importlib.util.spec_from_file_location("make_golden_live", os.path.join(ROOT, "oracle", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    mg.SEED_OFFSET, mg.N_ENVS, mg.N_STEPS = offset, n_envs, n_steps
+    return mg
+
+
+@pytest.mark.timeout(280)
+@pytest.mark.parametrize("flavour,code,offset", [("penalty", oracle.FLAVOUR_PENALTY, 50_000),
+                                                 ("nopenalty", oracle.FLAVOUR_NOPENALTY, 60_000)])
+def test_oracle_replays_fresh_reference_trajectories(flavour, code, offset):
+    g = recorder(offset, 64, 320).record_env(flavour)
+    replay_env(g, code, oracle_step)
+    fl = g["flags"]
+    assert fl.size == 64 * 320 and (fl & 1).mean() > 0.3 and ((fl >> 2) & 1).sum() > 0      # valid moves and finished games
