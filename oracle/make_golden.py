@@ -242,8 +242,8 @@ def record_qlearn(episodes: int = 150):
     """The loop of main.py:80-109 on the reference agent + penalty env."""
     penv = ref_shim.load_penalty_env()
     agent_mod = ref_shim.load_tabular_agent()
-    np.random.seed(0)
-    pyrandom.seed(0)
+    np.random.seed(SEED_OFFSET)
+    pyrandom.seed(SEED_OFFSET)
     env = penv.Game2048_env()
     agent = agent_mod.QLearningAgent(episodes, action_space=env.action_space.n, learning_rate=0.1,
                                      discount_factor=0.99, exploration_rate=0.95)

@@ -35,3 +35,19 @@ def test_oracle_replays_fresh_reference_trajectories(flavour, code, offset):
     replay_env(g, code, oracle_step)
     fl = g["flags"]
     assert fl.size == 64 * 320 and (fl & 1).mean() > 0.3 and ((fl >> 2) & 1).sum() > 0      # valid moves and finished games
+
+
+@pytest.mark.timeout(280)
+def test_oracle_replays_a_fresh_reference_training_run():
+    """The reference's QLearningAgent + penalty env in the loop of main.py:80-109 under seeds other than the committed
+    golden's: the oracle's float64 agent must take the same greedy actions and end with the same table, bit for bit."""
+    g = recorder(777, 1, 1).record_qlearn(episodes=40)
+    episodes, lr, gamma, eps0, eps_min = g["params"]
+    tab = oracle.QTable(1 << 17, f32=False)
+    actions = tab.replay_agent_f64(g["s"], g["explore"], g["rand_action"], g["r"], g["s2"], g["done"], lr, gamma)
+    assert np.array_equal(actions, g["a"]) and len(g["s"]) > 3000
+    keys, rows = tab.export()
+    assert np.array_equal(keys, g["q_keys"])
+    assert np.array_equal(rows.view(np.uint64), g["q_rows"].view(np.uint64))
+    sched = oracle.decay_exploration_schedule(int(episodes), eps0, eps_min)
+    assert np.array_equal(sched.view(np.uint64), g["eps"].view(np.uint64))
