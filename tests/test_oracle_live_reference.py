@@ -51,3 +51,17 @@ def test_oracle_replays_a_fresh_reference_training_run():
     assert np.array_equal(rows.view(np.uint64), g["q_rows"].view(np.uint64))
     sched = oracle.decay_exploration_schedule(int(episodes), eps0, eps_min)
     assert np.array_equal(sched.view(np.uint64), g["eps"].view(np.uint64))
+
+
+@pytest.mark.timeout(280)
+@pytest.mark.parametrize("flavour", ["penalty", "nopenalty"])
+def test_committed_goldens_are_what_the_recorder_produces(flavour, golden):
+    """tests/golden/env_*.npz == a fresh run of oracle/make_golden.py:record_env against the reference checkout."""
+    want = golden(f"env_{flavour}")
+    mg = recorder(0, 96, 384)
+    got = mg.record_env(flavour)
+    assert set(got) == set(want)
+    for k in want:
+        a, b = np.asarray(got[k]), np.asarray(want[k])
+        assert a.shape == b.shape and a.dtype == b.dtype, k
+        assert np.array_equal(a.view(np.uint8) if a.dtype.kind == "f" else a, b.view(np.uint8) if b.dtype.kind == "f" else b), k
