@@ -306,7 +306,9 @@ G2048_API int g2048_qtable_export(const void* table, uint64_t capacity, uint64_t
 
 /* ------------------------------------------------------------------ host-buffer API */
 typedef struct g2048_ctx g2048_ctx;
-/* device buffers for up to max_envs envs, one stream, and (table_capacity > 0) a Q-table in HBM */
+/* device buffers for up to max_envs envs, one stream, and (table_capacity > 0) a Q-table in HBM.  Contexts for up to
+ * 64 envs (the N = 1 drop-in adapters) stage through one pinned, mapped host block that the kernels read and write
+ * directly, so a call costs its kernel and one stream synchronisation instead of a dozen small copies. */
 G2048_API g2048_ctx* g2048_ctx_create(int device, int64_t max_envs, uint64_t table_capacity);
 G2048_API void g2048_ctx_destroy(g2048_ctx* ctx);
 G2048_API int g2048_ctx_env_reset(g2048_ctx* ctx, uint64_t* boards, int32_t* score, const uint8_t* mask,
