@@ -201,3 +201,40 @@ def test_sequential_rollout_of_one_env_is_the_reference_loop_step_by_step(flavou
     assert np.array_equal(b1, b2) and np.array_equal(a1, a2) and np.array_equal(s1, s2)
     (k1, r1), (k2, r2) = t1.export(), t2.export()
     assert np.array_equal(k1, k2) and np.array_equal(r1, r2) and len(k1) > 50
+
+
+def test_apply_commutes_across_different_state_actions_only():
+    """The invariant behind the sort-based deterministic apply and the owner-computes exchange: applying records is
+    invariant under ANY reordering that keeps the relative order of the records of one (state, action) -- e.g. grouping
+    by (state, action), or partitioning by the owner of the state and ordering each part by global env index -- and it
+    is NOT invariant under reorderings inside one (state, action)."""
+    rng = np.random.RandomState(3)
+    n, owners = 20_000, 8
+    pool = rng.randint(1, 1 << 40, size=300).astype(np.uint64)
+    keys = pool[rng.randint(0, 300, n)]
+    acts = rng.randint(0, 4, n).astype(np.uint8)
+    tg = rng.standard_normal(n).astype(np.float32)
+
+    def table_after(order):
+        t = oracle.QTable(1 << 12, f32=True)
+        t.apply_targets_f32(keys[order].copy(), acts[order].copy(), tg[order].copy(), 0.1)
+        return t.export()
+
+    k0, r0 = table_after(np.arange(n))
+    # (a) stable grouping by (state, action): what the radix sort + segment apply does
+    grouped = np.lexsort((np.arange(n), acts, keys))
+    # (b) owner-computes: records arrive in arbitrary order, are split by owner and sorted by (slot, action, global index)
+    arrival = rng.permutation(n)
+    owner = (keys[arrival] % np.uint64(owners)).astype(np.int64)
+    parts = []
+    for j in rng.permutation(owners):                      # the owners work independently, in any order
+        mine = arrival[owner == j]
+        parts.append(mine[np.lexsort((mine, acts[mine], keys[mine]))])
+    owned = np.concatenate(parts)
+    for order in (grouped, owned):
+        k, r = table_after(order)
+        assert np.array_equal(k, k0) and np.array_equal(r, r0)
+    # (c) reversing the records inside the (state, action) groups changes the float32 result
+    rev = np.lexsort((-np.arange(n), acts, keys))
+    k, r = table_after(rev)
+    assert np.array_equal(k, k0) and not np.array_equal(r, r0)
