@@ -28,17 +28,34 @@ def _nvcc() -> str:
     raise G2048Error("nvcc not found: libg2048.so cannot be built (there is no CPU fallback)")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (cross-compiles without a GPU)."""
-    stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(SO_PATH) for d in DEPENDS)
-    if force or stale:
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + SOURCES
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise G2048Error("nvcc failed:\n" + res.stdout + res.stderr)
-        if verbose:
-            print(res.stderr)
-    return SO_PATH
+def _stale() -> bool:
+    return (not os.path.exists(SO_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(SO_PATH) for d in DEPENDS)
+
+
+def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None, out: str | None = None) -> str:
+    """Compile the CUDA library in-tree for sm_100a (cross-compiles without a GPU).  Safe under torchrun: one process
+    compiles (file lock) into a temporary file that is renamed into place, the others wait and load the finished file."""
+    target = out or SO_PATH
+    if not (force or out or _stale()):
+        return target
+    import fcntl
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or out or _stale():       # nobody built it while this process waited for the lock
+                tmp = f"{target}.{os.getpid()}.tmp"
+                cmd = [_nvcc()] + NVCC_FLAGS + (extra_flags or []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                if res.returncode != 0:
+                    if os.path.exists(tmp):
+                        os.unlink(tmp)
+                    raise G2048Error("nvcc failed:\n" + res.stdout + res.stderr)
+                os.replace(tmp, target)
+                if verbose:
+                    print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return target
 
 
 def declared_symbols() -> list[str]:
@@ -118,7 +135,8 @@ def lib():
     """Load (building first if needed) libg2048.so and attach the prototypes."""
     global _lib
     if _lib is None:
-        path = build()
+        # G2048_LIB: load another build of the same library (kernel experiments; tools/ only)
+        path = os.environ.get("G2048_LIB") or build()
         try:
             handle = C.CDLL(path)
         except OSError as e:  # e.g. libcudart missing

@@ -3,8 +3,8 @@ from __future__ import annotations
 
 FLAVOURS = {"penalty": 0, "nopenalty": 1}
 AUX_INIT = 0x000000000000FF01
-N_COUNTERS = 9
-COUNTER_NAMES = ("steps", "valid", "episodes", "score", "maxlvl", "reward_fx", "inserts", "dropped", "lost")
+N_COUNTERS = 16
+COUNTER_NAMES = ("steps", "valid", "episodes", "score", "maxlvl", "reward_fx", "inserts", "dropped", "lost", "retried")
 MODES = {"atomic": 0, "deterministic": 1}
 
 

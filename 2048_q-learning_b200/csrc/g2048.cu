@@ -6,8 +6,8 @@
 //   k_rollout_random  K steps per env with the board in registers, row LUT staged in shared memory by
 //                     one bulk-async (TMA) copy, Philox spawn, in-kernel reset
 //   k_rollout_qlearn  the same loop with epsilon-greedy choose_action and the TD update on the HBM hash
-//                     table fused in (probe loads are the only dependent memory chain; insert and update are
-//                     speculative atomicCAS checked one step later)
+//                     table fused in: a table visit is one load + ONE atomic (a new state is inserted together with
+//                     its first update by a 128-bit CAS), settled one step later; every update is applied
 //   k_qlearn_phase_a / k_q_update_phase_a / k_keys_to_records + k_apply_atomic / CUB radix sort +
 //   k_segment_apply   synchronous batched update, atomic and deterministic modes
 //   k_q_lookup, k_choose_action, k_q_size, k_q_export, k_legal_mask, k_pack, k_unpack, k_onehot,
@@ -48,7 +48,10 @@ constexpr size_t kLutRowBytes = 65536 * sizeof(uint16_t);
 constexpr size_t kLutMergedBytes = 65536;
 constexpr size_t kLutCoreBytes = kLutRowBytes + kLutMergedBytes + 256 * sizeof(uint32_t);  // row | merged | mscore
 constexpr size_t kLutBytes = kLutCoreBytes + kHotDoubles * sizeof(double);               // + hot reward tables
-constexpr int kRolloutThreads = 1024;
+#ifndef G2048_EXP_THREADS
+#define G2048_EXP_THREADS 1024
+#endif
+constexpr int kRolloutThreads = G2048_EXP_THREADS;
 constexpr int kSmallRolloutThreads = 128;   // small batches: LUT through L1, more registers per thread
 constexpr long long kEnvStepSmemLutMinEnvs = 1 << 19;   // g2048_env_step: stage the LUT in shared memory from this batch size on
 
@@ -273,21 +276,78 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
 }
 
 // main.py:91-101 fused.  Per step: Philox -> epsilon-greedy from the carried row of s -> env step ->
-// find-or-insert s' -> q <- q + lr (target - q) on Q[s][a] -> carry (slot, row) of s' as the next s.
+// look s' up -> q <- q + lr (target - q) on Q[s][a] -> carry (slot, row) of s' as the next s.
 //
-// Measured on B200 (tools/membench*.cu, profiles/r01_membench.txt): random loads that miss L2 saturate at ~36 G/s
-// (each moves a 128-byte line), atomicCAS that misses L2 at ~20 G/s, and "load a random 32-byte sector, then write
-// 4 bytes into it" -- exactly one table visit -- at 16.8 G/s.  That, not the 6.5 TB/s streaming peak, bounds a hash
-// table in HBM: ~20 G env-steps/s for this kernel (0.85 table visits per step).  So the kernel issues exactly one
-// load per probe and keeps everything else off the dependent chain:
-//   * lookup = plain 256-bit load(s); an empty slot is claimed with atomicCAS (an L2 hit by then) WITHOUT
-//     waiting for its result: the lane goes on as if the insert succeeded (a new state has a zero row
-//     wherever it lands) and checks the CAS result one step later, re-probing only if another state won the slot;
-//   * the update is ONE atomicCAS from the value this lane read (again an L2 hit, again checked a step later):
-//     it applies q <- q + lr (target - q) atomically, and is skipped (counted in LOST) if another env changed
-//     the same Q value in between -- stale deltas are never summed, so heavily shared early-game states cannot
-//     diverge, and no lane spins on a contended address.  With one env nothing is ever lost: N = 1 is the
-//     reference's sequential order exactly.
+// What bounds it (tools/membench5.cu, profiles/r02_membench.txt): the table lives in 32-64 GiB of HBM, every lookup is
+// an L2 miss, and the memory system charges PER REQUEST, not per byte: ~29 ps for a load that misses (35 G/s) and
+// about as much again for EVERY write-type request (store, RED or CAS alike, even to a sector that is already dirty):
+// load + insert CAS + update CAS = 12.2 G table visits/s, load + ONE write = 17.5 G/s, and neither more threads nor
+// less computing between the requests changes either figure.  So a table visit is cut down to two requests:
+//   * the lookup is plain 256-bit load(s) and writes nothing: a state that is not in the table yet is carried as
+//     `fresh` (slot = the empty slot that ended its probe sequence, zero row);
+//   * one step later the update of Q[s][a] goes out as ONE atomic without waiting for it: a 32-bit CAS on the value
+//     if s is in the table, or -- s fresh -- a 128-bit CAS {0, 0, 0} -> {key, q0, q1} on the first half of the slot
+//     that inserts the state and applies its first update together (a fresh row is zero, so a greedy policy picks
+//     action 0 and the value shares the half with the key; for actions 2, 3 the key is inserted first);
+//   * the result of that atomic is looked at one step later.  A lost race (another env changed the value, inserted
+//     the same state, or took the slot for another state) is settled then by a compare-and-swap loop on the winner's
+//     value, re-probing if need be -- EVERY update is applied (counters[RETRIED] counts the second attempts, LOST stays
+//     0), concurrent updates of one Q value compose like the reference's sequential loop (a contraction towards the
+//     targets), and with one env nothing ever races: N = 1 is the reference's order exactly;
+//   * defaultdict semantics (main.py:16, :41): states that are read but never updated -- the s' of a terminal
+//     transition, the state an env sits in when the launch ends -- are inserted on their own.
+enum { kPendNone = 0, kPendUpd32 = 1, kPendMerged = 2 };
+struct PendingUpdate {
+    u64 key;        // merged: the state being inserted
+    u64 ret_key;    // merged: key found in the slot (0 = the insert went through)
+    u64 ret_q01;    // merged: {q0, q1} found; 32-bit CAS: the value found (low word)
+    u32 slot, assumed;
+    float target;
+    int kind, a;
+    bool patch;     // the env still sits in this state (invalid move): its carried row follows the outcome
+};
+template <class TAB>
+__device__ __forceinline__ void settle_update(const TAB& tab, PendingUpdate& P, float lr, float4& row, u32& slot, Counters& c) {
+    constexpr bool SYS = TAB::kSys;
+    if (P.kind == kPendUpd32) {
+        const u32 old = (u32)P.ret_q01;
+        if (old != P.assumed) {
+            c.retried += 1;
+#ifdef G2048_EXP_NORETRY
+            c.lost += 1;
+            if (P.patch) q_set(row, P.a, __uint_as_float(old));
+#else
+            float nq = q_update_atomic<SYS>(&tab.at(P.slot)->q[P.a], __uint_as_float(old), lr, P.target);
+            if (P.patch) q_set(row, P.a, nq);
+#endif
+        }
+    } else if (P.kind == kPendMerged) {
+        if (P.ret_key == 0) {
+            c.inserts += 1;
+        } else {
+            c.retried += 1;
+            u32 s = P.slot;
+            float start;
+            if (P.ret_key == P.key) {   // another env inserted the same state first: its values are in ret_q01
+                if (P.patch) { row.x = __uint_as_float((u32)P.ret_q01); row.y = __uint_as_float((u32)(P.ret_q01 >> 32)); }
+                start = __uint_as_float(P.a == 0 ? (u32)P.ret_q01 : (u32)(P.ret_q01 >> 32));
+            } else {                    // another state took the slot: find a place for ours now
+                float4 r2;
+                s = table_find<true>(tab, P.key, r2, c.inserts);
+                start = q_at(r2, P.a);
+                if (P.patch) slot = s;
+            }
+            if (s != kNoSlot) {
+                float nq = q_update_atomic<SYS>(&tab.at(s)->q[P.a], start, lr, P.target);
+                if (P.patch) q_set(row, P.a, nq);
+            } else {
+                c.dropped += 1;
+                c.lost += 1;
+            }
+        }
+    }
+    P.kind = kPendNone;
+}
 template <int FLAVOUR, bool SMEM_LUT, class TAB>
 __global__ void __launch_bounds__(SMEM_LUT ? kRolloutThreads : kSmallRolloutThreads, 1)
 k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ TAB table, long long n,
@@ -296,88 +356,101 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_const
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ Slot* shard_base[G2048_MAX_PEERS];
     const auto tab = table.view(shard_base);
+    constexpr bool SYS = decltype(tab)::kSys;
     Lut L = SMEM_LUT ? stage_lut(T, smem) : global_lut(T);
     Counters c;
+#ifdef G2048_EXP_STAGGER
+    __nanosleep((((threadIdx.x >> 5) + 32u * blockIdx.x) * 2654435761u >> 18) & 16383u);
+#endif
+#ifdef G2048_EXP_TIMING
+    u64 t_begin;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#endif
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         Env e;
         env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
         u64 id = id_base + (u64)i;
         float4 row;
+        bool fresh = false;
         u32 slot = table_find<true>(tab, e.board, row, c.inserts);
         c.dropped += (slot == kNoSlot);
-        bool ins_pending = false, term_pending = false, upd_pending = false, upd_patch = false;
-        u64 ins_old = 0, term_old = 0, term_key = 0;   // speculative inserts: of the current state / of a terminal state
-        u32 upd_old = 0, upd_assumed = 0;
-        int upd_a = 0;
+        PendingUpdate P;
+        P.kind = kPendNone;
         for (long long k = 0; k < k_steps; ++k) {
             u64 t = step_base + (u64)k;
             Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
-            // results of the speculative operations of the previous step
-            if (term_pending) {
-                term_pending = false;
-                if (term_old == 0) c.inserts += 1;
-                else if (term_old != term_key) { float4 r2; table_find<true>(tab, term_key, r2, c.inserts); }
-            }
-            if (ins_pending) {
-                ins_pending = false;
-                if (ins_old == 0) c.inserts += 1;
-                else if (ins_old != e.board) {   // another state won the slot: find a place for ours now
-                    float4 r2;
-                    slot = table_find<true>(tab, e.board, r2, c.inserts);
-                    c.dropped += (slot == kNoSlot);
-                }
-            }
-            if (upd_pending) {
-                upd_pending = false;
-                if (upd_old != upd_assumed) {
-                    c.lost += 1;
-                    if (upd_patch) q_set(row, upd_a, __uint_as_float(upd_old));   // s' == s: see the winner's value
-                }
-            }
+#ifdef G2048_EXP_LATESETTLE
+            if (P.kind != kPendNone && P.patch) settle_update(tab, P, lr, row, slot, c);
+#else
+            if (P.kind != kPendNone) settle_update(tab, P, lr, row, slot, c);   // the atomic issued one step ago
+#endif
             int a = choose_action(row, x, eps_thresh);
-            u64 s_board = e.board;
+            const u64 s_board = e.board;
             StepOut o;
             philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
             c.add(o);
             float4 row2 = row;
             u32 slot2 = slot;
+            bool fresh2 = fresh;
             const bool same = (e.board == s_board);   // an invalid move leaves s' == s
-            if (!same) {
-                if (o.done) {   // a terminal s': its insert is checked through its own pair, the env moves on at once
-                    term_key = e.board;
-                    slot2 = table_find_spec(tab, e.board, row2, term_pending, term_old, c.dropped);
-                } else {
-                    slot2 = table_find_spec(tab, e.board, row2, ins_pending, ins_old, c.dropped);
-                }
+            if (!same) slot2 = table_probe(tab, e.board, row2, fresh2, c.dropped);
+#ifdef G2048_EXP_LATESETTLE
+            if (P.kind != kPendNone) settle_update(tab, P, lr, row, slot, c);
+#endif
+            if (fresh && a >= 2 && slot != kNoSlot) {   // key and value in different halves of the slot: insert first
+                slot = insert_at(tab, slot, s_board, c.inserts, c.dropped);
+                fresh = false;
+                if (same) { slot2 = slot; fresh2 = false; }
             }
             if (slot != kNoSlot) {
-                float q = q_at(row, a);
-                float nq = td_apply(q, lr, td_target(gamma, (float)o.reward, max4(row2), o.done));
-                upd_assumed = __float_as_uint(q);
-                upd_old = cas32<decltype(tab)::kSys>(reinterpret_cast<u32*>(&tab.at(slot)->q[a]), upd_assumed, __float_as_uint(nq));
-                upd_pending = true; upd_patch = same && !o.done; upd_a = a;
-                if (same) q_set(row2, a, nq);
+                const float q = q_at(row, a);
+                const float target = td_target(gamma, (float)o.reward, max4(row2), o.done);
+                const float nq = td_apply(q, lr, target);
+                Slot* sp = tab.at(slot);
+                P.slot = slot; P.a = a; P.target = target; P.patch = same && !o.done;
+                if (!fresh) {
+                    P.assumed = __float_as_uint(q);
+                    P.ret_q01 = cas32<SYS>(reinterpret_cast<u32*>(&sp->q[a]), P.assumed, __float_as_uint(nq));
+                    P.kind = kPendUpd32;
+                } else {
+                    P.key = s_board;
+                    cas_w0<SYS>(sp, 0ull, 0ull, s_board, (u64)__float_as_uint(nq) << (32 * a), P.ret_key, P.ret_q01);
+                    P.kind = kPendMerged;
+                }
+                if (same) { q_set(row2, a, nq); fresh2 = false; }
+            } else {
+                c.lost += 1;   // the state has no slot (table full): the update cannot be stored
             }
             row = row2;
             slot = slot2;
-            if (o.done) {   // state = env.reset() is read at once (main.py:81-82, :92), speculatively as well
+            fresh = fresh2;
+            if (o.done) {
+                // update_q_value read Q[next_state] (main.py:41): the terminal state is in the table from now on;
+                // state = env.reset() is looked up at once (main.py:81-82, :92)
+                if (fresh && slot != kNoSlot) insert_at(tab, slot, e.board, c.inserts, c.dropped);
                 philox_autoreset(e, seed, id, t);
-                slot = table_find_spec(tab, e.board, row, ins_pending, ins_old, c.dropped);
+                slot = table_probe(tab, e.board, row, fresh, c.dropped);
             }
         }
-        if (term_pending) {
-            if (term_old == 0) c.inserts += 1;
-            else if (term_old != term_key) { float4 r2; table_find<true>(tab, term_key, r2, c.inserts); }
-        }
-        if (ins_pending) {
-            if (ins_old == 0) c.inserts += 1;
-            else if (ins_old != e.board) { float4 r2; table_find<true>(tab, e.board, r2, c.inserts); }
-        }
-        if (upd_pending && upd_old != upd_assumed) c.lost += 1;
+        if (P.kind != kPendNone) settle_update(tab, P, lr, row, slot, c);
+        if (fresh && slot != kNoSlot) insert_at(tab, slot, e.board, c.inserts, c.dropped);   // the launch ends: reading a state creates it
         boards[i] = e.board;
         if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
         if (score) score[i] = e.score;
     }
+#ifdef G2048_EXP_TIMING
+    {
+        u64 t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        long long dt = (long long)(t_end - t_begin);
+        if ((threadIdx.x & 31) == 0 && counters) {
+            atomicMax(counters + 10, dt);
+            atomicAdd((unsigned long long*)(counters + 11), (unsigned long long)dt);
+            atomicMin(counters + 12, dt);
+            atomicAdd((unsigned long long*)(counters + 13), 1ull);
+        }
+    }
+#endif
     flush_counters(c, counters);
 }
 

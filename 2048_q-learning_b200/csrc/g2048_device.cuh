@@ -7,6 +7,7 @@
 //   Deep_QLearning/environment/Game2048_nopenalty_env.py + mainDQL_CNN_step2.py:163-237
 //   QLearningBase/Agent/main.py:34-43                choose_action / update_q_value
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -359,14 +360,19 @@ __device__ __forceinline__ void philox_autoreset(Env& e, u64 seed, u64 env_id, u
 }
 
 // ------------------------------------------------------------------ HBM hash Q-table
-// 32-byte slots (one DRAM sector): key, meta (unused), float q[4].  key 0 = empty (an all-empty
-// board never occurs).  Open addressing, linear probing, capacity a power of two.
+// 32-byte slots (one DRAM sector) = two 16-byte halves:  W0 = {key, q[0], q[1]}   W1 = {q[2], q[3], meta (unused)}.
+// key 0 = empty (an all-empty board never occurs).  Open addressing, linear probing, capacity a power of two.
+// The key shares W0 with two Q values so that a NEW state and its first update can be written by ONE 128-bit
+// compare-and-swap (see k_rollout_qlearn): on B200 every write-type request to the table costs about as much as the
+// line fill of the lookup itself, whatever it writes (tools/membench5.cu), so one request less per new state is worth
+// a third of the table time.
 struct __align__(32) Slot {
     u64 key;
-    u64 meta;
     float q[4];
+    u64 meta;
 };
 static_assert(sizeof(Slot) == G2048_QTABLE_SLOT_BYTES, "slot size");
+static_assert(offsetof(Slot, q) == 8 && offsetof(Slot, meta) == 24, "slot layout");
 
 __device__ __forceinline__ u64 mix64(u64 x) {  // splitmix64 finaliser
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
@@ -419,15 +425,32 @@ template <bool SYS> __device__ __forceinline__ u32 cas32(u32* p, u32 cmp, u32 va
     return SYS ? atomicCAS_system(p, cmp, val) : atomicCAS(p, cmp, val);
 }
 // one 256-bit load of a whole slot, coherent at L2 (L1 is bypassed: other SMs -- or, system scope, other GPUs --
-// update rows with atomics)
+// update rows with atomics).  .L2::64B: a miss fills 64 bytes instead of the default whole 128-byte line (ncu:
+// 2.0 instead of 3.98 DRAM sectors per random load, same request rate -- tools/membench6.cu).
 template <bool SYS = false>
 __device__ __forceinline__ void load_slot(const Slot* s, u64& key, float4& q) {
-    u64 k, m, q01, q23;
-    if (SYS) asm volatile("ld.relaxed.sys.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(m), "=l"(q01), "=l"(q23) : "l"(s));
-    else asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(m), "=l"(q01), "=l"(q23) : "l"(s));
+    u64 k, q01, q23, m;
+    if (SYS) asm volatile("ld.relaxed.sys.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(q01), "=l"(q23), "=l"(m) : "l"(s));
+#ifdef G2048_EXP_CGLOAD
+    else asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(q01), "=l"(q23), "=l"(m) : "l"(s));
+#else
+    else asm volatile("ld.relaxed.gpu.global.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(q01), "=l"(q23), "=l"(m) : "l"(s));
+#endif
     key = k;
     q.x = __uint_as_float((u32)q01); q.y = __uint_as_float((u32)(q01 >> 32));
     q.z = __uint_as_float((u32)q23); q.w = __uint_as_float((u32)(q23 >> 32));
+}
+// 128-bit compare-and-swap on the first half of a slot {key, q[0] | q[1] << 32}; returns what was there
+template <bool SYS>
+__device__ __forceinline__ void cas_w0(Slot* s, u64 cmp_key, u64 cmp_q01, u64 new_key, u64 new_q01, u64& old_key, u64& old_q01) {
+    if (SYS)
+        asm volatile("{\n\t.reg .b128 c, n, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\t"
+                     "atom.relaxed.sys.global.cas.b128 d, [%6], c, n;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                     : "=l"(old_key), "=l"(old_q01) : "l"(cmp_key), "l"(cmp_q01), "l"(new_key), "l"(new_q01), "l"(s) : "memory");
+    else
+        asm volatile("{\n\t.reg .b128 c, n, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\t"
+                     "atom.relaxed.gpu.global.cas.b128 d, [%6], c, n;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                     : "=l"(old_key), "=l"(old_q01) : "l"(cmp_key), "l"(cmp_q01), "l"(new_key), "l"(new_q01), "l"(s) : "memory");
 }
 // Linear probing by single 32-byte slots.  (A two-slot 64-byte bucket loaded as a pair was measured SLOWER --
 // 10.7 vs 14.2 G steps/s: what saturates is the number of L2-miss sector requests, ~36 G/s on B200 whatever the
@@ -456,25 +479,35 @@ template <bool INSERT>
 __device__ __forceinline__ u32 table_find(Slot* tab, u64 mask, u64 key, float4& q, u32& inserted) {
     return table_find<INSERT>(LocalTable{tab, mask}, key, q, inserted);
 }
-// Speculative find-or-insert for the fused rollout: probe with plain loads; an empty slot is claimed with ONE
-// atomicCAS (issued after the probe loop, so its destination register is not touched again) whose result
-// (ins_old) the caller inspects one step later -- the row of a new state is zero wherever it finally lands, only
-// the slot index may need a re-probe (ins_old neither 0 nor key).
+// Lookup WITHOUT insert for the fused rollout: returns the slot of `key` and its row, or -- fresh = true -- the
+// empty slot that ends its probe sequence with a zero row; nothing is written.  The fused kernel inserts a fresh
+// state together with its first update (one 128-bit CAS on {key, q[0], q[1]}), or on its own when no update follows.
 template <class TAB>
-__device__ __forceinline__ u32 table_find_spec(const TAB& tab, u64 key, float4& q, bool& ins_pending, u64& ins_old,
-                                               u32& dropped) {
+__device__ __forceinline__ u32 table_probe(const TAB& tab, u64 key, float4& q, bool& fresh, u32& dropped) {
     u64 h = mix64(key) & tab.mask, k = 1;
     int p = 0;
     for (; p < kMaxProbe; ++p, h = (h + 1) & tab.mask) {
         load_slot<TAB::kSysLoad>(tab.at(h), k, q);
         if (k == key || k == 0) break;
     }
+    fresh = false;
     if (k == key) return (u32)h;
     q = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p == kMaxProbe) { dropped += 1; return kNoSlot; }
-    ins_old = cas64<TAB::kSys>(&tab.at(h)->key, 0ull, key);
-    ins_pending = true;
+    fresh = true;
     return (u32)h;
+}
+// Insert `key` (zero row) at `slot`, the empty slot a table_probe returned; if another state took the slot meanwhile,
+// find-or-insert from the home slot again.  Returns the slot that holds the key now (kNoSlot: table full).
+template <class TAB>
+__device__ __forceinline__ u32 insert_at(const TAB& tab, u32 slot, u64 key, u32& inserted, u32& dropped) {
+    u64 old = cas64<TAB::kSys>(&tab.at(slot)->key, 0ull, key);
+    if (old == 0) { inserted += 1; return slot; }
+    if (old == key) return slot;
+    float4 r;
+    u32 s = table_find<true>(tab, key, r, inserted);
+    dropped += (s == kNoSlot);
+    return s;
 }
 __device__ __forceinline__ float q_at(const float4& q, int a) { return a == 0 ? q.x : a == 1 ? q.y : a == 2 ? q.z : q.w; }
 __device__ __forceinline__ void q_set(float4& q, int a, float v) {
@@ -510,11 +543,12 @@ __device__ __forceinline__ ulonglong2 pack_record(u64 key, int a, float target) 
 // updates of the same (state, action) compose like the reference's sequential loop (a contraction
 // towards the targets) instead of summing stale deltas, which diverges once the number of
 // simultaneous updaters exceeds 2 / lr.  `guess` is the caller's last view of the value.
+template <bool SYS = false>
 __device__ __forceinline__ float q_update_atomic(float* addr, float guess, float lr, float target) {
     u32 assumed = __float_as_uint(guess);
     while (true) {
         float nq = td_apply(__uint_as_float(assumed), lr, target);
-        u32 old = atomicCAS(reinterpret_cast<u32*>(addr), assumed, __float_as_uint(nq));
+        u32 old = cas32<SYS>(reinterpret_cast<u32*>(addr), assumed, __float_as_uint(nq));
         if (old == assumed) return nq;
         assumed = old;
     }
@@ -524,7 +558,7 @@ __device__ __forceinline__ float q_update_atomic(float* addr, float guess, float
 // Per-thread partial sums (32-bit where a launch cannot overflow them), reduced per warp and added to the
 // caller's int64 counters with one atomic per warp and counter.
 struct Counters {
-    u32 steps = 0, valid = 0, episodes = 0, inserts = 0, dropped = 0, lost = 0;
+    u32 steps = 0, valid = 0, episodes = 0, inserts = 0, dropped = 0, lost = 0, retried = 0;
     int maxlvl = 0;
     long long score = 0, reward_fx = 0;
     __device__ __forceinline__ void add(const StepOut& o) {
@@ -540,14 +574,14 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 }
 __device__ __forceinline__ void flush_counters(const Counters& c, long long* out) {
     if (!out) return;
-    long long v[8] = {c.steps, c.valid, c.episodes, c.score, c.reward_fx, c.inserts, c.dropped, c.lost};
-    const int idx[8] = {G2048_C_STEPS, G2048_C_VALID, G2048_C_EPISODES, G2048_C_SCORE, G2048_C_REWARD_FX,
-                        G2048_C_INSERTS, G2048_C_DROPPED, G2048_C_LOST};
+    long long v[9] = {c.steps, c.valid, c.episodes, c.score, c.reward_fx, c.inserts, c.dropped, c.lost, c.retried};
+    const int idx[9] = {G2048_C_STEPS, G2048_C_VALID, G2048_C_EPISODES, G2048_C_SCORE, G2048_C_REWARD_FX,
+                        G2048_C_INSERTS, G2048_C_DROPPED, G2048_C_LOST, G2048_C_RETRIED};
     int mx = c.maxlvl;
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, s));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 9; ++i) {
         long long s = warp_sum(v[i]);
         if ((threadIdx.x & 31) == 0 && s) atomicAdd((unsigned long long*)(out + idx[i]), (unsigned long long)s);
     }

@@ -373,7 +373,7 @@ def main():
         assert L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, SEED, 0, base, stream) == 0
         return b, a, s
 
-    counters = torch.zeros(9, dtype=torch.int64, device=dev)
+    counters = torch.zeros(16, dtype=torch.int64, device=dev)
 
     # ---- pre-warm: ramp clocks with random-policy rollouts (not counted) --------------------------------
     b, a, s = device_envs()
@@ -418,14 +418,15 @@ def main():
     pst = pst.tolist()
     table_stats = {"mean_probe_length": 1 + pst[1] / max(pst[0], 1), "max_probe_length": 1 + pst[2],
                    "inserts_per_sec": world * float(c[6]) / launches * args.steps / elapsed_s, "capacity_slots": cap, "table_GiB": cap * 32 / 2**30, "states": int(c[6]),
-                   "load_factor_end": int(c[6]) / cap, "dropped": int(c[7]), "lost_updates": int(c[8]),
+                   "load_factor_end": int(c[6]) / cap, "dropped": int(c[7]), "lost_updates": int(c[8]), "retried_updates": int(c[9]),
+                   "retried_update_fraction": int(c[9]) / max(int(c[0]), 1),
                    "lost_update_fraction": int(c[8]) / max(int(c[0]), 1),
                    "new_state_fraction": int(c[6]) / max(int(c[0]), 1)}
 
     # ---- arm 2: end to end through the host-buffer C-ABI call (pinned host memory) --------------------------
     assert L.g2048_ctx_qtable_clear(ctx) == 0
     (hb, ha, hs), pins = fresh_host_envs(L, ctx, n, base, pinned=True)
-    hc = np.zeros(9, np.int64)
+    hc = np.zeros(16, np.int64)
 
     def e2e_step(i):
         rc = L.g2048_ctx_rollout_qlearn(ctx, vp(hb), vp(ha), vp(hs), n, k, 0, LR, GAMMA, EPS, SEED, i * k, base, vp(hc))
@@ -692,7 +693,7 @@ def shared_table_measurement(torch, dist, g2048, dev, rank, world, n, max_over_r
         shared = gdist.SharedQTable(g2048.lib(), dev, slots)
     else:
         shared = gdist.SharedQTable(g2048.lib(), dev, slots, shards=[torch.zeros(slots * 4, dtype=torch.int64, device=dev)])
-    tot = torch.zeros(9, dtype=torch.int64, device=dev)
+    tot = torch.zeros(16, dtype=torch.int64, device=dev)
     for _ in range(warm):
         tot += shared.rollout(env, k, LR, GAMMA, EPS)      # (also loads torch's add kernel outside the timed region)
     tot.zero_()
@@ -746,7 +747,7 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
     b = torch.zeros(n, dtype=torch.int64, device=dev)
     a = torch.full((n,), 0x000000000000FF01, dtype=torch.int64, device=dev)
     s = torch.zeros(n, dtype=torch.int32, device=dev)
-    cnt = torch.zeros(9, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(16, dtype=torch.int64, device=dev)
     L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, SEED, 0, base, stream)
     # (a) fused random-policy rollout, 64 steps per launch
     for flavour, name in ((0, "penalty"), (1, "nopenalty")):
@@ -810,7 +811,7 @@ def side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak):
     ae = torch.full((n,), 0x000000000000FF01, dtype=torch.int64, device=dev)
     se = torch.zeros(n, dtype=torch.int32, device=dev)
     L.g2048_env_reset(be.data_ptr(), se.data_ptr(), None, None, n, SEED, 0, base, stream)
-    ce = torch.zeros(9, dtype=torch.int64, device=dev)
+    ce = torch.zeros(16, dtype=torch.int64, device=dev)
     ke, launch_no = 16, [0]
 
     def rollout_095():

@@ -36,7 +36,7 @@
 #define G2048_API __attribute__((visibility("default")))
 #endif
 
-#define G2048_VERSION 100
+#define G2048_VERSION 200
 
 /* error codes (< 0) */
 #define G2048_ERR_ARG (-1)      /* bad argument (null pointer, bad flavour/mode, capacity not 2^k ...) */
@@ -73,8 +73,12 @@
 #define G2048_C_REWARD_FX 5  /* sum of trunc(reward * 2^20): order-independent checksum of the rewards */
 #define G2048_C_INSERTS 6    /* new Q-table states */
 #define G2048_C_DROPPED 7    /* lookups that hit the probe limit (table too full) */
-#define G2048_C_LOST 8       /* fused rollout: updates skipped because another env changed the same Q value first */
-#define G2048_N_COUNTERS 9
+#define G2048_C_LOST 8       /* Q-updates that were NOT applied: the state had no slot (table full).  The fused rollout
+                                applies every other update -- a compare-and-swap that loses a race is re-issued on the
+                                winner's value -- so this stays 0 unless DROPPED is non-zero */
+#define G2048_C_RETRIED 9    /* fused rollout: updates whose first compare-and-swap lost a race against another env and
+                                were re-applied (a contention measure; always 0 with one env) */
+#define G2048_N_COUNTERS 16  /* 10-15 reserved (zero) */
 
 /* Q-learning modes */
 #define G2048_MODE_ATOMIC 0         /* q <- q + lr (target - q) as an atomic CAS loop (order among duplicates unspecified);
@@ -82,7 +86,7 @@
                                        of records at once costs one L2 round trip per record: use DETERMINISTIC there */
 #define G2048_MODE_DETERMINISTIC 1  /* sort by (state, action), duplicates applied one after another in ascending env order */
 
-#define G2048_QTABLE_SLOT_BYTES 32  /* key u64 | meta u64 | float q[4] */
+#define G2048_QTABLE_SLOT_BYTES 32  /* key u64 | float q[4] | meta u64 (unused) */
 
 /* one-hot dtypes */
 #define G2048_DTYPE_F32 0

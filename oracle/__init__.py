@@ -21,7 +21,7 @@ _SRC = os.path.join(_HERE, "g2048_oracle.c")
 FLAVOUR_PENALTY, FLAVOUR_NOPENALTY = 0, 1
 AUX_INIT = 0x000000000000FF01
 PEN_SAT = 25
-N_COUNTERS = 9
+N_COUNTERS = 16
 
 
 def build(force: bool = False) -> str:

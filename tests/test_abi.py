@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(handle, s)]
     assert not missing, missing
     assert set(_lib._SIG) == set(declared), set(_lib._SIG) ^ set(declared)
-    assert handle.g2048_version() == 100
+    assert handle.g2048_version() == 200
 
 
 def test_only_the_c_abi_is_exported():

@@ -34,7 +34,7 @@ def test_synchronous_deterministic_qlearning_matches_oracle(g, flavour, code):
     cb = np_boards(env.boards).copy()
     ca, cs = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
     tab = oracle.QTable(1 << 20, f32=True)
-    total = np.zeros(9, np.int64)
+    total = np.zeros(16, np.int64)
     env.counters.zero_()
     for t in range(steps):
         agent.step_sync(env, mode="deterministic")

@@ -37,7 +37,7 @@ def envs(n, seed=3, base=0):
 
 def test_empty_batches_are_no_ops(L, ctx):
     z8, z4, z1 = np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.uint8)
-    c = np.zeros(9, np.int64)
+    c = np.zeros(16, np.int64)
     assert L.g2048_ctx_env_step(ctx, vp(z8), vp(z8), vp(z4), vp(z1), None, None, None, None, None, 0, 0, 1, 2, 3) == 0
     assert L.g2048_ctx_env_reset(ctx, vp(z8), None, None, None, 0, 1, 2, 3) == 0
     assert L.g2048_ctx_rollout_random(ctx, vp(z8), vp(z8), vp(z4), 0, 10, 0, 1, 2, 3, vp(c)) == 0
@@ -58,7 +58,7 @@ def test_ragged_batch_sizes(L, ctx, n, flavour):
     seed, base, t0, k = 5, (1 << 40) + 12345, (1 << 33) + 7, 37
     b, a, s = envs(n, seed, base)
     cb, ca, cs = b.copy(), a.copy(), s.copy()
-    c = np.zeros(9, np.int64)
+    c = np.zeros(16, np.int64)
     assert L.g2048_ctx_rollout_random(ctx, vp(b), vp(a), vp(s), n, k, flavour, seed, t0, base, vp(c)) == 0
     cc = oracle.rollout_random(cb, ca, cs, k, flavour, seed, t0, base, threads=4)
     assert np.array_equal(b, cb) and np.array_equal(s, cs) and np.array_equal(c, cc)
@@ -129,7 +129,7 @@ def test_table_that_runs_full_drops_and_survives(L):
     try:
         n = 20000
         b, a, s = envs(n)
-        c = np.zeros(9, np.int64)
+        c = np.zeros(16, np.int64)
         assert L.g2048_ctx_rollout_qlearn(small, vp(b), vp(a), vp(s), n, 40, 0, 0.1, 0.99, 0.5, 1, 0, 0, vp(c)) == 0
         assert c[0] == n * 40 and c[7] > 0
         size = L.g2048_ctx_qtable_size(small)

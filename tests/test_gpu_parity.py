@@ -149,7 +149,7 @@ def test_rollout_random_matches_oracle(L, ctx, flavour, n, k):
     seed, base, t0 = 99 + n, 12345, 7
     gb, ga, gs = fresh_envs(n, seed, 0, base)
     cb, ca, cs = gb.copy(), ga.copy(), gs.copy()
-    gc = np.zeros(9, np.int64)
+    gc = np.zeros(16, np.int64)
     ok(L, L.g2048_ctx_rollout_random(ctx, vp(gb), vp(ga), vp(gs), n, k, flavour, seed, t0, base, vp(gc)))
     cc = oracle.rollout_random(cb, ca, cs, k, flavour, seed, t0, base, threads=8)
     assert np.array_equal(gb, cb) and np.array_equal(gs, cs)
@@ -163,12 +163,12 @@ def test_rollout_random_is_sharding_invariant_at_1M_envs(L, ctx):
     """BASELINE config 3 size: 2^20 envs; one launch == two half-size launches with shifted env ids."""
     n, k, seed = 1 << 20, 48, 0x2048
     b, a, s = fresh_envs(n, seed)
-    b1, a1, s1, c1 = b.copy(), a.copy(), s.copy(), np.zeros(9, np.int64)
+    b1, a1, s1, c1 = b.copy(), a.copy(), s.copy(), np.zeros(16, np.int64)
     ok(L, L.g2048_ctx_rollout_random(ctx, vp(b1), vp(a1), vp(s1), n, k, 0, seed, 0, 0, vp(c1)))
     h = n // 2
-    c2 = np.zeros(9, np.int64)
+    c2 = np.zeros(16, np.int64)
     for lo in (0, h):
-        bb, aa, ss, cc = b[lo:lo + h].copy(), a[lo:lo + h].copy(), s[lo:lo + h].copy(), np.zeros(9, np.int64)
+        bb, aa, ss, cc = b[lo:lo + h].copy(), a[lo:lo + h].copy(), s[lo:lo + h].copy(), np.zeros(16, np.int64)
         ok(L, L.g2048_ctx_rollout_random(ctx, vp(bb), vp(aa), vp(ss), h, k, 0, seed, 0, lo, vp(cc)))
         assert np.array_equal(bb, b1[lo:lo + h]) and np.array_equal(aa, a1[lo:lo + h]) and np.array_equal(ss, s1[lo:lo + h])
         c2 += cc
@@ -202,10 +202,10 @@ def test_rollout_random_8M_envs_as_one_launch_or_eight_shards(L):
             return b, a, s
         b1, a1, s1 = fresh()
         start = b1[n - h:n - h + 4096].cpu().numpy().view(np.uint64).copy()
-        c1 = torch.zeros(9, dtype=torch.int64, device="cuda")
+        c1 = torch.zeros(16, dtype=torch.int64, device="cuda")
         ok(L, L.g2048_rollout_random(b1.data_ptr(), a1.data_ptr(), s1.data_ptr(), n, k, flavour, seed, 0, 0, c1.data_ptr(), st))
         b2, a2, s2 = fresh()
-        c2 = torch.zeros(9, dtype=torch.int64, device="cuda")
+        c2 = torch.zeros(16, dtype=torch.int64, device="cuda")
         for r in range(G):
             lo = r * h
             ok(L, L.g2048_rollout_random(b2[lo:].data_ptr(), a2[lo:].data_ptr(), s2[lo:].data_ptr(), h, k, flavour, seed, 0,
@@ -344,7 +344,7 @@ def test_rollout_qlearn_single_env_is_the_reference_order(L, ctx):
         ok(L, L.g2048_ctx_qtable_clear(ctx))
         gb, ga, gs = fresh_envs(1, seed, 0, base)
         cb, ca, cs = gb.copy(), ga.copy(), gs.copy()
-        gc = np.zeros(9, np.int64)
+        gc = np.zeros(16, np.int64)
         tab = oracle.QTable(1 << 15, f32=True)
         for part in range(2):   # two launches: the carried state must survive the boundary
             ok(L, L.g2048_ctx_rollout_qlearn(ctx, vp(gb), vp(ga), vp(gs), 1, k, flavour, 0.1, 0.99, eps, seed, part * k,
@@ -367,7 +367,7 @@ def test_rollout_qlearn_1M_envs_properties(L, ctx):
     assert big, L.g2048_last_error()
     try:
         b, a, s = fresh_envs(n, seed)
-        c = np.zeros(9, np.int64)
+        c = np.zeros(16, np.int64)
         ok(L, L.g2048_ctx_rollout_qlearn(big, vp(b), vp(a), vp(s), n, k, 0, 0.1, 0.99, 0.1, seed, 0, 0, vp(c)))
         assert c[0] == n * k and c[7] == 0
         size = L.g2048_ctx_qtable_size(big)
@@ -391,7 +391,7 @@ def test_philox_mode_matches_the_reference_statistics(L, ctx):
     n, k = 1 << 16, 8000   # ~55 episodes per env: the unfinished last episode biases steps/episodes by < 1 %
     for flavour, length, invalid, score in ((0, 140.8, 0.161, 1088.0), (1, 131.4, 0.135, 1002.0)):
         b, a, s = fresh_envs(n, seed=77 + flavour)
-        c = np.zeros(9, np.int64)
+        c = np.zeros(16, np.int64)
         ok(L, L.g2048_ctx_rollout_random(ctx, vp(b), vp(a), vp(s), n, k, flavour, 77 + flavour, 0, 0, vp(c)))
         steps, valid, episodes, total_score = (float(x) for x in c[:4])
         assert abs(steps / episodes - length) < 0.04 * length          # reference sample: +-1.4 (1 sigma of the mean)
