@@ -49,9 +49,10 @@ constexpr size_t kLutMergedBytes = 65536;
 constexpr size_t kLutCoreBytes = kLutRowBytes + kLutMergedBytes + 256 * sizeof(uint32_t);  // row | merged | mscore
 constexpr size_t kLutBytes = kLutCoreBytes + kHotDoubles * sizeof(double);               // + hot reward tables
 #ifndef G2048_EXP_THREADS
-#define G2048_EXP_THREADS 1024
+#define G2048_EXP_THREADS 768
 #endif
-constexpr int kRolloutThreads = G2048_EXP_THREADS;
+constexpr int kRolloutThreads = 1024;
+constexpr int kQlearnThreads = G2048_EXP_THREADS;   // fused Q-learning rollout
 constexpr int kSmallRolloutThreads = 128;   // small batches: LUT through L1, more registers per thread
 constexpr long long kEnvStepSmemLutMinEnvs = 1 << 19;   // g2048_env_step: stage the LUT in shared memory from this batch size on
 
@@ -60,7 +61,15 @@ struct DeviceState {
     Tables tables{};
     void* lut = nullptr;      // kLutBytes, 128-byte aligned
     int sm_count = 0;
+    unsigned long long* queue = nullptr;   // kQueueSlots env-queue heads of the fused Q-learning rollout, one per launch in flight
+    unsigned queue_next = 0;
+    // deferred-update lists of the fused Q-learning rollout (+ the sort buffers that apply them): a small ring, so that
+    // launches on different streams do not share one; grown on demand
+    struct DeferSet { void* buf = nullptr; size_t bytes = 0; } defer[4];
+    unsigned defer_next = 0;
 };
+constexpr unsigned kQueueSlots = 256;
+constexpr int64_t kDeferMinEnvs = 16384;   // fused rollouts of fewer envs settle lost races in place (no list)
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
 
@@ -281,110 +290,157 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
 // What bounds it (tools/membench5.cu, profiles/r02_membench.txt): the table lives in 32-64 GiB of HBM, every lookup is
 // an L2 miss, and the memory system charges PER REQUEST, not per byte: ~29 ps for a load that misses (35 G/s) and
 // about as much again for EVERY write-type request (store, RED or CAS alike, even to a sector that is already dirty):
-// load + insert CAS + update CAS = 12.2 G table visits/s, load + ONE write = 17.5 G/s, and neither more threads nor
-// less computing between the requests changes either figure.  So a table visit is cut down to two requests:
+// load + insert CAS + update CAS = 12.2 G table visits/s, load + ONE write = 17.5 G/s.  With two requests per visit
+// the kernel is bound by round trips instead (1024 envs in flight per SM), so nothing is waited for where it is issued:
 //   * the lookup is plain 256-bit load(s) and writes nothing: a state that is not in the table yet is carried as
 //     `fresh` (slot = the empty slot that ended its probe sequence, zero row);
-//   * one step later the update of Q[s][a] goes out as ONE atomic without waiting for it: a 32-bit CAS on the value
-//     if s is in the table, or -- s fresh -- a 128-bit CAS {0, 0, 0} -> {key, q0, q1} on the first half of the slot
-//     that inserts the state and applies its first update together (a fresh row is zero, so a greedy policy picks
-//     action 0 and the value shares the half with the key; for actions 2, 3 the key is inserted first);
-//   * the result of that atomic is looked at one step later.  A lost race (another env changed the value, inserted
-//     the same state, or took the slot for another state) is settled then by a compare-and-swap loop on the winner's
-//     value, re-probing if need be -- EVERY update is applied (counters[RETRIED] counts the second attempts, LOST stays
-//     0), concurrent updates of one Q value compose like the reference's sequential loop (a contraction towards the
-//     targets), and with one env nothing ever races: N = 1 is the reference's order exactly;
+//   * one step later the update of Q[s][a] goes out as ONE atomic: a 32-bit CAS on the value if s is in the table, or
+//     -- s fresh -- a 128-bit CAS {0, 0, 0} -> {key, q0, q1} on the first half of the slot that inserts the state and
+//     applies its first update together (a fresh row is zero, so a greedy policy picks action 0 and the value shares
+//     the half with the key; for actions 2, 3 the key is inserted by a 64-bit CAS and the value follows);
+//   * the result of that atomic is looked at one step later, after the next lookup's wait, when it has long arrived.
+//     A lost race (another env changed the value or inserted the same state first) is NOT retried in place: thousands
+//     of envs leave the same few start states every step, and a compare-and-swap loop serialises at one success per
+//     round trip per address, slower than those updates arrive (measured: 2.6 ms per launch instead of 1.0).  The
+//     update is appended to a list as (slot * 4 + action, target) and g2048_rollout_qlearn applies the list after the
+//     rollout: sorted by address, every run of records one after another (k_segment_apply).  EVERY update is applied
+//     exactly once (counters[RETRIED] counts the deferred ones, LOST stays 0), updates of one Q value compose like the
+//     reference's sequential loop (a contraction towards the targets);
+//   * small launches (no list: D.count == NULL) settle everything in place with compare-and-swap loops; with one env
+//     nothing ever races, and N = 1 is the reference's sequential order exactly;
 //   * defaultdict semantics (main.py:16, :41): states that are read but never updated -- the s' of a terminal
-//     transition, the state an env sits in when the launch ends -- are inserted on their own.
-enum { kPendNone = 0, kPendUpd32 = 1, kPendMerged = 2 };
+//     transition, the state an env sits in when the launch ends -- are inserted on their own;
+//   * warps take their 32 envs at a time from a queue (one atomicAdd per warp and rollout), so a warp that met long
+//     probe sequences plays fewer envs instead of holding the whole grid up.
+struct Deferred {
+    u64* key;                      // [cap] slot * 4 + action; all ones = unused
+    float* target;                 // [cap]
+    unsigned long long* count;     // appended so far (may exceed cap: the excess was applied in place); NULL = no list
+    unsigned long long cap;
+};
+enum { kPendNone = 0, kPendUpd32 = 1, kPendMerged = 2, kPendInsert = 3 };
 struct PendingUpdate {
-    u64 key;        // merged: the state being inserted
-    u64 ret_key;    // merged: key found in the slot (0 = the insert went through)
+    u64 key;        // merged / insert: the state being inserted
+    u64 ret_key;    // merged / insert: key found in the slot (0 = the insert went through)
     u64 ret_q01;    // merged: {q0, q1} found; 32-bit CAS: the value found (low word)
     u32 slot, assumed;
     float target;
     int kind, a;
-    bool patch;     // the env still sits in this state (invalid move): its carried row follows the outcome
 };
+// An update that could not go out as its step's single atomic: q <- q + lr (target - q) on Q[slot][a], `seen` = the
+// last value seen there.
+struct LateUpdate {
+    bool pending = false;
+    u32 slot = 0;
+    int a = 0;
+    float target = 0.f, seen = 0.f;
+};
+// Look at the result of the update atomic issued one step ago; what is left to do comes back in `late`.
+// `cur_slot` follows if the state the env still sits in had to move to another slot.
 template <class TAB>
-__device__ __forceinline__ void settle_update(const TAB& tab, PendingUpdate& P, float lr, float4& row, u32& slot, Counters& c) {
-    constexpr bool SYS = TAB::kSys;
+__device__ __forceinline__ void settle_update(const TAB& tab, PendingUpdate& P, u64 cur_key, u32& cur_slot, Counters& c,
+                                              LateUpdate& late) {
     if (P.kind == kPendUpd32) {
-        const u32 old = (u32)P.ret_q01;
-        if (old != P.assumed) {
+        if ((u32)P.ret_q01 != P.assumed) {       // another env changed the value first
             c.retried += 1;
-#ifdef G2048_EXP_NORETRY
-            c.lost += 1;
-            if (P.patch) q_set(row, P.a, __uint_as_float(old));
-#else
-            float nq = q_update_atomic<SYS>(&tab.at(P.slot)->q[P.a], __uint_as_float(old), lr, P.target);
-            if (P.patch) q_set(row, P.a, nq);
-#endif
+            late.pending = true; late.slot = P.slot; late.a = P.a; late.target = P.target;
+            late.seen = __uint_as_float((u32)P.ret_q01);
         }
-    } else if (P.kind == kPendMerged) {
+    } else if (P.kind != kPendNone) {            // merged insert + update, or insert alone (the update still to come)
+        u32 s = P.slot;
+        float seen = 0.f;
+        bool todo = (P.kind == kPendInsert);
         if (P.ret_key == 0) {
             c.inserts += 1;
-        } else {
-            c.retried += 1;
-            u32 s = P.slot;
-            float start;
-            if (P.ret_key == P.key) {   // another env inserted the same state first: its values are in ret_q01
-                if (P.patch) { row.x = __uint_as_float((u32)P.ret_q01); row.y = __uint_as_float((u32)(P.ret_q01 >> 32)); }
-                start = __uint_as_float(P.a == 0 ? (u32)P.ret_q01 : (u32)(P.ret_q01 >> 32));
-            } else {                    // another state took the slot: find a place for ours now
-                float4 r2;
-                s = table_find<true>(tab, P.key, r2, c.inserts);
-                start = q_at(r2, P.a);
-                if (P.patch) slot = s;
-            }
-            if (s != kNoSlot) {
-                float nq = q_update_atomic<SYS>(&tab.at(s)->q[P.a], start, lr, P.target);
-                if (P.patch) q_set(row, P.a, nq);
-            } else {
-                c.dropped += 1;
-                c.lost += 1;
-            }
+        } else if (P.ret_key == P.key) {         // another env inserted the same state first
+            todo = true;
+            if (P.kind == kPendMerged) seen = __uint_as_float(P.a == 0 ? (u32)P.ret_q01 : (u32)(P.ret_q01 >> 32));
+        } else {                                 // another state took the slot (rare): find a place for ours now
+            float4 r2;
+            s = table_find<true>(tab, P.key, r2, c.inserts);
+            seen = q_at(r2, P.a);
+            todo = true;
+            if (cur_key == P.key) cur_slot = s;
+        }
+        if (todo) {
+            c.retried += (P.kind == kPendMerged);
+            if (s != kNoSlot) { late.pending = true; late.slot = s; late.a = P.a; late.target = P.target; late.seen = seen; }
+            else { c.dropped += 1; c.lost += 1; }
         }
     }
     P.kind = kPendNone;
 }
+// The late updates of a warp (all its `live` lanes, lane 0 among them, call this together): appended to the list of deferred updates -- the warp
+// reserves 64 places at a time with one atomicAdd and fills them from a cursor it carries in registers; places it does
+// not use stay all ones -- or, without a list or beyond its end, applied in place by a compare-and-swap loop.
+template <class TAB>
+__device__ __forceinline__ void flush_late(const TAB& tab, const Deferred& D, const LateUpdate& late, float lr,
+                                           unsigned long long& cur, unsigned long long& end, unsigned live) {
+    const unsigned m = __ballot_sync(live, late.pending);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long j = ~0ull;
+    if (D.count) {
+        const int cnt = __popc(m);
+        if (cur + (unsigned long long)cnt > end) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(D.count, 64ull);
+            cur = __shfl_sync(live, base, 0);
+            end = cur + 64;
+        }
+        j = cur + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+        cur += (unsigned long long)cnt;
+    }
+    if (late.pending) {
+        if (j < D.cap) {
+            D.key[j] = (u64)late.slot * 4 + (u64)late.a;
+            D.target[j] = late.target;
+        } else {
+            q_update_atomic<TAB::kSys>(&tab.at(late.slot)->q[late.a], late.seen, lr, late.target);
+        }
+    }
+}
 template <int FLAVOUR, bool SMEM_LUT, class TAB>
-__global__ void __launch_bounds__(SMEM_LUT ? kRolloutThreads : kSmallRolloutThreads, 1)
+__global__ void __launch_bounds__(SMEM_LUT ? kQlearnThreads : kSmallRolloutThreads, 1)
 k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ TAB table, long long n,
                  long long k_steps, float lr, float gamma, u64 eps_thresh, u64 seed, u64 step_base, u64 id_base,
-                 long long* counters) {
+                 long long* counters, unsigned long long* queue, const __grid_constant__ Deferred D) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ Slot* shard_base[G2048_MAX_PEERS];
     const auto tab = table.view(shard_base);
     constexpr bool SYS = decltype(tab)::kSys;
     Lut L = SMEM_LUT ? stage_lut(T, smem) : global_lut(T);
     Counters c;
-#ifdef G2048_EXP_STAGGER
-    __nanosleep((((threadIdx.x >> 5) + 32u * blockIdx.x) * 2654435761u >> 18) & 16383u);
-#endif
-#ifdef G2048_EXP_TIMING
-    u64 t_begin;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-#endif
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long dcur = 0, dend = 0;         // the warp's reserved places in the list of deferred updates
+    for (;;) {
+        long long i = 0;
+        if (lane == 0) i = (long long)atomicAdd(queue, 32ull);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= n) break;
+        i += lane;
+        const unsigned live = __ballot_sync(0xFFFFFFFFu, i < n);   // the last batch may be ragged: the lanes without an env
+        if (i >= n) continue;                                      // wait at the top, the others play on under this mask
         Env e;
         env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
-        u64 id = id_base + (u64)i;
+        const u64 id = id_base + (u64)i;
         float4 row;
-        bool fresh = false;
-        u32 slot = table_find<true>(tab, e.board, row, c.inserts);
-        c.dropped += (slot == kNoSlot);
+        bool fresh;
+        u32 slot = table_probe(tab, e.board, row, fresh, c.dropped);
         PendingUpdate P;
         P.kind = kPendNone;
-        for (long long k = 0; k < k_steps; ++k) {
-            u64 t = step_base + (u64)k;
-            Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
-#ifdef G2048_EXP_LATESETTLE
-            if (P.kind != kPendNone && P.patch) settle_update(tab, P, lr, row, slot, c);
+#ifdef G2048_EXP_TIMING
+        u64 tm0, tm1, tm2, tm3, tm_probe = 0, tm_settle = 0, tm_upd = 0, tm_done = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
+        const u64 tm_start = tm0;
+#define TM(acc) do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1)); acc += tm1 - tm0; tm0 = tm1; } while (0)
 #else
-            if (P.kind != kPendNone) settle_update(tab, P, lr, row, slot, c);   // the atomic issued one step ago
+#define TM(acc) do { } while (0)
 #endif
-            int a = choose_action(row, x, eps_thresh);
+        for (long long k = 0; k < k_steps; ++k) {
+            const u64 t = step_base + (u64)k;
+            Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
+            const int a = choose_action(row, x, eps_thresh);
             const u64 s_board = e.board;
             StepOut o;
             philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
@@ -392,38 +448,59 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_const
             float4 row2 = row;
             u32 slot2 = slot;
             bool fresh2 = fresh;
-            const bool same = (e.board == s_board);   // an invalid move leaves s' == s
+            const bool same = (e.board == s_board);   // an invalid move leaves s' == s: nothing to look up
+            TM(tm_done);
             if (!same) slot2 = table_probe(tab, e.board, row2, fresh2, c.dropped);
-#ifdef G2048_EXP_LATESETTLE
-            if (P.kind != kPendNone) settle_update(tab, P, lr, row, slot, c);
-#endif
-            if (fresh && a >= 2 && slot != kNoSlot) {   // key and value in different halves of the slot: insert first
-                slot = insert_at(tab, slot, s_board, c.inserts, c.dropped);
-                fresh = false;
-                if (same) { slot2 = slot; fresh2 = false; }
+            __syncwarp(live);
+            TM(tm_probe);
+            // the atomic issued one step ago has arrived by now (a whole lookup went by)
+            LateUpdate late;
+            if (P.kind != kPendNone) {
+                settle_update(tab, P, s_board, slot, c, late);
+                if (same) slot2 = slot;
             }
-            if (slot != kNoSlot) {
+            __syncwarp(live);
+            flush_late(tab, D, late, lr, dcur, dend, live);
+            TM(tm_settle);
+            if (slot == kNoSlot) {
+                c.lost += 1;                       // the state has no slot (table full): the update cannot be stored
+            } else {
                 const float q = q_at(row, a);
                 const float target = td_target(gamma, (float)o.reward, max4(row2), o.done);
                 const float nq = td_apply(q, lr, target);
                 Slot* sp = tab.at(slot);
-                P.slot = slot; P.a = a; P.target = target; P.patch = same && !o.done;
+                P.slot = slot; P.a = a; P.target = target;
                 if (!fresh) {
                     P.assumed = __float_as_uint(q);
                     P.ret_q01 = cas32<SYS>(reinterpret_cast<u32*>(&sp->q[a]), P.assumed, __float_as_uint(nq));
                     P.kind = kPendUpd32;
-                } else {
+                } else if (a < 2) {
                     P.key = s_board;
                     cas_w0<SYS>(sp, 0ull, 0ull, s_board, (u64)__float_as_uint(nq) << (32 * a), P.ret_key, P.ret_q01);
                     P.kind = kPendMerged;
+                } else if (D.count) {              // key and value in different halves: the value follows the insert
+                    P.key = s_board;
+                    P.ret_key = cas64<SYS>(&sp->key, 0ull, s_board);
+                    P.kind = kPendInsert;
+                } else {                           // no list: insert now, then the usual 32-bit CAS
+                    slot = insert_at(tab, slot, s_board, c.inserts, c.dropped);
+                    if (same) slot2 = slot;
+                    if (slot != kNoSlot) {
+                        P.slot = slot;
+                        P.assumed = 0u;
+                        P.ret_q01 = cas32<SYS>(reinterpret_cast<u32*>(&tab.at(slot)->q[a]), 0u, __float_as_uint(nq));
+                        P.kind = kPendUpd32;
+                    } else {
+                        c.lost += 1;
+                    }
                 }
                 if (same) { q_set(row2, a, nq); fresh2 = false; }
-            } else {
-                c.lost += 1;   // the state has no slot (table full): the update cannot be stored
             }
             row = row2;
             slot = slot2;
             fresh = fresh2;
+            __syncwarp(live);
+            TM(tm_upd);
             if (o.done) {
                 // update_q_value read Q[next_state] (main.py:41): the terminal state is in the table from now on;
                 // state = env.reset() is looked up at once (main.py:81-82, :92)
@@ -432,25 +509,32 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_const
                 slot = table_probe(tab, e.board, row, fresh, c.dropped);
             }
         }
-        if (P.kind != kPendNone) settle_update(tab, P, lr, row, slot, c);
+        {
+            LateUpdate late;
+            if (P.kind != kPendNone) settle_update(tab, P, e.board, slot, c, late);
+            __syncwarp(live);
+            flush_late(tab, D, late, lr, dcur, dend, live);
+        }
         if (fresh && slot != kNoSlot) insert_at(tab, slot, e.board, c.inserts, c.dropped);   // the launch ends: reading a state creates it
         boards[i] = e.board;
         if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
         if (score) score[i] = e.score;
-    }
 #ifdef G2048_EXP_TIMING
-    {
-        u64 t_end;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-        long long dt = (long long)(t_end - t_begin);
-        if ((threadIdx.x & 31) == 0 && counters) {
+        __syncwarp(live);
+        TM(tm_done);
+        if (lane == 0) {
+            long long dt = (long long)(tm1 - tm_start);
             atomicMax(counters + 10, dt);
             atomicAdd((unsigned long long*)(counters + 11), (unsigned long long)dt);
-            atomicMin(counters + 12, dt);
             atomicAdd((unsigned long long*)(counters + 13), 1ull);
+            unsigned sm;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            if (dt > 400000) printf("slow rollout: sm %u warp %d env %lld total %lld us: probe %llu settle %llu update %llu step+done %llu\n", sm,
+                                    (int)(threadIdx.x >> 5), i, dt / 1000, tm_probe / 1000, tm_settle / 1000, tm_upd / 1000, tm_done / 1000);
         }
-    }
 #endif
+    }
+#undef TM
     flush_counters(c, counters);
 }
 
@@ -730,6 +814,197 @@ k_long_run_apply(Slot* tab, const u64* sortkey, const float* target, float lr, l
             j += 32; kk = kn; tt = tn;
         }
         if (lane == 0) *qp = q;
+    }
+}
+
+// ---- the deferred updates of a fused rollout: group by address, apply every group as one sequential chain --------
+// No sort is needed, only "all the records of one Q value in one thread's hands": the records are counted into 2^18
+// hash buckets of their address (one atomicAdd each, which also gives the record its place in the bucket), the bucket
+// sizes are prefix-summed, the records scattered bucket by bucket, and one thread per bucket applies what it holds
+// (a bucket holds a few records of different addresses, or the hundreds that pile up on the action a popular start
+// state takes).  The order inside a group is whatever the atomics produced: the asynchronous mode promises one
+// sequential application of every update, not a particular one.
+constexpr int kDeferBucketBits = 18;
+constexpr u32 kDeferBuckets = 1u << kDeferBucketBits;
+constexpr u32 kInlineBucket = 24;     // buckets of more records than this are applied by a warp
+constexpr u32 kFoldBucket = 256;       // ... and from this size on the warp folds them segment-wise
+__device__ __forceinline__ u32 defer_bucket(u64 key) { return (u32)((key * 0x9E3779B97F4A7C15ull) >> (64 - kDeferBucketBits)); }
+__global__ void __launch_bounds__(256)
+k_defer_count(const u64* key, const unsigned long long* count, unsigned long long cap, u32* pos, u32* bcount) {
+    const unsigned long long m = *count < cap ? *count : cap;
+    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < m; j += (unsigned long long)gridDim.x * blockDim.x) {
+        const u64 k = key[j];
+        if (k != ~0ull) pos[j] = atomicAdd(&bcount[defer_bucket(k)], 1u);
+    }
+}
+// exclusive prefix sum over the 2^18 bucket sizes: 256 blocks scan 1024 each, block 0's last warp then scans the 256
+// block totals once every block has published its own (a counter in sums[257] says how many have)
+__global__ void __launch_bounds__(1024) k_defer_scan(u32* bcount, u32* sums, u32* work) {
+    __shared__ u32 warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 idx = blockIdx.x * 1024u + threadIdx.x;
+    const u32 v = bcount[idx];
+    if (v > kInlineBucket) work[atomicAdd(&sums[257], 1u)] = idx;   // long buckets get a warp each (k_defer_apply)
+    u32 x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = warp_tot[lane], z = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
+        warp_tot[lane] = z - w;
+        if (lane == 31) sums[blockIdx.x] = z;          // this block's total
+    }
+    __syncthreads();
+    bcount[idx] = x - v + warp_tot[warp];              // exclusive, within the block
+}
+__global__ void __launch_bounds__(256) k_defer_scan_sums(u32* sums) {   // 256 block totals -> exclusive offsets, total in sums[256]
+    __shared__ u32 warp_tot[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 v = sums[threadIdx.x];
+    u32 x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    sums[threadIdx.x] = x - v + base;
+    if (threadIdx.x == 255) sums[256] = x + base;
+}
+__global__ void __launch_bounds__(256)
+k_defer_scatter(const u64* key, const float* target, const unsigned long long* count, unsigned long long cap, const u32* pos,
+                const u32* boff, const u32* sums, u64* key_out, float* target_out) {
+    const unsigned long long m = *count < cap ? *count : cap;
+    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < m; j += (unsigned long long)gridDim.x * blockDim.x) {
+        const u64 k = key[j];
+        if (k == ~0ull) continue;
+        const u32 b = defer_bucket(k);
+        const u32 d = sums[b >> 10] + boff[b] + pos[j];
+        key_out[d] = k;
+        target_out[d] = target[j];
+    }
+}
+// q <- q + lr (target - q) record after record; the value is written back with a compare-and-swap from what was read,
+// so that a rollout running on another stream cannot be overwritten (it rarely is: start again).  One kernel, two kinds
+// of blocks that run side by side: the first `long_blocks` blocks take the long buckets (more than kInlineBucket records:
+// a popular start state's action collects thousands per launch; queued in work[0 .. sums[257]) by k_defer_scan), one
+// WARP per bucket; the other blocks take one bucket per THREAD and skip the long ones.
+__device__ __forceinline__ void defer_bucket_range(const u32* boff, const u32* sums, u32 b, u32& begin, u32& end) {
+    begin = sums[b >> 10] + boff[b];
+    end = (b + 1 == kDeferBuckets) ? sums[256] : sums[(b + 1) >> 10] + boff[b + 1];
+}
+__global__ void __launch_bounds__(256)
+k_defer_apply(Slot* tab, u64* key, const float* target, const u32* boff, const u32* sums, float lr, const u32* work,
+              int long_blocks) {
+    if ((int)blockIdx.x >= long_blocks) {
+        const u32 b = (blockIdx.x - long_blocks) * blockDim.x + threadIdx.x;
+        if (b >= kDeferBuckets) return;
+        u32 begin, end;
+        defer_bucket_range(boff, sums, b, begin, end);
+        if (end - begin > kInlineBucket) return;
+        for (u32 r = begin; r < end; ++r) {
+            const u64 k = key[r];
+            if (k == ~0ull) continue;                  // applied together with an earlier record of the same address
+            float* qp = &tab[k >> 2].q[k & 3];
+            u32 seen = __float_as_uint(__ldcg(qp));
+            for (;;) {
+                float q = __uint_as_float(seen);
+                for (u32 t = r; t < end; ++t)
+                    if (key[t] == k) q = td_apply(q, lr, target[t]);
+                const u32 old = atomicCAS(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
+                if (old == seen) break;
+                seen = old;
+            }
+            for (u32 t = r + 1; t < end; ++t)
+                if (key[t] == k) key[t] = ~0ull;
+        }
+        return;
+    }
+    // for every address of the bucket (in order of first appearance) the lanes fetch the bucket 32 records at a time and
+    // fold the targets into the chain in record order: 3 dependent float operations per record, the sequential update
+    const int lane = threadIdx.x & 31;
+    const u32 n_warps = (u32)long_blocks * (blockDim.x >> 5), n_work = sums[257];
+    for (u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_work; w += n_warps) {
+        u32 begin, end;
+        defer_bucket_range(boff, sums, work[w], begin, end);
+        u32 r = begin;
+        for (;;) {                                     // warp-uniform
+            // the next record that has not been applied yet, 32 at a time
+            u64 k = ~0ull;
+            while (r < end) {
+                const u32 t = r + lane;
+                const u64 kt = t < end ? key[t] : ~0ull;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, kt != ~0ull);
+                if (m) {
+                    const int l = __ffs((int)m) - 1;
+                    k = __shfl_sync(0xFFFFFFFFu, kt, l);
+                    r += (u32)l;
+                    break;
+                }
+                r += 32;
+            }
+            if (r >= end) break;
+            float* qp = &tab[k >> 2].q[k & 3];
+            u32 seen = __float_as_uint(__ldcg(qp));
+            if (end - r >= kFoldBucket) {
+                // Thousands of records on one value (the action a popular start state takes): a chain of that length
+                // would be the whole phase.  Every lane folds the records r + lane, r + lane + 32, ... into its own map
+                // q -> A q + B (B = the exact chain started from 0, A = (1 - lr)^count), then the 32 maps are composed
+                // lane after lane: one sequential order of all the updates, evaluated segment-wise (equal to the plain
+                // chain up to float32 rounding of the composition).
+                const float keep = __fsub_rn(1.0f, lr);
+                float A = 1.0f, B = 0.0f;
+                for (u32 t = r + lane; t < end; t += 32)
+                    if (key[t] == k) { B = td_apply(B, lr, target[t]); A = __fmul_rn(A, keep); }
+                for (;;) {
+                    float q = __uint_as_float(seen);
+#pragma unroll
+                    for (int l = 0; l < 32; ++l)
+                        q = __fadd_rn(__fmul_rn(__shfl_sync(0xFFFFFFFFu, A, l), q), __shfl_sync(0xFFFFFFFFu, B, l));
+                    u32 old = 0;
+                    if (lane == 0) old = atomicCAS(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
+                    old = __shfl_sync(0xFFFFFFFFu, old, 0);
+                    if (old == seen) break;
+                    seen = old;
+                }
+            } else
+            for (;;) {
+                float q = __uint_as_float(seen);
+                u32 t = r + lane;
+                bool mine = t < end && key[t] == k;
+                float tt = mine ? target[t] : 0.f;
+                for (u32 base = r; base < end; base += 32) {
+                    const u32 tn = base + 32 + lane;           // the next chunk is in flight while this one is folded
+                    const bool mine_n = tn < end && key[tn] == k;
+                    const float tt_n = mine_n ? target[tn] : 0.f;
+                    unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (m == 0xFFFFFFFFu) {
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) q = td_apply(q, lr, __shfl_sync(0xFFFFFFFFu, tt, l));
+                    } else {
+                        while (m) {
+                            const int l = __ffs((int)m) - 1;
+                            m &= m - 1;
+                            q = td_apply(q, lr, __shfl_sync(0xFFFFFFFFu, tt, l));
+                        }
+                    }
+                    mine = mine_n;
+                    tt = tt_n;
+                }
+                u32 old = 0;
+                if (lane == 0) old = atomicCAS(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
+                old = __shfl_sync(0xFFFFFFFFu, old, 0);
+                if (old == seen) break;
+                seen = old;
+            }
+            for (u32 t = r + lane; t < end; t += 32)
+                if (key[t] == k) key[t] = ~0ull;
+            __syncwarp();
+            r += 1;
+        }
     }
 }
 
@@ -1027,6 +1302,7 @@ G2048_API int g2048_init(int device) {
                       (const uint32_t*)((const char*)lut + kLutRowBytes + kLutMergedBytes), (const double*)rv,
                       (const double*)ri, (const double*)pn};
     CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaMalloc(&d.queue, kQueueSlots * sizeof(unsigned long long)));
     CK(cudaFuncSetAttribute(k_rollout_random<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_rollout_random<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_env_step<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
@@ -1171,9 +1447,10 @@ G2048_API int g2048_dqn_env_step(uint64_t* boards, int32_t* score, const float* 
 
 // fused rollouts: one persistent CTA per SM with the LUT in shared memory once there is enough work to
 // amortise the 213 KB staging copy; small batches read the LUT through L1 instead.
-static inline void rollout_geometry(const DeviceState* D, int64_t n, int& grid, int& block, int& smem_lut, size_t& smem) {
+static inline void rollout_geometry(const DeviceState* D, int64_t n, int& grid, int& block, int& smem_lut, size_t& smem,
+                                    int big_block = kRolloutThreads) {
     if (n >= 16384) {
-        block = kRolloutThreads;
+        block = big_block;
         grid = (int)((n + block - 1) / block);
         if (grid > D->sm_count) grid = D->sm_count;
         smem_lut = 1;
@@ -1208,23 +1485,22 @@ G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* sco
 }
 
 namespace {
+struct Scratch;
+size_t scratch_bytes(int64_t n);
+int carve(void* scratch, size_t bytes, int64_t n, Scratch& s);
+int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, float lr, int mode, cudaStream_t st,
+                  int kshift = 0);
+inline Slot* local_slots(const LocalTable& t) { return t.base; }
+inline Slot* local_slots(const ShardedTable&) { return nullptr; }
+inline uint64_t table_slots(const LocalTable& t) { return t.mask + 1; }
+inline uint64_t table_slots(const ShardedTable& t) { return t.mask + 1; }
+
+struct DeferBuffers;
 template <class TAB>
 int launch_rollout_qlearn(DeviceState* D, const TAB& tab, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n,
                           int64_t k_steps, int flavour, float lr, float gamma, double eps, uint64_t seed,
-                          uint64_t step_base, uint64_t env_id_base, int64_t* counters, void* stream) {
-    int grid, block, smem_lut;
-    size_t smem;
-    rollout_geometry(D, n, grid, block, smem_lut, smem);
-#define LAUNCH_RQ(F, SM)                                                                                              \
-    k_rollout_qlearn<F, SM, TAB><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, tab, n,   \
-                                                                   k_steps, lr, gamma, eps_threshold(eps), seed,       \
-                                                                   step_base, env_id_base, (long long*)counters)
-    if (flavour == 0) { if (smem_lut) LAUNCH_RQ(0, true); else LAUNCH_RQ(0, false); }
-    else { if (smem_lut) LAUNCH_RQ(1, true); else LAUNCH_RQ(1, false); }
-#undef LAUNCH_RQ
-    LAUNCH_CHECK("k_rollout_qlearn");
-    return 0;
-}
+                          uint64_t step_base, uint64_t env_id_base, int64_t* counters, void* stream,
+                          const DeferBuffers* shared_list = nullptr);
 // shards[j] = device pointer to slots_per_shard slots (local or peer memory); n_shards and slots_per_shard powers of two
 int make_sharded(const void* const* shards, int n_shards, uint64_t slots_per_shard, ShardedTable& t, const char* who) {
     if (!shards || n_shards < 1 || n_shards > G2048_MAX_PEERS || (n_shards & (n_shards - 1)) || !pow2(slots_per_shard) ||
@@ -1320,7 +1596,7 @@ int carve(void* scratch, size_t bytes, int64_t n, Scratch& s) {
 }
 // apply the records in s.key_in / s.val_in
 int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, float lr, int mode, cudaStream_t st,
-                  int kshift = 0) {
+                  int kshift) {
     int g = grid_for(n, 256, D->sm_count);
     if (mode == G2048_MODE_ATOMIC) {
         k_apply_atomic<<<g, 256, 0, st>>>(tab, s.key_in, s.val_in, lr, n);
@@ -1344,6 +1620,111 @@ int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int6
         k_long_run_apply<<<D->sm_count * 4, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist, kshift);
         LAUNCH_CHECK("k_long_run_apply");
     }
+    return 0;
+}
+}  // namespace
+
+
+namespace {
+// a zeroed list of `cap` deferred updates and the buffers that group them, from the device's ring
+struct DeferBuffers {
+    unsigned long long* count;
+    u64 *key, *key_out;
+    float *target, *target_out;
+    u32 *pos, *boff, *sums, *work;
+    int64_t cap;
+};
+int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B) {
+    DeviceState::DeferSet* set;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        set = &D->defer[D->defer_next++ % 4];
+    }
+    const size_t m = (size_t)cap;
+    const size_t need = 256 + 2 * align256(m * 8) + 3 * align256(m * 4) + 2 * align256(kDeferBuckets * 4) + align256(258 * 4);
+    if (set->bytes < need) {
+        CK(cudaDeviceSynchronize());               // growing: nobody may still be using the old buffer
+        if (set->buf) CK(cudaFree(set->buf));
+        set->buf = nullptr;
+        set->bytes = 0;
+        CK(cudaMalloc(&set->buf, need));
+        set->bytes = need;
+    }
+    char* p = (char*)set->buf;
+    B.count = (unsigned long long*)p; p += 256;
+    B.key = (u64*)p; p += align256(m * 8);
+    B.key_out = (u64*)p; p += align256(m * 8);
+    B.target = (float*)p; p += align256(m * 4);
+    B.target_out = (float*)p; p += align256(m * 4);
+    B.pos = (u32*)p; p += align256(m * 4);
+    B.boff = (u32*)p; p += align256(kDeferBuckets * 4);
+    B.work = (u32*)p; p += align256(kDeferBuckets * 4);
+    B.sums = (u32*)p;
+    B.cap = cap;
+    CK(cudaMemsetAsync(B.count, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(B.key, 0xFF, m * sizeof(u64), st));   // all ones = no record
+    CK(cudaMemsetAsync(B.boff, 0, kDeferBuckets * sizeof(u32), st));
+    CK(cudaMemsetAsync(B.sums, 0, 258 * sizeof(u32), st));
+    return 0;
+}
+// room for one lost race in eight env steps (measured: one in 16-25 once the games have spread out; only the first
+// launch after a common reset, where every env sits on one of 480 boards, overflows into the in-place loop)
+int64_t deferred_capacity(int64_t n, int64_t k_steps) {
+    const long double want = (long double)n * (long double)k_steps / 8;
+    int64_t cap = 1 << 16;
+    while (cap < (1 << 23) && (long double)cap < want) cap <<= 1;
+    return cap;
+}
+int apply_deferred(DeviceState* D, Slot* tab, const DeferBuffers& B, float lr, cudaStream_t st) {
+    const int g = grid_for(B.cap, 256, D->sm_count);
+    k_defer_count<<<g, 256, 0, st>>>(B.key, B.count, (unsigned long long)B.cap, B.pos, B.boff);
+    k_defer_scan<<<kDeferBuckets / 1024, 1024, 0, st>>>(B.boff, B.sums, B.work);
+    k_defer_scan_sums<<<1, 256, 0, st>>>(B.sums);
+    k_defer_scatter<<<g, 256, 0, st>>>(B.key, B.target, B.count, (unsigned long long)B.cap, B.pos, B.boff, B.sums, B.key_out,
+                                       B.target_out);
+    const int long_blocks = D->sm_count * 4;
+    k_defer_apply<<<long_blocks + kDeferBuckets / 256, 256, 0, st>>>(tab, B.key_out, B.target_out, B.boff, B.sums, lr, B.work,
+                                                                      long_blocks);
+    LAUNCH_CHECK("apply_deferred");
+    return 0;
+}
+template <class TAB>
+int launch_rollout_qlearn(DeviceState* D, const TAB& tab, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n,
+                          int64_t k_steps, int flavour, float lr, float gamma, double eps, uint64_t seed,
+                          uint64_t step_base, uint64_t env_id_base, int64_t* counters, void* stream,
+                          const DeferBuffers* shared_list) {
+    int grid, block, smem_lut;
+    size_t smem;
+    rollout_geometry(D, n, grid, block, smem_lut, smem, kQlearnThreads);
+    // the warps take their envs from a queue: its head is a counter zeroed in stream order before the launch
+    unsigned long long* queue;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        queue = D->queue + (D->queue_next++ % kQueueSlots);
+    }
+    CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), S(stream)));
+    // big launches on a local table: lost races go to a list that is applied after the rollout (see the kernel)
+    // (shared_list: the caller runs several launches into one list and applies it itself)
+    Deferred defer{};
+    DeferBuffers db{};
+    int64_t cap = 0;
+    if (shared_list) {
+        defer = Deferred{shared_list->key, shared_list->target, shared_list->count, (unsigned long long)shared_list->cap};
+    } else if (n >= kDeferMinEnvs && local_slots(tab)) {
+        cap = deferred_capacity(n, k_steps);
+        int rc = deferred_list(D, cap, S(stream), db);
+        if (rc) return rc;
+        defer = Deferred{db.key, db.target, db.count, (unsigned long long)cap};
+    }
+#define LAUNCH_RQ(F, SM)                                                                                              \
+    k_rollout_qlearn<F, SM, TAB><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, tab, n,   \
+                                                                   k_steps, lr, gamma, eps_threshold(eps), seed,       \
+                                                                   step_base, env_id_base, (long long*)counters, queue, defer)
+    if (flavour == 0) { if (smem_lut) LAUNCH_RQ(0, true); else LAUNCH_RQ(0, false); }
+    else { if (smem_lut) LAUNCH_RQ(1, true); else LAUNCH_RQ(1, false); }
+#undef LAUNCH_RQ
+    LAUNCH_CHECK("k_rollout_qlearn");
+    if (cap) return apply_deferred(D, local_slots(tab), db, lr, S(stream));
     return 0;
 }
 }  // namespace
@@ -1646,7 +2027,7 @@ struct g2048_ctx {
     uint64_t capacity = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // chunked rollouts: copies of one chunk overlap the kernel of another
-    cudaEvent_t ev_start = nullptr, ev_done[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr, ev_done[3] = {nullptr, nullptr, nullptr}, ev_kernel[3] = {nullptr, nullptr, nullptr};
     void* table = nullptr;
     // device staging, sized for max_envs
     u64 *boards = nullptr, *aux = nullptr, *keys2 = nullptr;
@@ -1676,7 +2057,8 @@ G2048_API g2048_ctx* g2048_ctx_create(int device, int64_t max_envs, uint64_t tab
               cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming) == cudaSuccess;
     for (int j = 0; ok && j < 3; ++j)
         ok = cudaStreamCreateWithFlags(&c->pipe[j], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&c->ev_done[j], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&c->ev_done[j], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_kernel[j], cudaEventDisableTiming) == cudaSuccess;
     if (ok && max_envs <= kTinyCtxEnvs) {
         const size_t slot = align256(m * 16);            // every staging buffer fits one slot (rows: 16 B per env)
         c->arena_bytes = 13 * slot;
@@ -1731,6 +2113,7 @@ G2048_API void g2048_ctx_destroy(g2048_ctx* c) {
     for (int j = 0; j < 3; ++j) {
         if (c->pipe[j]) cudaStreamDestroy(c->pipe[j]);
         if (c->ev_done[j]) cudaEventDestroy(c->ev_done[j]);
+        if (c->ev_kernel[j]) cudaEventDestroy(c->ev_kernel[j]);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     delete c;
@@ -1848,6 +2231,11 @@ static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* s
     const int64_t T = (int64_t)D->sm_count * kRolloutThreads;
     const int64_t unit = T * (n / (6 * T) > 1 ? n / (6 * T) : 1);
     const bool pipelined = n >= (1 << 18) && n > unit;
+    // the chunks of a Q-learning rollout share one list of deferred updates, applied once all their kernels are done
+    // (while the last chunk's results are still on their way back to the host)
+    DeferBuffers db{};
+    const bool shared_list = qlearn && pipelined && n >= kDeferMinEnvs;
+    if (shared_list) RC(deferred_list(D, deferred_capacity(n, k_steps), st, db));
     CK(cudaEventRecord(c->ev_start, st));
     int64_t lo = 0;
     for (int j = 0; lo < n; ++j) {
@@ -1858,19 +2246,25 @@ static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* s
         CK(cudaMemcpyAsync(c->boards + lo, boards + lo, (size_t)m * 8, cudaMemcpyDefault, ps));
         if (aux) CK(cudaMemcpyAsync(c->aux + lo, aux + lo, (size_t)m * 8, cudaMemcpyDefault, ps));
         if (score) CK(cudaMemcpyAsync(c->score + lo, score + lo, (size_t)m * 4, cudaMemcpyDefault, ps));
-        uint64_t* db = (uint64_t*)c->boards + lo;
+        uint64_t* dbo = (uint64_t*)c->boards + lo;
         uint64_t* da = aux ? (uint64_t*)c->aux + lo : nullptr;
         int32_t* ds = score ? c->score + lo : nullptr;
         if (qlearn)
-            RC(g2048_rollout_qlearn(db, da, ds, c->table, c->capacity, m, k_steps, flavour, lr, gamma, eps, seed, step_base,
-                                    env_id_base + (uint64_t)lo, (int64_t*)c->counters, ps));
+            RC(launch_rollout_qlearn(D, LocalTable{(Slot*)c->table, c->capacity - 1}, dbo, da, ds, m, k_steps, flavour, lr,
+                                     gamma, eps, seed, step_base, env_id_base + (uint64_t)lo, (int64_t*)c->counters, ps,
+                                     shared_list ? &db : nullptr));
         else
-            RC(g2048_rollout_random(db, da, ds, m, k_steps, flavour, seed, step_base, env_id_base + (uint64_t)lo,
+            RC(g2048_rollout_random(dbo, da, ds, m, k_steps, flavour, seed, step_base, env_id_base + (uint64_t)lo,
                                     (int64_t*)c->counters, ps));
+        if (shared_list) CK(cudaEventRecord(c->ev_kernel[j % 3], ps));
         CK(cudaMemcpyAsync(boards + lo, c->boards + lo, (size_t)m * 8, cudaMemcpyDefault, ps));
         if (aux) CK(cudaMemcpyAsync(aux + lo, c->aux + lo, (size_t)m * 8, cudaMemcpyDefault, ps));
         if (score) CK(cudaMemcpyAsync(score + lo, c->score + lo, (size_t)m * 4, cudaMemcpyDefault, ps));
         lo += m;
+    }
+    if (shared_list) {
+        for (int j = 0; j < 3; ++j) CK(cudaStreamWaitEvent(st, c->ev_kernel[j], 0));
+        RC(apply_deferred(D, (Slot*)c->table, db, lr, st));
     }
     if (pipelined)
         for (int j = 0; j < 3; ++j) {

@@ -15,7 +15,6 @@ s = torch.zeros(n, dtype=torch.int32, device=dev)
 assert L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, 0x2048, 0, 0, st) == 0
 table = torch.zeros(cap * 4, dtype=torch.int64, device=dev)
 cs = [torch.zeros(16, dtype=torch.int64, device=dev) for _ in range(launches)]
-for c in cs: c[12] = 1 << 62
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(launches + 1)]
 torch.cuda.synchronize(); ev[0].record()
 for i in range(launches):
@@ -28,4 +27,4 @@ for i in range(launches):
     c = cs[i].tolist(); ms = ev[i].elapsed_time(ev[i + 1])
     w = max(c[13], 1)
     print(f"launch {i:2d}: {ms:6.3f} ms  {n*k/ms/1e6:6.2f} G/s  valid {c[1]/c[0]:.3f} new {c[6]/c[0]:.3f} retried {c[9]/c[0]:.3f} episodes {c[2]}"
-          + (f"  warp time max {c[10]/1e6:.3f} mean {c[11]/w/1e6:.3f} min {c[12]/1e6:.3f} ms" if c[13] else ""))
+          + (f"  rollout time max {c[10]/1e3:.0f} mean {c[11]/w/1e3:.0f} us" if c[13] else ""))
