@@ -823,7 +823,7 @@ k_long_run_apply(Slot* tab, const u64* sortkey, const float* target, float lr, l
 // sizes are prefix-summed, the records scattered bucket by bucket, and one thread per bucket applies what it holds
 // (a bucket holds a few records of different addresses, or the hundreds that pile up on the action a popular start
 // state takes).  The order inside a group is whatever the atomics produced: the asynchronous mode promises one
-// sequential application of every update, not a particular one.
+// sequential application of every update; within a group of up to kInlineBucket records it is the order of the list.
 constexpr int kDeferBucketBits = 18;
 constexpr u32 kDeferBuckets = 1u << kDeferBucketBits;
 constexpr u32 kInlineBucket = 24;     // buckets of more records than this are applied by a warp
@@ -876,7 +876,7 @@ __global__ void __launch_bounds__(256) k_defer_scan_sums(u32* sums) {   // 256 b
 }
 __global__ void __launch_bounds__(256)
 k_defer_scatter(const u64* key, const float* target, const unsigned long long* count, unsigned long long cap, const u32* pos,
-                const u32* boff, const u32* sums, u64* key_out, float* target_out) {
+                const u32* boff, const u32* sums, u64* key_out, float* target_out, u32* index_out) {
     const unsigned long long m = *count < cap ? *count : cap;
     for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < m; j += (unsigned long long)gridDim.x * blockDim.x) {
         const u64 k = key[j];
@@ -885,6 +885,7 @@ k_defer_scatter(const u64* key, const float* target, const unsigned long long* c
         const u32 d = sums[b >> 10] + boff[b] + pos[j];
         key_out[d] = k;
         target_out[d] = target[j];
+        index_out[d] = (u32)j;                       // its place in the list = the order in which its warp appended it
     }
 }
 // q <- q + lr (target - q) record after record; the value is written back with a compare-and-swap from what was read,
@@ -897,8 +898,8 @@ __device__ __forceinline__ void defer_bucket_range(const u32* boff, const u32* s
     end = (b + 1 == kDeferBuckets) ? sums[256] : sums[(b + 1) >> 10] + boff[b + 1];
 }
 __global__ void __launch_bounds__(256)
-k_defer_apply(Slot* tab, u64* key, const float* target, const u32* boff, const u32* sums, float lr, const u32* work,
-              int long_blocks) {
+k_defer_apply(Slot* tab, u64* key, const float* target, const u32* index, const u32* boff, const u32* sums, float lr,
+              const u32* work, int long_blocks) {
     if ((int)blockIdx.x >= long_blocks) {
         const u32 b = (blockIdx.x - long_blocks) * blockDim.x + threadIdx.x;
         if (b >= kDeferBuckets) return;
@@ -911,9 +912,18 @@ k_defer_apply(Slot* tab, u64* key, const float* target, const u32* boff, const u
             float* qp = &tab[k >> 2].q[k & 3];
             u32 seen = __float_as_uint(__ldcg(qp));
             for (;;) {
+                // the records of this address in the order of the list (an env's own updates of one value keep their
+                // order: a warp appends in time order): repeatedly the smallest list index above the last one
                 float q = __uint_as_float(seen);
-                for (u32 t = r; t < end; ++t)
-                    if (key[t] == k) q = td_apply(q, lr, target[t]);
+                long long last = -1;
+                for (;;) {
+                    u32 best = ~0u, best_t = 0;
+                    for (u32 t = r; t < end; ++t)
+                        if (key[t] == k && (long long)index[t] > last && index[t] < best) { best = index[t]; best_t = t; }
+                    if (best == ~0u) break;
+                    q = td_apply(q, lr, target[best_t]);
+                    last = (long long)best;
+                }
                 const u32 old = atomicCAS(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
                 if (old == seen) break;
                 seen = old;
@@ -1631,7 +1641,7 @@ struct DeferBuffers {
     unsigned long long* count;
     u64 *key, *key_out;
     float *target, *target_out;
-    u32 *pos, *boff, *sums, *work;
+    u32 *pos, *index_out, *boff, *sums, *work;
     int64_t cap;
 };
 int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B) {
@@ -1641,7 +1651,7 @@ int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B)
         set = &D->defer[D->defer_next++ % 4];
     }
     const size_t m = (size_t)cap;
-    const size_t need = 256 + 2 * align256(m * 8) + 3 * align256(m * 4) + 2 * align256(kDeferBuckets * 4) + align256(258 * 4);
+    const size_t need = 256 + 2 * align256(m * 8) + 4 * align256(m * 4) + 2 * align256(kDeferBuckets * 4) + align256(258 * 4);
     if (set->bytes < need) {
         CK(cudaDeviceSynchronize());               // growing: nobody may still be using the old buffer
         if (set->buf) CK(cudaFree(set->buf));
@@ -1657,6 +1667,7 @@ int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B)
     B.target = (float*)p; p += align256(m * 4);
     B.target_out = (float*)p; p += align256(m * 4);
     B.pos = (u32*)p; p += align256(m * 4);
+    B.index_out = (u32*)p; p += align256(m * 4);
     B.boff = (u32*)p; p += align256(kDeferBuckets * 4);
     B.work = (u32*)p; p += align256(kDeferBuckets * 4);
     B.sums = (u32*)p;
@@ -1681,10 +1692,10 @@ int apply_deferred(DeviceState* D, Slot* tab, const DeferBuffers& B, float lr, c
     k_defer_scan<<<kDeferBuckets / 1024, 1024, 0, st>>>(B.boff, B.sums, B.work);
     k_defer_scan_sums<<<1, 256, 0, st>>>(B.sums);
     k_defer_scatter<<<g, 256, 0, st>>>(B.key, B.target, B.count, (unsigned long long)B.cap, B.pos, B.boff, B.sums, B.key_out,
-                                       B.target_out);
+                                       B.target_out, B.index_out);
     const int long_blocks = D->sm_count * 4;
-    k_defer_apply<<<long_blocks + kDeferBuckets / 256, 256, 0, st>>>(tab, B.key_out, B.target_out, B.boff, B.sums, lr, B.work,
-                                                                      long_blocks);
+    k_defer_apply<<<long_blocks + kDeferBuckets / 256, 256, 0, st>>>(tab, B.key_out, B.target_out, B.index_out, B.boff, B.sums,
+                                                                      lr, B.work, long_blocks);
     LAUNCH_CHECK("apply_deferred");
     return 0;
 }

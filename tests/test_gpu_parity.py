@@ -359,9 +359,9 @@ def test_rollout_qlearn_single_env_is_the_reference_order(L, ctx):
 
 
 def test_rollout_qlearn_1M_envs_properties(L, ctx):
-    """BASELINE config 3 size (2^20 envs): step count, no dropped inserts, table size == inserts, finite Q
-    bounded by |r|max / (1 - gamma) although thousands of envs update the same start states
-    concurrently (the atomic update is a contraction, not a sum of stale deltas), boards stay legal."""
+    """BASELINE config 3 size (2^20 envs): step count, no dropped inserts, table size == inserts, EVERY update applied
+    (LOST == 0 while thousands of envs update the same start states concurrently: RETRIED > 0), finite Q bounded by
+    |r|max / (1 - gamma) (the update is a contraction, not a sum of stale deltas), boards stay legal."""
     n, k, seed = 1 << 20, 48, 0x2048
     big = L.g2048_ctx_create(0, n, 1 << 27)
     assert big, L.g2048_last_error()
@@ -370,6 +370,7 @@ def test_rollout_qlearn_1M_envs_properties(L, ctx):
         c = np.zeros(16, np.int64)
         ok(L, L.g2048_ctx_rollout_qlearn(big, vp(b), vp(a), vp(s), n, k, 0, 0.1, 0.99, 0.1, seed, 0, 0, vp(c)))
         assert c[0] == n * k and c[7] == 0
+        assert c[8] == 0 and c[9] > 0          # LOST, RETRIED (include/g2048.h)
         size = L.g2048_ctx_qtable_size(big)
         assert size == c[6]
         keys, rows = np.zeros(size, np.uint64), np.zeros((size, 4), np.float32)
@@ -377,6 +378,136 @@ def test_rollout_qlearn_1M_envs_properties(L, ctx):
         assert len(np.unique(keys)) == size and (keys != 0).all()
         assert np.isfinite(rows).all() and np.abs(rows).max() <= 20 / (1 - 0.99)
         assert (b != 0).all()
+    finally:
+        L.g2048_ctx_destroy(big)
+
+
+def test_fused_rollout_all_exploring_is_the_random_rollout_and_stores_every_visited_state(L):
+    """BASELINE config 3 size, epsilon = 1: the actions do not depend on Q, so the fused Q-learning rollout must leave
+    boards / aux / score bit-identical to the oracle's random-policy rollout (same Philox action x3 >> 30), and --
+    defaultdict semantics, main.py:16 -- its table must hold exactly the states the oracle visits: the reset boards
+    and the board after each of the 16 steps (no game ends that early), nothing more, nothing twice."""
+    n, k, seed = 1 << 20, 16, 0x2048
+    big = L.g2048_ctx_create(0, n, 1 << 26)
+    assert big, L.g2048_last_error()
+    try:
+        b, a, s = fresh_envs(n, seed)
+        cb, ca, cs = b.copy(), a.copy(), s.copy()
+        c = np.zeros(16, np.int64)
+        ok(L, L.g2048_ctx_rollout_qlearn(big, vp(b), vp(a), vp(s), n, k, 0, 0.1, 0.99, 1.0, seed, 0, 0, vp(c)))
+        visited = [cb.copy()]
+        total = np.zeros(oracle.N_COUNTERS, np.int64)
+        for t in range(k):
+            ct = oracle.rollout_random(cb, ca, cs, 1, 0, seed, t, 0, threads=8)
+            mx = max(total[4], ct[4])
+            total += ct
+            total[4] = mx                                       # the max level is a maximum, not a sum
+            visited.append(cb.copy())
+        assert total[2] == 0                                   # no episode ended: every visited state is in `visited`
+        assert np.array_equal(b, cb) and np.array_equal(a, ca) and np.array_equal(s, cs)
+        assert np.array_equal(c[:6], total[:6])               # steps, valid, episodes, score, max level, reward checksum
+        assert c[7] == 0 and c[8] == 0
+        want = np.unique(np.concatenate(visited))
+        size = L.g2048_ctx_qtable_size(big)
+        assert size == len(want) == c[6]
+        keys, rows = np.zeros(size, np.uint64), np.zeros((size, 4), np.float32)
+        assert L.g2048_ctx_qtable_export(big, vp(keys), vp(rows), size) == size
+        assert np.array_equal(np.sort(keys), want)
+        assert np.isfinite(rows).all()
+    finally:
+        L.g2048_ctx_destroy(big)
+
+
+def late_game_boards(rng, n):
+    """n boards with 7 tiles of levels 5..12 on random cells: nine cells stay empty (no game ends within a few moves)
+    and two such boards -- or any of their successors -- coincide with negligible probability."""
+    b = np.zeros(n, np.uint64)
+    for i in range(n):
+        cells = rng.choice(16, 7, replace=False)
+        lv = rng.randint(5, 13, size=7)
+        v = 0
+        for cell, l in zip(cells, lv):
+            v |= int(l) << (4 * int(cell))
+        b[i] = v
+    return b
+
+
+def test_fused_rollout_collision_free_envs_are_their_own_sequential_runs(L):
+    """20,000 envs teleported to different late-game boards: an env that shares no state with any other env for the
+    next steps must come out of the asynchronous fused rollout (big-launch path: 128-bit insert + update, deferred
+    list, grouped apply) exactly as out of sequential Q-learning on its own (main.py:91-101) -- boards, aux, score and
+    every Q row it touched, bit for bit.  The oracle's trajectories say which envs those are (all but a handful)."""
+    n, k, seed = 20000, 6, 99
+    big = L.g2048_ctx_create(0, n, 1 << 22)
+    assert big, L.g2048_last_error()
+    try:
+        b = late_game_boards(np.random.RandomState(5), n)
+        assert len(np.unique(b)) == n
+        a, s = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+        cb, ca, cs = b.copy(), a.copy(), s.copy()
+        c = np.zeros(16, np.int64)
+        ok(L, L.g2048_ctx_rollout_qlearn(big, vp(b), vp(a), vp(s), n, k, 0, 0.1, 0.99, 0.3, seed, 0, 0, vp(c)))
+        assert c[0] == n * k and c[7] == 0 and c[8] == 0
+        tab = oracle.QTable(1 << 20, f32=True)
+        visited = [cb.copy()]
+        for t in range(k):
+            cc = oracle.rollout_qlearn_seq(cb, ca, cs, tab, 1, 0.1, 0.99, 0.3, 0, seed, t, 0)
+            assert cc[2] == 0                                  # no game ended: no common reset boards
+            visited.append(cb.copy())
+        # states seen by more than one env; an env that ever stood on one is not on its own any more
+        per_env = np.stack(visited, 1)                         # [n][k + 1]
+        pairs = np.unique(np.stack([per_env.ravel(), np.repeat(np.arange(n, dtype=np.uint64), k + 1)], 1), axis=0)
+        keys_seen, owners = np.unique(pairs[:, 0], return_counts=True)
+        shared = keys_seen[owners > 1]
+        clean = ~np.isin(per_env, shared).any(1)
+        assert clean.mean() > 0.99
+        assert np.array_equal(b[clean], cb[clean]) and np.array_equal(a[clean], ca[clean]) and np.array_equal(s[clean], cs[clean])
+        size = L.g2048_ctx_qtable_size(big)
+        keys, rows = np.zeros(size, np.uint64), np.zeros((size, 4), np.float32)
+        assert L.g2048_ctx_qtable_export(big, vp(keys), vp(rows), size) == size
+        order = np.argsort(keys)
+        keys, rows = keys[order], rows[order]
+        wk, wr = tab.export()
+        own = np.unique(per_env[clean])                        # touched by clean envs only (shared states are excluded)
+        gi, wi = np.searchsorted(keys, own), np.searchsorted(wk, own)
+        assert np.array_equal(keys[gi], own) and np.array_equal(wk[wi], own)
+        assert np.array_equal(rows[gi], wr[wi].astype(np.float32))
+        assert len(own) > 2 * n
+    finally:
+        L.g2048_ctx_destroy(big)
+
+
+def test_fused_rollout_applies_every_update_when_all_envs_update_one_value(L):
+    """The worst collision there is: 32,768 envs on the SAME board take the same greedy action (zero row: action 0) in
+    one step, i.e. 32,768 simultaneous updates of one Q value, all with the same target (their next states differ by
+    the spawned tile and are new: max Q = 0).  Sequential Q-learning -- in any order -- gives q_N = T (1 - (1 - lr)^N);
+    every update dropped would lower it by lr e^-2 T = 8e-6 T.  The kernel that skipped an update whenever its
+    compare-and-swap lost (round 1) keeps a handful of them; here LOST must be 0 and the value within 1e-3 of the chain
+    (the long group is folded segment-wise: float32 rounding of the composition, see k_defer_apply)."""
+    n, seed, lr = 1 << 15, 7, 2.0 ** -14
+    big = L.g2048_ctx_create(0, n, 1 << 20)
+    assert big, L.g2048_last_error()
+    try:
+        b0 = late_game_boards(np.random.RandomState(11), 1)[0]
+        assert oracle.move(np.array([b0], np.uint64), np.zeros(1, np.uint8))[1][0]   # action 0 moves this board
+        b = np.full(n, b0, np.uint64)
+        a, s = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+        c = np.zeros(16, np.int64)
+        ok(L, L.g2048_ctx_rollout_qlearn(big, vp(b), vp(a), vp(s), n, 1, 0, lr, 0.99, 0.0, seed, 0, 0, vp(c)))
+        assert c[0] == n and c[8] == 0 and c[9] > n // 2       # nearly every first attempt loses its race
+        one = np.array([b0], np.uint64)
+        reward, flags, _, _ = oracle.env_step(one.copy(), np.array([oracle.AUX_INIT], np.uint64), np.zeros(1, np.int32),
+                                              np.zeros(1, np.uint8), None, 0, seed, 0, 0)
+        target = np.float32(reward[0])
+        q = np.float32(0)
+        for _ in range(n):
+            q = np.float32(q + np.float32(np.float32(lr) * np.float32(target - q)))
+        rows, found = np.zeros((1, 4), np.float32), np.zeros(1, np.uint8)
+        ok(L, L.g2048_ctx_qtable_lookup(big, vp(one), 1, vp(rows), vp(found), 0))
+        assert found[0] and abs(float(target)) > 0.01
+        assert abs(rows[0, 0] - q) <= 1e-3 * abs(q), (rows[0], q, target)
+        assert (rows[0, 1:] == 0).all()
+        assert L.g2048_ctx_qtable_size(big) == c[6] == 1 + len(np.unique(b))
     finally:
         L.g2048_ctx_destroy(big)
 
