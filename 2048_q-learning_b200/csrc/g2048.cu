@@ -67,6 +67,7 @@ struct DeviceState {
     // launches on different streams do not share one; grown on demand
     struct DeferSet { void* buf = nullptr; size_t bytes = 0; } defer[4];
     unsigned defer_next = 0;
+    int* abort_flag = nullptr;         // device int, set by a g2048_peer_barrier that timed out: peer record lists are not consumed any more
 };
 constexpr unsigned kQueueSlots = 256;
 constexpr int64_t kDeferMinEnvs = 16384;   // fused rollouts of fewer envs settle lost races in place (no list)
@@ -695,8 +696,10 @@ struct RecordLists {
 // (system-scope loads, never cached in L1), finds-or-inserts the state in ITS replica and writes the sort key +
 // target for the deterministic apply.  Consecutive threads read consecutive records: 512 B per warp over NVLink.
 __global__ void __launch_bounds__(256)
-k_peer_records_to_sortkeys(Slot* tab, u64 mask, RecordLists R, long long n, u64* sortkey, float* target) {
+k_peer_records_to_sortkeys(Slot* tab, u64 mask, RecordLists R, long long n, u64* sortkey, float* target, const int* abort_flag) {
+    const bool aborted = abort_flag && *(const volatile int*)abort_flag != 0;   // a peer never reached the barrier: its list is not valid
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (aborted) { sortkey[i] = ~0ull; target[i] = 0.f; continue; }
         int j = 0;
         while (j + 1 < R.n_lists && i >= R.end[j]) ++j;
         long long local = i - (j ? R.end[j - 1] : 0);
@@ -712,8 +715,10 @@ k_peer_records_to_sortkeys(Slot* tab, u64 mask, RecordLists R, long long n, u64*
 // owner-computes form: the owner pulls its lists out of every rank's memory (NVLink peer reads, coalesced) into the
 // sort buffers; the records already carry the sort key
 __global__ void __launch_bounds__(256)
-k_gather_owned(RecordLists R, long long n, u64* sortkey, float* target) {
+k_gather_owned(RecordLists R, long long n, u64* sortkey, float* target, const int* abort_flag) {
+    const bool aborted = abort_flag && *(const volatile int*)abort_flag != 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (aborted) { sortkey[i] = ~0ull; target[i] = 0.f; continue; }
         int j = 0;
         while (j + 1 < R.n_lists && i >= R.end[j]) ++j;
         long long local = i - (j ? R.end[j - 1] : 0);
@@ -727,7 +732,7 @@ k_gather_owned(RecordLists R, long long n, u64* sortkey, float* target) {
 // peer (release, system scope) and waits until all of its own flags reached `epoch` (acquire).  Epochs only grow,
 // so the flags never need a reset.  A peer that never arrives is reported after `timeout_ns` instead of hanging.
 struct PeerFlags { u64* ptr[G2048_MAX_PEERS]; };
-__global__ void k_peer_barrier(PeerFlags F, int rank, int world, u64 epoch, u64 timeout_ns, int* timed_out) {
+__global__ void k_peer_barrier(PeerFlags F, int rank, int world, u64 epoch, u64 timeout_ns, int* timed_out, int* abort_flag) {
     int t = threadIdx.x;
     if (t >= world) return;
     __threadfence_system();
@@ -739,7 +744,11 @@ __global__ void k_peer_barrier(PeerFlags F, int rank, int world, u64 epoch, u64 
         if (v >= epoch) break;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (now - t0 > timeout_ns) {
-            if (timed_out) atomicExch(timed_out, 1 + t);
+            if (abort_flag) *(volatile int*)abort_flag = 1 + t;   // what the apply kernels of this device look at
+            if (timed_out) {                       // the caller's copy, device or pinned host memory: a plain system-scope store
+                *(volatile int*)timed_out = 1 + t;
+                __threadfence_system();
+            }
             break;
         }
         __nanosleep(200);
@@ -897,9 +906,20 @@ __device__ __forceinline__ void defer_bucket_range(const u32* boff, const u32* s
     begin = sums[b >> 10] + boff[b];
     end = (b + 1 == kDeferBuckets) ? sums[256] : sums[(b + 1) >> 10] + boff[b + 1];
 }
+template <class TAB>
+__device__ __forceinline__ u32 load_q_bits(const float* p) {   // coherent at L2 / at the owner GPU
+    u32 v;
+    if (TAB::kSysLoad) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <class TAB>
 __global__ void __launch_bounds__(256)
-k_defer_apply(Slot* tab, u64* key, const float* target, const u32* index, const u32* boff, const u32* sums, float lr,
-              const u32* work, int long_blocks) {
+k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, const u32* index, const u32* boff, const u32* sums,
+              float lr, const u32* work, int long_blocks) {
+    __shared__ Slot* shard_base[G2048_MAX_PEERS];
+    const auto tab = table.view(shard_base);
+    using VIEW = decltype(tab);
     if ((int)blockIdx.x >= long_blocks) {
         const u32 b = (blockIdx.x - long_blocks) * blockDim.x + threadIdx.x;
         if (b >= kDeferBuckets) return;
@@ -909,8 +929,8 @@ k_defer_apply(Slot* tab, u64* key, const float* target, const u32* index, const 
         for (u32 r = begin; r < end; ++r) {
             const u64 k = key[r];
             if (k == ~0ull) continue;                  // applied together with an earlier record of the same address
-            float* qp = &tab[k >> 2].q[k & 3];
-            u32 seen = __float_as_uint(__ldcg(qp));
+            float* qp = &tab.at(k >> 2)->q[k & 3];
+            u32 seen = load_q_bits<VIEW>(qp);
             for (;;) {
                 // the records of this address in the order of the list (an env's own updates of one value keep their
                 // order: a warp appends in time order): repeatedly the smallest list index above the last one
@@ -924,7 +944,7 @@ k_defer_apply(Slot* tab, u64* key, const float* target, const u32* index, const 
                     q = td_apply(q, lr, target[best_t]);
                     last = (long long)best;
                 }
-                const u32 old = atomicCAS(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
+                const u32 old = cas32<VIEW::kSys>(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
                 if (old == seen) break;
                 seen = old;
             }
@@ -957,8 +977,8 @@ k_defer_apply(Slot* tab, u64* key, const float* target, const u32* index, const 
                 r += 32;
             }
             if (r >= end) break;
-            float* qp = &tab[k >> 2].q[k & 3];
-            u32 seen = __float_as_uint(__ldcg(qp));
+            float* qp = &tab.at(k >> 2)->q[k & 3];
+            u32 seen = load_q_bits<VIEW>(qp);
             if (end - r >= kFoldBucket) {
                 // Thousands of records on one value (the action a popular start state takes): a chain of that length
                 // would be the whole phase.  Every lane folds the records r + lane, r + lane + 32, ... into its own map
@@ -975,7 +995,7 @@ k_defer_apply(Slot* tab, u64* key, const float* target, const u32* index, const 
                     for (int l = 0; l < 32; ++l)
                         q = __fadd_rn(__fmul_rn(__shfl_sync(0xFFFFFFFFu, A, l), q), __shfl_sync(0xFFFFFFFFu, B, l));
                     u32 old = 0;
-                    if (lane == 0) old = atomicCAS(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
+                    if (lane == 0) old = cas32<VIEW::kSys>(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
                     old = __shfl_sync(0xFFFFFFFFu, old, 0);
                     if (old == seen) break;
                     seen = old;
@@ -1005,7 +1025,7 @@ k_defer_apply(Slot* tab, u64* key, const float* target, const u32* index, const 
                     tt = tt_n;
                 }
                 u32 old = 0;
-                if (lane == 0) old = atomicCAS(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
+                if (lane == 0) old = cas32<VIEW::kSys>(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
                 old = __shfl_sync(0xFFFFFFFFu, old, 0);
                 if (old == seen) break;
                 seen = old;
@@ -1313,6 +1333,8 @@ G2048_API int g2048_init(int device) {
                       (const double*)ri, (const double*)pn};
     CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaMalloc(&d.queue, kQueueSlots * sizeof(unsigned long long)));
+    CK(cudaMalloc(&d.abort_flag, sizeof(int)));
+    CK(cudaMemset(d.abort_flag, 0, sizeof(int)));
     CK(cudaFuncSetAttribute(k_rollout_random<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_rollout_random<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_env_step<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
@@ -1500,10 +1522,6 @@ size_t scratch_bytes(int64_t n);
 int carve(void* scratch, size_t bytes, int64_t n, Scratch& s);
 int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, float lr, int mode, cudaStream_t st,
                   int kshift = 0);
-inline Slot* local_slots(const LocalTable& t) { return t.base; }
-inline Slot* local_slots(const ShardedTable&) { return nullptr; }
-inline uint64_t table_slots(const LocalTable& t) { return t.mask + 1; }
-inline uint64_t table_slots(const ShardedTable& t) { return t.mask + 1; }
 
 struct DeferBuffers;
 template <class TAB>
@@ -1686,7 +1704,8 @@ int64_t deferred_capacity(int64_t n, int64_t k_steps) {
     while (cap < (1 << 23) && (long double)cap < want) cap <<= 1;
     return cap;
 }
-int apply_deferred(DeviceState* D, Slot* tab, const DeferBuffers& B, float lr, cudaStream_t st) {
+template <class TAB>
+int apply_deferred(DeviceState* D, const TAB& tab, const DeferBuffers& B, float lr, cudaStream_t st) {
     const int g = grid_for(B.cap, 256, D->sm_count);
     k_defer_count<<<g, 256, 0, st>>>(B.key, B.count, (unsigned long long)B.cap, B.pos, B.boff);
     k_defer_scan<<<kDeferBuckets / 1024, 1024, 0, st>>>(B.boff, B.sums, B.work);
@@ -1694,8 +1713,8 @@ int apply_deferred(DeviceState* D, Slot* tab, const DeferBuffers& B, float lr, c
     k_defer_scatter<<<g, 256, 0, st>>>(B.key, B.target, B.count, (unsigned long long)B.cap, B.pos, B.boff, B.sums, B.key_out,
                                        B.target_out, B.index_out);
     const int long_blocks = D->sm_count * 4;
-    k_defer_apply<<<long_blocks + kDeferBuckets / 256, 256, 0, st>>>(tab, B.key_out, B.target_out, B.index_out, B.boff, B.sums,
-                                                                      lr, B.work, long_blocks);
+    k_defer_apply<TAB><<<long_blocks + kDeferBuckets / 256, 256, 0, st>>>(tab, B.key_out, B.target_out, B.index_out, B.boff,
+                                                                           B.sums, lr, B.work, long_blocks);
     LAUNCH_CHECK("apply_deferred");
     return 0;
 }
@@ -1714,14 +1733,14 @@ int launch_rollout_qlearn(DeviceState* D, const TAB& tab, uint64_t* boards, uint
         queue = D->queue + (D->queue_next++ % kQueueSlots);
     }
     CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), S(stream)));
-    // big launches on a local table: lost races go to a list that is applied after the rollout (see the kernel)
+    // big launches: lost races go to a list that is applied after the rollout (see the kernel)
     // (shared_list: the caller runs several launches into one list and applies it itself)
     Deferred defer{};
     DeferBuffers db{};
     int64_t cap = 0;
     if (shared_list) {
         defer = Deferred{shared_list->key, shared_list->target, shared_list->count, (unsigned long long)shared_list->cap};
-    } else if (n >= kDeferMinEnvs && local_slots(tab)) {
+    } else if (n >= kDeferMinEnvs) {
         cap = deferred_capacity(n, k_steps);
         int rc = deferred_list(D, cap, S(stream), db);
         if (rc) return rc;
@@ -1735,7 +1754,7 @@ int launch_rollout_qlearn(DeviceState* D, const TAB& tab, uint64_t* boards, uint
     else { if (smem_lut) LAUNCH_RQ(1, true); else LAUNCH_RQ(1, false); }
 #undef LAUNCH_RQ
     LAUNCH_CHECK("k_rollout_qlearn");
-    if (cap) return apply_deferred(D, local_slots(tab), db, lr, S(stream));
+    if (cap) return apply_deferred(D, tab, db, lr, S(stream));
     return 0;
 }
 }  // namespace
@@ -1813,7 +1832,7 @@ G2048_API int g2048_qtable_apply_records(void* table, uint64_t capacity, const g
     int rc = carve(scratch, scratch_bytes_, n, sc);
     if (rc) return rc;
     k_peer_records_to_sortkeys<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>((Slot*)table, capacity - 1, R, n,
-                                                                                      sc.key_in, sc.val_in);
+                                                                                      sc.key_in, sc.val_in, D->abort_flag);
     LAUNCH_CHECK("k_peer_records_to_sortkeys");
     return apply_records(D, (Slot*)table, capacity, sc, n, lr, mode, S(stream));
 }
@@ -1873,7 +1892,7 @@ G2048_API int g2048_qtable_apply_owned(void* shard, uint64_t slots_per_shard, co
     Scratch sc{};
     int rc = carve(scratch, scratch_bytes_, n, sc);
     if (rc) return rc;
-    k_gather_owned<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>(R, n, sc.key_in, sc.val_in);
+    k_gather_owned<<<grid_for(n, 256, D->sm_count), 256, 0, S(stream)>>>(R, n, sc.key_in, sc.val_in, D->abort_flag);
     LAUNCH_CHECK("k_gather_owned");
     return apply_records(D, (Slot*)shard, slots_per_shard, sc, n, lr, G2048_MODE_DETERMINISTIC, S(stream), idx_bits);
 }
@@ -1934,7 +1953,10 @@ G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, ui
         if (!flags[j]) return fail(G2048_ERR_ARG, "g2048_peer_barrier: null flag pointer");
         F.ptr[j] = (u64*)flags[j];
     }
-    k_peer_barrier<<<1, 32, 0, S(stream)>>>(F, rank, world, epoch, timeout_ns ? timeout_ns : 5000000000ull, timed_out);
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    int* abort_flag = (dev >= 0 && dev < kMaxDevices && g_dev[dev].ready) ? g_dev[dev].abort_flag : nullptr;
+    k_peer_barrier<<<1, 32, 0, S(stream)>>>(F, rank, world, epoch, timeout_ns ? timeout_ns : 5000000000ull, timed_out, abort_flag);
     LAUNCH_CHECK("k_peer_barrier");
     return 0;
 }
@@ -2275,7 +2297,7 @@ static int ctx_rollout(g2048_ctx* c, uint64_t* boards, uint64_t* aux, int32_t* s
     }
     if (shared_list) {
         for (int j = 0; j < 3; ++j) CK(cudaStreamWaitEvent(st, c->ev_kernel[j], 0));
-        RC(apply_deferred(D, (Slot*)c->table, db, lr, st));
+        RC(apply_deferred(D, LocalTable{(Slot*)c->table, c->capacity - 1}, db, lr, st));
     }
     if (pipelined)
         for (int j = 0; j < 3; ++j) {

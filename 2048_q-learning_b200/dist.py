@@ -103,8 +103,9 @@ class PeerRecordBuffers:
         nbytes = self.FLAG_BYTES + 2 * self.slot_bytes
         self._mine, self.base, self._opened = _share_device_memory(lib, device, nbytes, group)
         self._flags = (ctypes.c_void_p * self.world)(*self.base)
-        with torch.cuda.device(device):
-            self.timed_out = torch.zeros(1, dtype=torch.int32, device=device)
+        # the barrier's time-out flag lives in pinned host memory: the kernel stores into it, the host reads it at every
+        # step without a synchronisation, and the apply kernels look at it before they consume a peer's records
+        self.timed_out = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.epoch = 0
 
     def _check(self, rc, what):
@@ -123,9 +124,11 @@ class PeerRecordBuffers:
                                                     torch.cuda.current_stream().cuda_stream), "g2048_peer_barrier")
 
     def check_timeout(self):
-        v = int(self.timed_out.item())
+        """Raises once a barrier of this rank has timed out (a peer stalled for more than the time-out): the exchange
+        is over -- the device side already ignores the peers' records (g2048_peer_barrier in include/g2048.h)."""
+        v = int(self.timed_out[0])
         if v:
-            raise RuntimeError(f"peer barrier timed out waiting for rank {v - 1}")
+            raise RuntimeError(f"peer barrier timed out waiting for rank {v - 1}: the ranks are no longer in step")
 
     def close(self):
         _unshare_device_memory(self.lib, self.device, self._mine, self._opened, self.group)
@@ -169,6 +172,7 @@ class ShardedQLearning:
     def step(self):
         if self.transport == "peer":
             p, slot = self.peers, self.t & 1
+            p.check_timeout()                       # a barrier of an earlier step gave up: stop before anything else is applied
             self.engine.emit_records(p.records(self.rank, slot))
             p.barrier()
             self.engine.apply_records([p.records(r, slot) for r in range(self.world)], self.sizes)
@@ -328,7 +332,7 @@ class OwnerComputesQLearning:
         self._mine, self.base, self._opened = _share_device_memory(self.lib, self.device, nbytes, group)
         with torch.cuda.device(self.device):
             self._flags = (ctypes.c_void_p * self.world)(*self.base)
-            self.timed_out = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.timed_out = torch.zeros(1, dtype=torch.int32).pin_memory()   # see PeerRecordBuffers
             self._scratch = None
             self._carry_slot = torch.zeros(env.n, dtype=torch.int32, device=self.device) if self.window > 1 else None
             self._carry_row = torch.zeros((env.n, 4), dtype=torch.float32, device=self.device) if self.window > 1 else None
@@ -353,6 +357,7 @@ class OwnerComputesQLearning:
         ct, env, sh, slot = self._ct, self.env, self.shared, self.t & 1
         st = torch.cuda.current_stream().cuda_stream
         total = 0
+        self._check_timeout()
         with torch.cuda.device(self.device):
             if self.k == 0:
                 self._check(self.lib.g2048_peer_memset(self._counts(self.rank, slot), 0, 128, st), "g2048_peer_memset")
@@ -388,6 +393,7 @@ class OwnerComputesQLearning:
         src = (ct.c_void_p * self.world)(*[self._counts(r, slot) + 8 * self.rank for r in range(self.world)])
         host = (ct.c_uint64 * self.world)()
         self._check(self.lib.g2048_peer_read_u64(src, self.world, host, st), "g2048_peer_read_u64")
+        self._check_timeout()                               # (the read synchronised the stream: the barrier is over)
         counts = (ct.c_int64 * self.world)(*[int(x) for x in host])
         total = sum(int(x) for x in host)
         need = int(self.lib.g2048_qlearn_scratch_bytes(max(total, 1)))
@@ -400,15 +406,20 @@ class OwnerComputesQLearning:
         self._barrier()                                     # all shards updated before anyone reads them again
         return total
 
-    def close(self):
-        self.flush()
-        with torch.cuda.device(self.device):
-            torch.cuda.synchronize()
-            v = int(self.timed_out.item())
-        _unshare_device_memory(self.lib, self.device, self._mine, self._opened, self.group)
-        self._mine, self._opened = None, []
+    def _check_timeout(self):
+        v = int(self.timed_out[0])
         if v:
-            raise RuntimeError(f"peer barrier timed out waiting for rank {v - 1}")
+            raise RuntimeError(f"peer barrier timed out waiting for rank {v - 1}: the ranks are no longer in step")
+
+    def close(self):
+        try:
+            self.flush()
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+            self._check_timeout()
+        finally:
+            _unshare_device_memory(self.lib, self.device, self._mine, self._opened, self.group)
+            self._mine, self._opened = None, []
 
 
 class GradientAllReduce:

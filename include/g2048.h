@@ -273,8 +273,10 @@ G2048_API int g2048_peer_free(void* dev_ptr);
 /* Stream-ordered barrier between the `world` GPUs: flags[j] (HOST array of device pointers) = rank j's flag
  * block (uint64[world], zero at start, in peer memory); epoch must grow by one per barrier.  Work enqueued
  * before it on every rank is visible to work enqueued after it on every rank.  If a peer does not arrive within
- * timeout_ns (0 = 5 s), *timed_out (device int, may be NULL) is set to 1 + the missing rank and the kernel
- * returns instead of hanging. */
+ * timeout_ns (0 = 5 s), *timed_out (an int in device or pinned host memory, may be NULL) is set to 1 + the missing
+ * rank and the kernel returns instead of hanging.  A time-out is fatal for the exchange: while the flag is set,
+ * g2048_qtable_apply_records and g2048_qtable_apply_owned on this device apply NOTHING (the peers' lists are not
+ * valid), and the caller must stop (dist.py raises at the step). */
 G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, uint64_t epoch, uint64_t timeout_ns,
                                  int* timed_out, void* stream);
 
