@@ -6,16 +6,20 @@
 
 Workload (BASELINE.json configs[2], "C3"): 2^20 envs per GPU, penalty-flavour env, epsilon-greedy tabular
 Q-learning (alpha 0.1, gamma 0.99, epsilon 0.1, Philox seed 0x2048) on an open-addressing hash Q-table in
-HBM.  One bench "step" = one fused launch of k_rollout_qlearn advancing every env by ENV_STEPS_PER_LAUNCH
-steps (each env step = choose_action + env.step + update_q_value, i.e. one Q-update).  Multi-GPU = weak
-scaling: every rank runs its own env shard (global env ids) against its own table replica, no data-path
-collective (DESIGN.md "Multi-GPU").
+HBM.  One bench "step" = one fused call g2048_rollout_qlearn advancing every env by ENV_STEPS_PER_LAUNCH
+steps (each env step = choose_action + env.step + update_q_value, i.e. one Q-update; every update is applied,
+`lost_update_fraction` is 0).  Multi-GPU `value` = weak scaling: every rank runs its own env shard (global env
+ids) against its own table replica, no data-path collective; with N > 1 the same line carries `shared_learning`:
+BASELINE configs[3] (2^23 envs in total learning ONE table across the GPUs: exact owner-computes exchange every step
+and every 16 steps, and the asynchronous table sharded over NVLink), each with its table digest compared with the
+1-GPU run (DESIGN.md "Multi-GPU").
 
 Prints ONE JSON line (rank 0).  `value`: device-resident throughput (CUDA events, max over ranks);
 `e2e`: the same metric through the host-buffer C-ABI call g2048_ctx_rollout_qlearn with pinned HOST buffers,
-host<->device copies inside the timed region; `roofline`: the fused kernel against the measured HBM peak
-(32 algorithmic bytes per env step); `cpu_baseline`: the C oracle port on the host cores (bounded sample).
-`--impl reference` times that CPU port as the reference arm.
+host<->device copies inside the timed region; `roofline`: the fused call against the measured HBM peak
+(32 algorithmic bytes per env step); `synchronous_step`: the exact batched step (atomic and deterministic apply) at
+the same size; `cpu_baseline`: the C oracle port on the host cores (bounded sample of the same training run).
+`--impl reference` times that same CPU run as the reference arm (one definition: cpu_reference()).
 
 Optional side measurements (extras of the same line): --exchange [--exchange-envs M] the exact synchronous mode across
 GPUs (replicated tables over NCCL / NVLink peer memory, owner-computes on one sharded table, every step and every 16
@@ -40,7 +44,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_ENVS_PER_GPU = 1 << 20
-ENV_STEPS_PER_LAUNCH = 16
+ENV_STEPS_PER_LAUNCH = 32
 LR, GAMMA, EPS, SEED = 0.1, 0.99, 0.1, 0x2048
 ALGO_BYTES_PER_STEP = 32        # key(s') 8 + row(s') 16 + Q(s,a) 4 R + 4 W, slot of s carried
 ALGO_BYTES_PER_UPDATE = 40      # stand-alone update API: + key(s) 8
@@ -67,10 +71,10 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the fused kernel from the committed
-    ncu --set full capture (profiles/r01_traffic.json), or None."""
+    """DRAM bytes per env step (dram__bytes_read.sum + dram__bytes_write.sum of k_rollout_qlearn / its env steps) from
+    the committed ncu --set full capture (profiles/r02_traffic.json), or None."""
     try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_launch"])
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["dram_bytes_per_env_step"])
     except Exception:
         return None
 
@@ -108,7 +112,7 @@ def rmw_peak():
 
 def ncu_dram_ops_per_step():
     try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_random_ops_per_env_step"])
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["dram_random_ops_per_env_step"])
     except Exception:
         return None
 
@@ -210,64 +214,54 @@ def fresh_host_envs(L, ctx, n, base, pinned):
     return (b, a, s), (pb, pa, ps)
 
 
-def cpu_baseline(n_threads, seconds=4.0, repeats=3):
-    """The C oracle's sequential-semantics Q-learning rollout, one env shard + one table per host thread."""
+CPU_ENVS_PER_THREAD = 2048
+
+
+def cpu_reference(threads, steps, warmup, k):
+    """THE CPU baseline, one definition for `cpu_baseline` (main line) and `--impl reference`: the C oracle's
+    sequential-semantics Q-learning (oracle/g2048_oracle.c, main.py:91-101 env after env) as a training run like the
+    GPU arm's -- `threads` host threads, each with its own env shard (2,048 envs) and its own PERSISTENT table (the
+    most generous CPU figure: no sharing, no locks), k env steps per bench step, `warmup` untimed steps first."""
     import oracle
     oracle.load()
-    per_thread_envs = 2048
+    n = CPU_ENVS_PER_THREAD * threads
+    b = np.zeros(n, np.uint64)
+    oracle.env_reset(b, None, None, None, seed=SEED)
+    a, s = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+    tables = [oracle.QTable(1 << 22, f32=True) for _ in range(threads)]
+    for w in range(warmup):
+        oracle.rollout_qlearn_mt_tables(b, a, s, k, LR, GAMMA, EPS, tables, 0, SEED, w * k, 0)
+    total, t0 = 0, time.perf_counter()
+    for i in range(steps):
+        total += int(oracle.rollout_qlearn_mt_tables(b, a, s, k, LR, GAMMA, EPS, tables, 0, SEED, (warmup + i) * k, 0)[0])
+    dt = time.perf_counter() - t0
+    sample = (f"C oracle port (oracle/g2048_oracle.c), {n} envs ({CPU_ENVS_PER_THREAD}/thread) x {k} env steps per bench "
+              f"step, {threads} threads each with its own persistent 2^22-slot table, {warmup} warm-up + {steps} timed steps")
+    return {"value": total / dt, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+            "host_cpus": os.cpu_count(), "ms_per_step": dt / max(steps, 1) * 1e3}
 
-    def run(k):
-        n = per_thread_envs * n_threads
-        b = np.zeros(n, np.uint64)
-        oracle.env_reset(b, None, None, None, seed=SEED)
-        a, s = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
-        t0 = time.perf_counter()
-        c = oracle.rollout_qlearn_mt(b, a, s, k, LR, GAMMA, EPS, 1 << 23, n_threads, 0, SEED, 0, 0)
-        return int(c[0]), time.perf_counter() - t0
 
-    steps, dt = run(64)
-    k = int(max(64, min(2048, 64 * seconds / max(dt, 1e-3))))
-    best = 0.0
-    for _ in range(repeats):
-        steps, dt = run(k)
-        best = max(best, steps / dt)
-    return {"value": best, "unit": UNIT, "cores": n_threads, "kind": "port",
-            "sample": f"C oracle port (oracle/g2048_oracle.c), {per_thread_envs} envs x {k} steps per thread, "
-                      f"{n_threads} threads each with its own table, best of {repeats}",
-            "host_cpus": os.cpu_count()}
+def cpu_baseline(n_threads):
+    """Bounded sample for the main line (about 10 bench steps of the same run --impl reference times in full)."""
+    return cpu_reference(n_threads, steps=10, warmup=2, k=ENV_STEPS_PER_LAUNCH)
 
 
 def run_reference(args, rank, world):
     """Reference arm: the CPU restatement of the reference path (the reference itself is pure Python and does
-    not exist on the GPU box), all host threads, one bounded sample of the C3 workload per step."""
+    not exist on the GPU box), all host threads, the bench step of cpu_reference()."""
     if rank != 0:
         return
-    import oracle
-    oracle.load()
     threads = os.cpu_count() or 1
-    per_thread_envs = 8192
-    n = per_thread_envs * threads
-    b = np.zeros(n, np.uint64)
-    oracle.env_reset(b, None, None, None, seed=SEED)
-    a, s = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
     k = ENV_STEPS_PER_LAUNCH
-    for w in range(args.warmup):
-        oracle.rollout_qlearn_mt(b, a, s, k, LR, GAMMA, EPS, 1 << 20, threads, 0, SEED, w * k, 0)
-    t0 = time.perf_counter()
-    total = 0
-    for i in range(args.steps):
-        c = oracle.rollout_qlearn_mt(b, a, s, k, LR, GAMMA, EPS, 1 << 20, threads, 0, SEED, (args.warmup + i) * k, 0)
-        total += int(c[0])
-    dt = time.perf_counter() - t0
-    v = total / dt
-    sample = (f"C oracle port, {n} envs ({per_thread_envs}/thread) x {k} steps per bench step, {threads} threads, "
-              f"fresh per-thread tables each step")
+    r = cpu_reference(threads, args.steps, args.warmup, k)
+    v = r["value"]
+    base = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]}
     emit_result({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 boards / f32 Q rows", "data": "synthetic",
-        "config": {"workload": workload_name(N_ENVS_PER_GPU, k), "cpu_sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(N_ENVS_PER_GPU, k), "cpu_sample": r["sample"]},
+        "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -306,6 +300,9 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU)
     ap.add_argument("--eps", type=float, default=EPS, help="fixed exploration rate (BASELINE config 3 quotes 0.1 and 0.95)")
     ap.add_argument("--no-extras", action="store_true", help="skip the explanatory side measurements")
+    ap.add_argument("--no-shared-learning", action="store_true",
+                    help="N > 1: skip BASELINE config 4 (2^23 envs learning one table across the GPUs)")
+    ap.add_argument("--shared-envs", type=int, default=1 << 23, help="total envs of the shared-learning measurement")
     ap.add_argument("--dqn", action="store_true",
                     help="also time BASELINE config 5: 65,536 nopenalty envs/GPU with the 197 M-parameter DQN forward in the loop")
     ap.add_argument("--exchange", action="store_true",
@@ -421,7 +418,8 @@ def main():
                    "load_factor_end": int(c[6]) / cap, "dropped": int(c[7]), "lost_updates": int(c[8]), "retried_updates": int(c[9]),
                    "retried_update_fraction": int(c[9]) / max(int(c[0]), 1),
                    "lost_update_fraction": int(c[8]) / max(int(c[0]), 1),
-                   "new_state_fraction": int(c[6]) / max(int(c[0]), 1)}
+                   "new_state_fraction": int(c[6]) / max(int(c[0]), 1),
+                   "valid_fraction": int(c[1]) / max(int(c[0]), 1)}
 
     # ---- arm 2: end to end through the host-buffer C-ABI call (pinned host memory) --------------------------
     assert L.g2048_ctx_qtable_clear(ctx) == 0
@@ -448,6 +446,14 @@ def main():
     for p in pins:
         L.g2048_host_free(p)
 
+    sync_step = synchronous_step_measurement(L, torch, dev, n, base, stream) if rank == 0 else None
+    shared_learning = None
+    if world > 1 and not args.no_shared_learning:
+        L.g2048_ctx_destroy(ctx)                   # the 64 GiB replica table makes room for the shared tables
+        ctx = None
+        torch.cuda.empty_cache()
+        shared_learning = shared_learning_measurement(torch, dist, g2048, dev, rank, world, args.shared_envs,
+                                                      max_over_ranks, barrier)
     extras = {}
     if args.exchange:
         sync = sync_exchange_measurement(torch, dist, g2048, dev, rank, world, args.exchange_envs or min(n, 1 << 20),
@@ -464,7 +470,7 @@ def main():
             extras["dqn_data_parallel_replay"] = dp
     if args.dqn and rank == 0:
         extras["dqn_in_the_loop"] = dqn_measurement(torch, g2048, dev)
-    if not args.no_extras and rank == 0:
+    if not args.no_extras and rank == 0 and ctx is not None:
         extras = dict(extras, **side_measurements(L, torch, dev, ctx, table, cap, n, base, stream, peak))
         rnd = random_access_peak()
         if rnd:
@@ -496,24 +502,215 @@ def main():
             "ms_per_step": elapsed_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 boards / f64 reward / f32 Q rows", "data": "synthetic",
             "config": {"workload": workload_name(n, k), "envs_per_gpu": n, "env_steps_per_launch": k, "alpha": LR,
-                       "gamma": GAMMA, "epsilon": EPS, "seed": SEED, "flavour": "penalty", "mode": "fused async atomic",
+                       "gamma": GAMMA, "epsilon": EPS, "seed": SEED, "flavour": "penalty",
+                       "mode": "fused asynchronous rollout, every update applied (lost races deferred to a grouped apply inside the call)",
                        "parallelism": f"env shards x{world}, table replica per GPU, no collective",
                        "l2": f"Q-table {cap * 32 / 2**30:.0f} GiB >> 126 MB L2 (random 32 B sectors); boards live in registers"},
-            "q_updates_per_sec": value, "table": table_stats,
+            "q_updates_per_sec": value * (1.0 - table_stats["lost_update_fraction"]),
+            "lost_update_fraction": table_stats["lost_update_fraction"],
+            "retried_update_fraction": table_stats["retried_update_fraction"], "table": table_stats,
+            "synchronous_step": sync_step, "shared_learning": shared_learning,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_rollout_qlearn<penalty>", "kernel_ms": kernel_ms,
+                         "traffic": (traffic * n * k) if traffic else None, "kernel": "k_rollout_qlearn<penalty>",
+                         "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "peak_source": peak_src,
-                         "note": "achieved = 32 algorithmic B/env-step / kernel time; every random slot access really moves a "
-                                 "128 B line (traffic = ncu DRAM bytes per launch), and HBM serves ~36 G such line "
-                                 "fetches/s (extras.hbm_random_access): that, not the streaming peak, bounds the table"},
+                         "request_bound": {"table_visits_per_sec": 17.5e9, "env_steps_per_sec": 17.5e9 / table_stats["valid_fraction"],
+                                           "frac_of_bound": value / world * table_stats["valid_fraction"] / 17.5e9,
+                                           "source": "tools/membench5.cu: random 32 B load that misses L2 + ONE write-type request"},
+                         "note": "achieved = 32 algorithmic B/env-step / duration of the whole call (k_rollout_qlearn = 91 % of "
+                                 "it, the deferred-update kernels the rest; CUDA events around the call).  The memory system "
+                                 "charges per request, not per byte (profiles/r02_membench.txt): a table visit of one load + "
+                                 "one write-type request runs at 17.5 G/s at most = 8.6 % of the streaming peak at 32 B; "
+                                 "traffic = ncu DRAM bytes (64 B fill + 32 B write-back per visit)"},
             "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary(),
             "cpu_baseline": cpu_baseline(os.cpu_count() or 1) if world == 1 else None,
             "extras": extras,
         }
         emit_result(out)
-    L.g2048_ctx_destroy(ctx)
+    if ctx is not None:
+        L.g2048_ctx_destroy(ctx)
     if world > 1:
         dist.destroy_process_group()
+
+
+def synchronous_step_measurement(L, torch, dev, n, base, stream, warm=64, steps=24):
+    """The exact synchronous batched step g2048_qlearn_step (all envs choose and bootstrap on the
+    table as it stands at step start; duplicates of one (state, action) applied one after another) at the headline
+    size, both apply modes, mid-game (after `warm` steps: the envs have left the 480 start boards)."""
+    out = {}
+    cap = 1 << 28
+    need = int(L.g2048_qlearn_scratch_bytes(n))
+    scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    table = torch.zeros(cap * 4, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(16, dtype=torch.int64, device=dev)
+    for mode, name in ((0, "atomic"), (1, "deterministic")):
+        table.zero_()
+        b = torch.zeros(n, dtype=torch.int64, device=dev)
+        a = torch.full((n,), 0x000000000000FF01, dtype=torch.int64, device=dev)
+        s = torch.zeros(n, dtype=torch.int32, device=dev)
+        assert L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n, SEED, 0, base, stream) == 0
+
+        def step(t):
+            rc = L.g2048_qlearn_step(b.data_ptr(), a.data_ptr(), s.data_ptr(), table.data_ptr(), cap, n, 0, LR, GAMMA, EPS,
+                                     mode, 1, SEED, t, base, cnt.data_ptr(), None, None, None, scratch.data_ptr(), need, stream)
+            assert rc == 0, L.g2048_last_error()
+        for t in range(warm):
+            step(t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(steps):
+            step(warm + t)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"env_steps_per_sec": n / ms * 1e3, "ms_per_step": ms, "envs": n,
+                     "parity": "bit-exact vs the oracle (tests/test_gpu_agent.py)" if mode else
+                               "float32 tolerance / hull of {old value, targets} vs the oracle (tests/test_gpu_parity.py)"}
+    del table, scratch
+    torch.cuda.empty_cache()
+    return out
+
+
+def device_table_digest(L, torch, dev, table_ptr, slots, stream):
+    """Order-independent exact digest of a table (or shard) computed on the device: [rows with a non-zero Q value, sum
+    of their float32 bit patterns, sum of the low words of their keys].  Replicas and shards differ only in untouched
+    zero rows, which are left out."""
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    assert L.g2048_qtable_size(table_ptr, slots, cnt.data_ptr(), stream) == 0, L.g2048_last_error()
+    m = int(cnt.item())
+    keys = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    rows = torch.empty((max(m, 1), 4), dtype=torch.float32, device=dev)
+    cnt.zero_()
+    assert L.g2048_qtable_export(table_ptr, slots, keys.data_ptr(), rows.data_ptr(), m, cnt.data_ptr(), stream) == 0
+    keys, rows = keys[:m], rows[:m]
+    nz = (rows != 0).any(1)
+    bits = rows.view(torch.int32).to(torch.int64)
+    d = torch.stack([nz.sum(), (bits * nz[:, None]).sum(), ((keys & 0xFFFFFFFF) * nz).sum()])
+    del keys, rows, bits
+    return d
+
+
+def shared_learning_measurement(torch, dist, g2048, dev, rank, world, n_total, max_over_ranks, barrier):
+    """BASELINE configs[3]: n_total (2^23) envs sharded over the GPUs learn ONE Q-table.  Three modes, ms per env step
+    of ALL envs: (1) exact, owner computes, exchange every step; (2) the same with the exchange every 16 steps (values
+    frozen inside a window); (3) the asynchronous fused rollout on the table sharded over the GPUs' HBM (remote loads /
+    atomics over NVLink inside the kernel).  For the exact modes the digest of the sharded table is compared with the
+    digest of the SAME run on one GPU with one table (rank 0 plays all n_total envs with g2048_qlearn_step in
+    deterministic mode): `digest_equal_to_1gpu`."""
+    from g2048 import dist as gdist
+    L = g2048.lib()
+    if world & (world - 1) or n_total % world:
+        return [{"skipped": "needs a power-of-two number of GPUs"}]
+    n = n_total // world
+    stream = torch.cuda.current_stream().cuda_stream
+    slots_total = 1 << 30
+    out = []
+
+    def run_owner(window, warm, steps):
+        env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
+        env.reset()
+        shared = gdist.SharedQTable(L, dev, slots_total // world)
+        oc = gdist.OwnerComputesQLearning(env, shared, n_total, LR, GAMMA, EPS, window=window)
+        for _ in range(warm):
+            oc.step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            oc.step()
+        e1.record()
+        barrier()
+        dt = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+        oc.flush()
+        torch.cuda.synchronize()
+        d = device_table_digest(L, torch, dev, shared.ptrs[rank], shared.slots_per_shard, stream)
+        dist.all_reduce(d)
+        cnt = env.counters.clone()
+        dist.all_reduce(cnt)
+        oc.close()
+        shared.close()
+        del env
+        torch.cuda.empty_cache()
+        return dt, d.tolist(), cnt.tolist()
+
+    def one_gpu_reference(window, total_steps):
+        """rank 0: the same run on one GPU, one table (the others wait)"""
+        d = None
+        if rank == 0:
+            cap = slots_total
+            table = torch.zeros(cap * 4, dtype=torch.int64, device=dev)
+            b = torch.zeros(n_total, dtype=torch.int64, device=dev)
+            a = torch.full((n_total,), 0x000000000000FF01, dtype=torch.int64, device=dev)
+            s = torch.zeros(n_total, dtype=torch.int32, device=dev)
+            cnt = torch.zeros(16, dtype=torch.int64, device=dev)
+            assert L.g2048_env_reset(b.data_ptr(), s.data_ptr(), None, None, n_total, SEED, 0, 0, stream) == 0
+            m = n_total * window
+            need = int(L.g2048_qlearn_scratch_bytes(m))
+            scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+            if window == 1:
+                for t in range(total_steps):
+                    assert L.g2048_qlearn_step(b.data_ptr(), a.data_ptr(), s.data_ptr(), table.data_ptr(), cap, n_total, 0, LR,
+                                               GAMMA, EPS, 1, 1, SEED, t, 0, cnt.data_ptr(), None, None, None,
+                                               scratch.data_ptr(), need, stream) == 0, L.g2048_last_error()
+            else:   # values frozen for `window` steps: emit the records of every step, apply them all in (step, env) order
+                rk = torch.empty(m, dtype=torch.int64, device=dev)
+                ra = torch.empty(m, dtype=torch.uint8, device=dev)
+                rt = torch.empty(m, dtype=torch.float32, device=dev)
+                for t0 in range(0, total_steps, window):
+                    for j in range(window):
+                        o = j * n_total
+                        assert L.g2048_qlearn_step(b.data_ptr(), a.data_ptr(), s.data_ptr(), table.data_ptr(), cap, n_total, 0,
+                                                   LR, GAMMA, EPS, 1, 0, SEED, t0 + j, 0, cnt.data_ptr(),
+                                                   rk.data_ptr() + 8 * o, ra.data_ptr() + o, rt.data_ptr() + 4 * o,
+                                                   None, 0, stream) == 0, L.g2048_last_error()
+                    assert L.g2048_qtable_apply_targets(table.data_ptr(), cap, rk.data_ptr(), ra.data_ptr(), rt.data_ptr(), m, LR,
+                                                        1, scratch.data_ptr(), need, stream) == 0, L.g2048_last_error()
+                del rk, ra, rt
+            torch.cuda.synchronize()
+            d = device_table_digest(L, torch, dev, table.data_ptr(), cap, stream).tolist()
+            del table, scratch, b, a, s
+            torch.cuda.empty_cache()
+        barrier()
+        return d
+
+    for window, warm, steps in ((1, 4, 12), (16, 16, 32)):
+        dt, digest, cnt = run_owner(window, warm, steps)
+        ref = one_gpu_reference(window, warm + steps)
+        if rank == 0:
+            out.append({"mode": f"owner computes, exact, exchange every {window} step" + ("s" if window > 1 else ""),
+                        "env_steps_per_sec": n_total * steps / dt, "ms_per_step": dt / steps * 1e3, "envs_total": n_total,
+                        "envs_per_gpu": n, "steps_timed": steps, "table_digest": digest, "digest_1gpu": ref,
+                        "digest_equal_to_1gpu": digest == ref, "lost": int(cnt[8]), "dropped": int(cnt[7])})
+    # (3) asynchronous, one table sharded over the GPUs
+    k, warm, launches = 16, 10, 8       # 160 warm-up env steps like the main arm: the games have left the 480 start boards
+    env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
+    env.reset()
+    shared = gdist.SharedQTable(L, dev, (1 << 31) // world)
+    tot = torch.zeros(16, dtype=torch.int64, device=dev)
+    for _ in range(warm):
+        tot += shared.rollout(env, k, LR, GAMMA, EPS)
+    tot.zero_()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(launches):
+        tot += shared.rollout(env, k, LR, GAMMA, EPS)
+    e1.record()
+    barrier()
+    dt = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+    dist.all_reduce(tot)
+    c = tot.tolist()
+    shared.close()
+    del env
+    torch.cuda.empty_cache()
+    if rank == 0:
+        out.append({"mode": "asynchronous fused rollout, one table sharded over the GPUs (NVLink loads / atomics in the kernel)",
+                    "env_steps_per_sec": n_total * k * launches / dt, "ms_per_step": dt / (k * launches) * 1e3,
+                    "envs_total": n_total, "envs_per_gpu": n, "steps_timed": k * launches, "digest_equal_to_1gpu": None,
+                    "lost": int(c[8]), "dropped": int(c[7]), "retried_update_fraction": c[9] / max(c[0], 1),
+                    "remote_access_fraction": (world - 1) / world})
+    return out
 
 
 def dqn_measurement(torch, g2048, dev, n=65536, steps=3):

@@ -73,6 +73,7 @@ def load():
             "orc_qlearn_step_sync": (None, [vp, vp, vp, vp, i64, i32, f32, f32, u64, u64, u64, u64, vp, vp, vp, vp, i32]),
             "orc_rollout_random_mt": (None, [vp, vp, vp, i64, i64, i32, u64, u64, u64, vp, i32]),
             "orc_rollout_qlearn_mt": (None, [vp, vp, vp, i64, i64, i32, f32, f32, u64, u64, u64, u64, vp, u64, i32]),
+            "orc_rollout_qlearn_mt_tables": (None, [vp, vp, vp, i64, i64, i32, f32, f32, u64, u64, u64, u64, vp, vp, i32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(_lib, name)
@@ -241,6 +242,17 @@ def rollout_qlearn_mt(boards, aux, score, k_steps, lr, gamma, eps, table_capacit
     load().orc_rollout_qlearn_mt(_p(boards, np.uint64), _p(aux, np.uint64), _p(score, np.int32), len(boards), k_steps,
                                  flavour, lr, gamma, eps_threshold(eps), seed, step_base, env_id_base,
                                  _p(counters, np.int64), table_capacity, threads)
+    return counters
+
+
+def rollout_qlearn_mt_tables(boards, aux, score, k_steps, lr, gamma, eps, tables, flavour=FLAVOUR_PENALTY, seed=0,
+                             step_base=0, env_id_base=0):
+    """CPU baseline with persistent tables: thread w plays its env shard against tables[w] (QTable, f32) across calls."""
+    counters = np.zeros(N_COUNTERS, np.int64)
+    arr = (C.c_void_p * len(tables))(*[t.h for t in tables])
+    load().orc_rollout_qlearn_mt_tables(_p(boards, np.uint64), _p(aux, np.uint64), _p(score, np.int32), len(boards),
+                                        k_steps, flavour, lr, gamma, eps_threshold(eps), seed, step_base, env_id_base,
+                                        _p(counters, np.int64), arr, len(tables))
     return counters
 
 

@@ -846,14 +846,16 @@ ORC_API void orc_qlearn_step_sync(uint64_t *boards, uint64_t *aux, int32_t *scor
 typedef struct {
     uint64_t *boards, *aux; int32_t *score; int64_t n, k_steps; int flavour; float lr, gamma;
     uint64_t eps_thresh, seed, step_base, env_id_base, table_cap; int qlearn; int64_t counters[C_N];
+    qtab_t **tables;   /* optional: one persistent table per thread (tables[w]) instead of a fresh one per call */
+    int worker;
 } mt_job_t;
 static void *mt_worker(void *arg) {
     mt_job_t *j = (mt_job_t *)arg;
     if (j->qlearn) {
-        qtab_t *t = orc_qtab_new(j->table_cap, 1);
+        qtab_t *t = j->tables ? j->tables[j->worker] : orc_qtab_new(j->table_cap, 1);
         orc_rollout_qlearn_seq(j->boards, j->aux, j->score, t, j->n, j->k_steps, j->flavour, j->lr, j->gamma,
                                j->eps_thresh, j->seed, j->step_base, j->env_id_base, j->counters);
-        orc_qtab_free(t);
+        if (!j->tables) orc_qtab_free(t);
     } else {
         orc_rollout_random(j->boards, j->aux, j->score, j->n, j->k_steps, j->flavour, j->seed, j->step_base,
                            j->env_id_base, j->counters);
@@ -872,6 +874,7 @@ static void mt_run(mt_job_t proto, int64_t n, int threads, int64_t *counters) {
         jobs[w].score = proto.score ? proto.score + lo : NULL;
         jobs[w].n = hi - lo;
         jobs[w].env_id_base = proto.env_id_base + (uint64_t)lo;
+        jobs[w].worker = w;
         memset(jobs[w].counters, 0, sizeof jobs[w].counters);
         pthread_create(&tid[w], NULL, mt_worker, &jobs[w]);
     }
@@ -887,7 +890,7 @@ static void mt_run(mt_job_t proto, int64_t n, int threads, int64_t *counters) {
 ORC_API void orc_rollout_random_mt(uint64_t *boards, uint64_t *aux, int32_t *score, int64_t n, int64_t k_steps,
                                    int flavour, uint64_t seed, uint64_t step_base, uint64_t env_id_base,
                                    int64_t *counters, int threads) {
-    mt_job_t p = {boards, aux, score, n, k_steps, flavour, 0, 0, 0, seed, step_base, env_id_base, 0, 0, {0}};
+    mt_job_t p = {boards, aux, score, n, k_steps, flavour, 0, 0, 0, seed, step_base, env_id_base, 0, 0, {0}, NULL, 0};
     mt_run(p, n, threads, counters);
 }
 ORC_API void orc_rollout_qlearn_mt(uint64_t *boards, uint64_t *aux, int32_t *score, int64_t n, int64_t k_steps,
@@ -895,6 +898,16 @@ ORC_API void orc_rollout_qlearn_mt(uint64_t *boards, uint64_t *aux, int32_t *sco
                                    uint64_t step_base, uint64_t env_id_base, int64_t *counters, uint64_t table_cap,
                                    int threads) {
     mt_job_t p = {boards, aux, score, n, k_steps, flavour, lr, gamma, eps_thresh, seed, step_base, env_id_base,
-                  table_cap, 1, {0}};
+                  table_cap, 1, {0}, NULL, 0};
+    mt_run(p, n, threads, counters);
+}
+/* the same with one persistent table per thread (tables[0 .. threads)), kept across calls: the training run bench.py
+ * times as the CPU baseline (thread w plays envs [n w / threads, n (w + 1) / threads) against tables[w]) */
+ORC_API void orc_rollout_qlearn_mt_tables(uint64_t *boards, uint64_t *aux, int32_t *score, int64_t n, int64_t k_steps,
+                                          int flavour, float lr, float gamma, uint64_t eps_thresh, uint64_t seed,
+                                          uint64_t step_base, uint64_t env_id_base, int64_t *counters,
+                                          qtab_t **tables, int threads) {
+    mt_job_t p = {boards, aux, score, n, k_steps, flavour, lr, gamma, eps_thresh, seed, step_base, env_id_base,
+                  0, 1, {0}, tables, 0};
     mt_run(p, n, threads, counters);
 }

@@ -406,6 +406,108 @@ def record_dqn(n_boards: int = 512, n_cases: int = 3000):
             "eps_steps": steps, "eps": np.array(eps, np.float64)}
 
 
+# --------------------------------------------------------------------------- BASELINE config 2 at its stated size
+C2_ENVS, C2_STEPS = 4096, 512
+FNV = np.uint64(0x100000001B3)
+
+
+def c2_fold(h, *words):
+    """Per-env running digest of everything a step returns (uint64 arithmetic wraps): the replay recomputes it."""
+    for w in words:
+        h = h * FNV + np.asarray(w).astype(np.uint64)
+    return h
+
+
+def record_config2(flavour: str, n_envs: int = C2_ENVS, n_steps: int = C2_STEPS, first_env: int = 0):
+    """SURVEY.md 8d "C2": env i is seeded np.random.seed(1000 + i), plays actions
+    np.random.RandomState(2000 + i).randint(0, 4) for 512 steps with reset-on-done (nopenalty flavour: caller commits
+    the board).  Stored: the INPUTS of a bit-exact replay, packed -- actions (2 bits), the spawn of the move
+    (k | is4 << 4, 255 = none), the full-board quirk spawn, the reset spawns -- and per env a 64-bit digest over every
+    step's outputs (board, reward bits, flags, max level, move score, env.score, aux) plus the final board/score/aux."""
+    mod = ref_shim.load_penalty_env() if flavour == "penalty" else ref_shim.load_nopenalty_env()
+    E, T = n_envs, n_steps
+    action = np.zeros((E, T), np.uint8)
+    spawn = np.full((E, T), 255, np.uint8)
+    quirk = np.full((E, T), 255, np.uint8)
+    digest = np.zeros(E, np.uint64)
+    final_board, final_score, final_aux = np.zeros(E, np.uint64), np.zeros(E, np.int32), np.zeros(E, np.uint64)
+    start_draws = np.zeros((E, 4), np.uint8)
+    resets = []                                    # (env, step after which the reset happened, k_a, is4_a, k_b, is4_b)
+    pen_table = [-1.0]
+    for _ in range(64):
+        pen_table.append(max(pen_table[-1] * 1.1, -10))
+    calls = {}
+    orig_move, orig_over = mod.Game2048.move, mod.Game2048.is_game_over
+
+    def move_wrap(self, *a, **k):
+        res = orig_move(self, *a, **k)
+        if not calls.get("in_over"):
+            calls.setdefault("move", []).append((bool(res[0]), int(res[1])))
+        return res
+
+    def over_wrap(self):
+        calls["in_over"] = True
+        res = orig_over(self)
+        calls["in_over"] = False
+        calls["over"] = bool(res)
+        return res
+
+    mod.Game2048.move, mod.Game2048.is_game_over = move_wrap, over_wrap
+    try:
+        with DrawRecorder() as rec:
+            for i in range(E):
+                np.random.seed(1000 + first_env + i)
+                rs = np.random.RandomState(2000 + first_env + i)
+                env = mod.Game2048_env()
+                sp = spawn_pairs(rec.take())
+                start_draws[i] = [sp[0][0], sp[0][1], sp[1][0], sp[1][1]]
+                h = np.uint64(0)
+                with np.errstate(over="ignore"):
+                    for t in range(T):
+                        full_before = not (np.asarray(env.game.board) == 0).any()
+                        a = int(rs.randint(0, 4))
+                        calls.clear()
+                        board, reward, done, max_number = env.step(a)
+                        valid, mscore = calls["move"][0]
+                        game_over = calls["over"]
+                        pairs = spawn_pairs(rec.take())
+                        if valid:
+                            spawn[i, t] = pairs[0][0] | (pairs[0][1] << 4)
+                        if flavour != "penalty":
+                            if full_before and not game_over:
+                                quirk[i, t] = pairs[-1][0] | (pairs[-1][1] << 4)
+                            env.game.board = board         # caller commit, mainDQL_CNN_step2.py:237
+                        action[i, t] = a
+                        aux = 0
+                        if flavour == "penalty":
+                            ca = 255 if env.consecutive_action is None else int(env.consecutive_action)
+                            pen_idx = min(pen_table.index(float(env.last_consecutive_penalty)), PEN_SAT)
+                            aux = (int(env.previous_max).bit_length() - 1) | (ca << 8) | (pen_idx << 16) | \
+                                  (int(env.consecutive_count) << 32)
+                        fl = int(valid) | (int(game_over) << 1) | (int(bool(done)) << 2)
+                        words = fl | ((int(max_number).bit_length() - 1) << 8) | (mscore << 16)
+                        h = c2_fold(h, np.uint64(pack_board(board)), np.float64(reward).view(np.uint64), np.uint64(words),
+                                    np.uint64(int(env.score)), np.uint64(aux))
+                        if done:
+                            env.reset()
+                            rp = spawn_pairs(rec.take())
+                            resets.append((i, t, rp[0][0], rp[0][1], rp[1][0], rp[1][1]))
+                digest[i] = h
+                final_board[i] = pack_board(env.game.board)
+                final_score[i] = int(env.score)
+                if flavour == "penalty":
+                    ca = 255 if env.consecutive_action is None else int(env.consecutive_action)
+                    pen_idx = min(pen_table.index(float(env.last_consecutive_penalty)), PEN_SAT)
+                    final_aux[i] = (int(env.previous_max).bit_length() - 1) | (ca << 8) | (pen_idx << 16) | \
+                                   (int(env.consecutive_count) << 32)
+    finally:
+        mod.Game2048.move, mod.Game2048.is_game_over = orig_move, orig_over
+    packed_actions = (action[:, 0::4] | (action[:, 1::4] << 2) | (action[:, 2::4] << 4) | (action[:, 3::4] << 6)).astype(np.uint8)
+    return {"actions4": packed_actions, "spawn": spawn, "quirk": quirk, "start_draws": start_draws,
+            "resets": np.array(resets, np.int32).reshape(-1, 6), "digest": digest, "final_board": final_board,
+            "final_score": final_score, "final_aux": final_aux, "shape": np.array([E, T, first_env], np.int64)}
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit(f"reference not found under {ref_shim.REF_ROOT}")
@@ -432,5 +534,17 @@ def main():
     print(f"{path}: {len(q['s'])} transitions, {len(q['q_keys'])} states, {os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def main_config2():
+    """python oracle/make_golden.py config2 penalty|nopenalty  (about ten minutes each)"""
+    flavour = sys.argv[2]
+    g = record_config2(flavour)
+    path = os.path.join(OUT_DIR, f"config2_{flavour}.npz")
+    np.savez_compressed(path, **g)
+    print("wrote", path, os.path.getsize(path), "bytes;", len(g["resets"]), "resets")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "config2":
+    main_config2()
+    sys.exit(0)
 if __name__ == "__main__":
     main()

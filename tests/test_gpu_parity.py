@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle
-from test_oracle_golden import replay_env
+from test_oracle_golden import replay_config2, replay_env
 
 pytestmark = pytest.mark.gpu
 
@@ -102,6 +102,26 @@ def make_ctx_step(L, ctx):
 def test_env_step_replays_reference_golden(L, ctx, golden, name, flavour):
     """Bit-exact replay of action/spawn trajectories recorded from the reference (BASELINE config 2 form)."""
     replay_env(golden(name), flavour, make_ctx_step(L, ctx))
+
+
+@pytest.mark.parametrize("name,flavour", [("config2_penalty", 0), ("config2_nopenalty", 1)])
+def test_config2_4096_envs_512_steps_replay_reference_recorded_draws(L, ctx, golden, name, flavour):
+    """BASELINE config 2 as written: 4,096 envs x 512 steps, the actions and spawn draws the REFERENCE made
+    (np.random.seed(1000 + i), actions RandomState(2000 + i)), replayed through g2048_ctx_env_step / _env_reset: every
+    env's digest over all its steps' outputs, final board, score and aux equal the reference's."""
+    def gpu_step(boards, aux, score, actions, draws, fl):
+        n = len(boards)
+        reward, flags = np.zeros(n, np.float64), np.zeros(n, np.uint8)
+        maxlvl, ms = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        ok(L, L.g2048_ctx_env_step(ctx, vp(boards), vp(aux), vp(score), vp(actions), vp(np.ascontiguousarray(draws)),
+                                   vp(reward), vp(flags), vp(maxlvl), vp(ms), n, fl, 0, 0, 0))
+        return reward, flags, maxlvl, ms
+
+    def gpu_reset(boards, score, mask, draws):
+        ok(L, L.g2048_ctx_env_reset(ctx, vp(boards), vp(score), vp(mask), vp(np.ascontiguousarray(draws)), len(boards), 0, 0, 0))
+
+    steps, resets = replay_config2(golden(name), flavour, gpu_step, gpu_reset)
+    assert steps == 4096 * 512 and resets > 4096
 
 
 @pytest.mark.parametrize("name", ["env_penalty", "env_nopenalty"])

@@ -41,6 +41,67 @@ def oracle_step(boards, aux, score, actions, draws, flavour):
     return oracle.env_step(boards, aux, score, actions, draws, flavour)
 
 
+FNV = np.uint64(0x100000001B3)
+
+
+def replay_config2(g, flavour, step_fn, reset_fn):
+    """BASELINE config 2 at its stated size (4,096 envs x 512 steps, SURVEY.md 8d "C2"): replay the recorded actions and
+    spawn draws of the reference step by step (all envs at once), folding everything a step returns into a per-env
+    64-bit digest the way oracle/make_golden.py:record_config2 did on the reference's own outputs; the digests, the
+    final boards, scores and aux words must be the reference's."""
+    E, T, _ = (int(x) for x in g["shape"])
+    a4 = g["actions4"]
+    actions = np.zeros((E, T), np.uint8)
+    for j in range(4):
+        actions[:, j::4] = (a4 >> (2 * j)) & 3
+    boards, score = np.zeros(E, np.uint64), np.zeros(E, np.int32)
+    aux = np.full(E, oracle.AUX_INIT, np.uint64)
+    reset_fn(boards, score, None, np.ascontiguousarray(g["start_draws"]))
+    resets = g["resets"]
+    by_step = {}
+    for row in resets:
+        by_step.setdefault(int(row[1]), []).append(row)
+    h = np.zeros(E, np.uint64)
+    with np.errstate(over="ignore"):
+        for t in range(T):
+            sp, qk = g["spawn"][:, t], g["quirk"][:, t]
+            draws = np.full((E, 4), 255, np.uint8)
+            has, hq = sp != 255, qk != 255
+            draws[has, 0], draws[has, 1] = sp[has] & 15, sp[has] >> 4
+            draws[hq, 2], draws[hq, 3] = qk[hq] & 15, qk[hq] >> 4
+            reward, flags, maxlvl, ms = step_fn(boards, aux, score, np.ascontiguousarray(actions[:, t]), draws, flavour)
+            words = (flags & 7).astype(np.uint64) | (maxlvl.astype(np.uint64) << np.uint64(8)) | \
+                    (ms.astype(np.int64).astype(np.uint64) << np.uint64(16))
+            aux_word = aux if flavour == oracle.FLAVOUR_PENALTY else np.zeros(E, np.uint64)
+            for w in (boards, reward.view(np.uint64), words, score.astype(np.int64).astype(np.uint64), aux_word):
+                h = h * FNV + w
+            done = ((flags >> 2) & 1).astype(bool)
+            rows = by_step.get(t, [])
+            assert sorted(int(r[0]) for r in rows) == np.nonzero(done)[0].tolist(), f"done envs differ at step {t}"
+            if rows:
+                mask = done.astype(np.uint8)
+                rd = np.zeros((E, 4), np.uint8)
+                for r in rows:
+                    rd[int(r[0])] = r[2:6]
+                reset_fn(boards, score, mask, rd)
+    assert np.array_equal(h, g["digest"]), f"{(h != g['digest']).sum()} of {E} trajectories differ"
+    assert np.array_equal(boards, g["final_board"]) and np.array_equal(score, g["final_score"])
+    if flavour == oracle.FLAVOUR_PENALTY:
+        assert np.array_equal(aux, g["final_aux"])
+    return E * T, len(resets)
+
+
+def oracle_reset(boards, score, mask, draws):
+    oracle.env_reset(boards, score, mask, draws)
+
+
+@pytest.mark.parametrize("name,flavour", [("config2_penalty", oracle.FLAVOUR_PENALTY),
+                                          ("config2_nopenalty", oracle.FLAVOUR_NOPENALTY)])
+def test_config2_full_size_replay_matches_reference(golden, name, flavour):
+    steps, resets = replay_config2(golden(name), flavour, oracle_step, oracle_reset)
+    assert steps == 4096 * 512 and resets > 4096          # every env finishes several games
+
+
 @pytest.mark.parametrize("name,flavour", [("env_penalty", oracle.FLAVOUR_PENALTY),
                                           ("env_nopenalty", oracle.FLAVOUR_NOPENALTY)])
 def test_env_step_matches_reference(golden, name, flavour):
