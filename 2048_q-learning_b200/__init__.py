@@ -6,7 +6,8 @@ reference's Python interfaces.  `import g2048` (repo root) is an importable alia
 """
 from ._lib import G2048Error, build, declared_symbols, init, lib  # noqa: F401
 from .compat import Game2048, Game2048_env, QLearningAgent, pack_tiles, unpack_tiles  # noqa: F401
-from .train import evaluate_tabular, train_dqn, train_tabular, train_tabular_batched  # noqa: F401
+from .train import (evaluate_dqn, evaluate_random, evaluate_tabular, train_dqn, train_tabular,  # noqa: F401
+                    train_tabular_batched)
 
 
 def __getattr__(name):  # the batched classes need torch: import lazily

@@ -13,9 +13,16 @@ Reference pieces mirrored
                                 act_ripetitive :326-336, update_epsilon :341-343, remember, replay :351-390
                                 (loss = mean over B x 4 of (target - q)^2 with target == q except at the taken
                                 action; terminal target = reward), update_target_model :338-339.
-Deliberate differences (documented, batched form): the replay memory stores next_state explicitly instead of
-keras-rl's "next stored observation"; the consecutive-duplicate filter of `remember` (:283-297) is a
-single-stream heuristic and is not applied to the batch; prioritisation is alpha = 0 (uniform) as in the reference.
+Differences from the reference (documented; DESIGN.md "Known divergences"):
+  * the replay memory stores next_state explicitly instead of keras-rl's "next stored observation" (:48-66), which for
+    one env is the same board except for the newest entry (all zeros there until the next append);
+  * by default the drivers below restrict every action to the legal moves and store every transition.  The
+    reference's own rule -- act() unrestricted, so invalid moves ARE played (reward -10) and stored;
+    act_ripetitive() only when the previous transition was not stored; remember() drops a transition that repeats
+    the env's previously stored (state, next_state) unless the game ended (:279-297, mainDQL_CNN_step2.py:176-185,
+    :220) -- is `dqn_step(..., reference_driver=True)`: the duplicate filter and the `memory_saved` bit are kept per
+    env (the reference has one env, so "the previous entry of the memory" is that env's);
+  * prioritisation is alpha = 0 (uniform) as in the reference.
 """
 from __future__ import annotations
 
@@ -90,6 +97,9 @@ class BatchedDQNAgent:
         self.mem_reward = torch.zeros(m, dtype=torch.float32, device=dev)
         self.mem_done = torch.zeros(m, dtype=torch.bool, device=dev)
         self.nb_entries, self._head = 0, 0
+        # reference driver (dqn_step(reference_driver=True)): per env the last stored (state, next_state) and whether the
+        # previous transition was stored (`memory_saved`, mainDQL_CNN_step2.py:183-185, :220)
+        self._last_state = self._last_next = self.memory_saved = None
         self._gen = torch.Generator(device=dev)
         self._gen.manual_seed(self.seed)
 
@@ -131,18 +141,34 @@ class BatchedDQNAgent:
         """act_ripetitive (:326-336): epsilon-greedy restricted to the legal moves (4-bit mask per env)."""
         return self._select(boards, legal_mask.to(torch.uint8).contiguous(), env_id_base)
 
-    def remember(self, state, action, reward, done, next_state) -> bool:
-        """remember (:279-297) for a batch of transitions (packed boards), ring-buffer append."""
+    def remember(self, state, action, reward, done, next_state, filter_duplicates: bool = False):
+        """remember (:279-297) for a batch of transitions (packed boards), ring-buffer append.  With
+        filter_duplicates (the reference's rule) a transition whose (state, next_state) equals the env's previously
+        stored one is dropped unless the game ended; returns the per-env `memory_saved` mask (all True otherwise)."""
         n = state.numel()
-        idx = (torch.arange(n, device=self.device) + self._head) % self.memory_size
-        self.mem_state[idx] = state
-        self.mem_next[idx] = next_state
-        self.mem_action[idx] = action.to(torch.int64)
-        self.mem_reward[idx] = reward.to(torch.float32)
-        self.mem_done[idx] = done.to(torch.bool)
-        self._head = (self._head + n) % self.memory_size
-        self.nb_entries = min(self.nb_entries + n, self.memory_size)
-        return True
+        keep = torch.ones(n, dtype=torch.bool, device=self.device)
+        if filter_duplicates:
+            if self._last_state is None or self._last_state.numel() != n:
+                self._last_state = torch.full((n,), -1, dtype=torch.int64, device=self.device)
+                self._last_next = torch.full((n,), -1, dtype=torch.int64, device=self.device)
+            keep = done.to(torch.bool) | (state != self._last_state) | (next_state != self._last_next)
+            self._last_state = torch.where(keep, state, self._last_state)
+            self._last_next = torch.where(keep, next_state, self._last_next)
+            state, next_state, action, reward, done = (state[keep], next_state[keep], action[keep], reward[keep], done[keep])
+            n = state.numel()
+        if n > self.memory_size:                     # more transitions than slots: only the newest fit (no index repeats)
+            state, next_state, action, reward, done = (t[-self.memory_size:] for t in (state, next_state, action, reward, done))
+            n = self.memory_size
+        if n:
+            idx = (torch.arange(n, device=self.device) + self._head) % self.memory_size
+            self.mem_state[idx] = state
+            self.mem_next[idx] = next_state
+            self.mem_action[idx] = action.to(torch.int64)
+            self.mem_reward[idx] = reward.to(torch.float32)
+            self.mem_done[idx] = done.to(torch.bool)
+            self._head = (self._head + n) % self.memory_size
+            self.nb_entries = min(self.nb_entries + n, self.memory_size)
+        return keep
 
     def replay(self, episode=None):
         """replay (:351-390): one Adam step on a uniformly sampled minibatch."""
@@ -216,18 +242,32 @@ def terminal_bonus(boards: torch.Tensor, done: torch.Tensor) -> torch.Tensor:
     return torch.where(done, bonus, torch.zeros_like(bonus))
 
 
-def dqn_step(env: BatchedGame2048Env, agent: BatchedDQNAgent, train: bool = True):
-    """One step of the driver loop mainDQL_CNN_step2.py:163-237 for all envs: legal-move mask, act_ripetitive,
-    env.step (nopenalty flavour; the commit of :237 is folded into the batched env), terminal bonus, remember,
-    and a reset of the finished games.  Unfused form (one library call per piece); `FusedDQNFeed` does the env side
-    in one launch."""
+def dqn_step(env: BatchedGame2048Env, agent: BatchedDQNAgent, train: bool = True, reference_driver: bool = False):
+    """One step of the driver loop mainDQL_CNN_step2.py:163-237 for all envs: legal-move mask, action, env.step
+    (nopenalty flavour; the commit of :237 is folded into the batched env), terminal bonus, remember, and a reset of
+    the finished games.  Unfused form (one library call per piece); `FusedDQNFeed` does the env side in one launch.
+
+    Default: every action is restricted to the legal moves (act_ripetitive) and every transition is stored.
+    reference_driver=True follows the reference literally: act() -- unrestricted, invalid moves are played, cost -10
+    and are stored -- unless the env's previous transition was not stored (:183-185), then act_ripetitive(); and
+    remember() drops repeats of the env's previously stored transition (:283-297)."""
     state = env.boards.clone()
     legal = env.legal_mask()
-    actions = agent.act_ripetitive(state, legal, env.env_id_base)
+    if reference_driver:
+        actions = agent.act(state, env.env_id_base)                                    # :176
+        saved = agent.memory_saved
+        if saved is None or saved.numel() != env.n:
+            saved = torch.zeros(env.n, dtype=torch.bool, device=env.device)            # memory_saved starts False
+        if not bool(saved.all()):
+            actions = torch.where(saved, actions, agent.act_ripetitive(state, legal, env.env_id_base))   # :183-185
+    else:
+        actions = agent.act_ripetitive(state, legal, env.env_id_base)
     next_state, reward, done, _ = env.step(actions)
     reward = reward.to(torch.float32) + terminal_bonus(next_state, done)
     if train:
-        agent.remember(state, actions, reward, done, next_state.clone())
+        kept = agent.remember(state, actions, reward, done, next_state.clone(), filter_duplicates=reference_driver)
+        if reference_driver:
+            agent.memory_saved = torch.where(done, torch.zeros_like(kept), kept)       # a new game starts unsaved (:153-158)
     if bool(done.any()):
         env.reset(mask=done)
     return reward, done

@@ -92,6 +92,9 @@ def train_dqn(env, agent, total_steps: int, *, replays_per_episode: int = 100, m
     1024 tile (Dqn8TestNOPERCNN.py:283-284, :299-310), target sync every 20 episodes (:275-277), full agent save every
     100 episodes (:322-328).  Not reproduced: the plotting (:271), the commented-out rollback block, and
     clean_low_score_episodes (:317-319; keras-rl episode bookkeeping that a flat transition ring does not keep).
+    Every action here is restricted to the legal moves and every transition is stored; the reference's own rule
+    (act() unrestricted with invalid moves played and stored, act_ripetitive() only after a dropped transition,
+    duplicate filter in remember()) is `dqn.dqn_step(env, agent, reference_driver=True)`, the unfused per-step form.
     Returns {"episodes", "steps", "max_tile_list", "score_list", "loss_history", "best_tile"} like the arrays the
     reference keeps (:100-103)."""
     import os
@@ -147,6 +150,55 @@ def train_dqn(env, agent, total_steps: int, *, replays_per_episode: int = 100, m
             on_step(step, row)
     return {"episodes": episodes, "steps": total_steps, "max_tile_list": max_tile_list, "score_list": score_list,
             "loss_history": loss_history, "best_tile": best_tile}
+
+
+def evaluate_random(env, episodes: int = 10, rng=None):
+    """The demo's "auto play" mode (GameDemo.py:272-286), headless: uniformly random actions on the N = 1 adapters or
+    the reference's env objects until the game ends.  Returns per-episode (game score, max tile, steps)."""
+    import numpy as np
+    rng = rng or np.random
+    out = []
+    for _ in range(episodes):
+        env.reset()
+        done, steps, max_tile = False, 0, 0
+        while not done:
+            step = env.step(int(rng.randint(0, 4)))
+            board, done, max_tile = step[0], step[2], step[3]
+            if hasattr(env.game, "moved_board"):          # nopenalty flavour: the caller commits the board (:279)
+                env.game.board = board
+            steps += 1
+        out.append((int(env.score), int(max_tile), steps))
+    return out
+
+
+def evaluate_dqn(env, agent, episodes: int = 1, max_steps: int = 100000):
+    """The demo's "model play" mode (GameDemo.py:288-316) for ALL envs of a batched nopenalty env at once: greedy on
+    the network's Q values restricted to the legal moves (epsilon = 0), no learning, until `episodes` games per env
+    have ended.  Returns {"scores": [...], "max_tiles": [...], "steps": n}."""
+    import torch
+
+    from .dqn import FusedDQNFeed
+    saved = (agent.epsilon_start, agent.epsilon_min, agent.step_counter)
+    agent.epsilon_start = agent.epsilon_min = 0.0
+    scores, tiles, steps = [], [], 0
+    try:
+        env.reset()
+        feed = FusedDQNFeed(env, agent)
+        left = torch.full((env.n,), episodes, dtype=torch.int64, device=env.device)
+        while steps < max_steps and bool((left > 0).any()):
+            prev_score = env.score.clone()
+            _, done = feed.step(train=False)
+            steps += 1
+            count = done & (left > 0)
+            if bool(count.any()):
+                final = feed.next_state[count]
+                lv = torch.stack([(final >> (4 * j)) & 15 for j in range(16)], dim=1).max(dim=1).values
+                tiles += (1 << lv.to(torch.int64)).tolist()
+                scores += prev_score[count].tolist()
+                left -= count.to(torch.int64)
+    finally:
+        agent.epsilon_start, agent.epsilon_min, agent.step_counter = saved
+    return {"scores": scores, "max_tiles": tiles, "steps": steps}
 
 
 def evaluate_tabular(env, agent, episodes: int = 10):

@@ -29,6 +29,111 @@ def test_forward_shapes_and_same_padding_on_cpu():
     assert torch.allclose(conv(xin), ref, atol=1e-6)
 
 
+def keras_semantics_forward(x, params):
+    """The reference network (Dqn8TestNOPERCNN.py:209-246) written out in numpy the way Keras/TensorFlow evaluates it:
+    Input(shape=(16, 4, 4)) is read channels-last (H = 16 levels, W = 4 rows, C = 4 columns); Conv2D kernels are
+    [kh, kw, c_in, c_out] with TF 'SAME' padding -- (k - 1) // 2 zeros before, k // 2 after, per spatial dimension;
+    conv_block = four parallel convolutions (k = 1..4) concatenated on the channel axis, ReLU; Flatten in (h, w, c)
+    order; Dense kernels are [in, out]; Dropout is the identity at inference."""
+    def conv_same(a, kernel, bias):                       # a [N, H, W, C]
+        kh, kw, _, cout = kernel.shape
+        ap = np.pad(a, ((0, 0), ((kh - 1) // 2, kh // 2), ((kw - 1) // 2, kw // 2), (0, 0)))
+        n, h, w, _ = a.shape
+        out = np.zeros((n, h, w, cout), np.float64)
+        for i in range(kh):
+            for j in range(kw):
+                out += np.einsum("nhwc,co->nhwo", ap[:, i:i + h, j:j + w, :], kernel[i, j])
+        return out + bias
+    a = x.astype(np.float64)                              # [N, 16, 4, 4] read as NHWC
+    for block in params["blocks"]:
+        a = np.maximum(np.concatenate([conv_same(a, k, b) for k, b in block], axis=-1), 0.0)
+    flat = a.reshape(a.shape[0], -1)
+    hid = np.maximum(flat @ params["fc1"][0] + params["fc1"][1], 0.0)
+    return hid @ params["fc2"][0] + params["fc2"][1]
+
+
+def test_model_forward_equals_a_numpy_keras_semantics_reference():
+    """DQNModel (PyTorch, channels-first, padding='same') against the numpy restatement above with the weights
+    transposed into Keras layout -- pins the channels-last reading of Input(16,4,4), the SAME padding of the even
+    kernels, the concatenation order and the Flatten order at reduced width (the arithmetic is width-independent)."""
+    from g2048 import dqn
+    torch.manual_seed(3)
+    m = dqn.DQNModel(width=24, hidden=10).double().eval()
+    rng = np.random.RandomState(0)
+    boards = np.array([int(rng.randint(0, 1 << 62)) for _ in range(6)] + [0x0000000000000021, 0xFFFFFFFFFFFFFFFF], np.uint64)
+    x = oracle.encode_onehot(boards)                                        # [N, 16, 4, 4] as encode_state returns it
+    params = {"blocks": [[(c.weight.detach().numpy().transpose(2, 3, 1, 0), c.bias.detach().numpy()) for c in blk.convs]
+                         for blk in m.blocks],
+              "fc1": (m.fc1.weight.detach().numpy().T, m.fc1.bias.detach().numpy()),
+              "fc2": (m.fc2.weight.detach().numpy().T, m.fc2.bias.detach().numpy())}
+    want = keras_semantics_forward(x, params)
+    got = m(torch.from_numpy(x).double()).detach().numpy()
+    assert got.shape == want.shape == (8, 4)
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_reference_driver_plays_invalid_moves_and_filters_repeats():
+    """dqn_step(reference_driver=True) = mainDQL_CNN_step2.py:176-185, :220 + Dqn8TestNOPERCNN.py:279-297 per env:
+    act() is unrestricted (invalid moves are played, cost -10, are stored once), a transition repeating the env's
+    previously stored (state, next_state) is dropped and the next action is then act_ripetitive() (a legal move)."""
+    import g2048
+    from g2048 import dqn
+    torch.manual_seed(0)
+    n = 2048
+    env = g2048.BatchedGame2048Env(n, "nopenalty", seed=5)
+    agent = dqn.BatchedDQNAgent(width=16, hidden=16, memory_size=1 << 17, batch_size=64, epsilon=0.9, epsilon_decay=1.0)
+    env.reset()
+    stored, invalid_rewards, forced_legal = 0, 0, 0
+    for t in range(60):
+        before = env.boards.clone()
+        legal = env.legal_mask()
+        unsaved = None if agent.memory_saved is None else ~agent.memory_saved
+        entries = agent.nb_entries
+        reward, done = dqn.dqn_step(env, agent, reference_driver=True)
+        kept = agent.nb_entries - entries
+        stored += kept
+        assert 0 < kept <= n
+        invalid_rewards += int((reward == -10).sum())
+        if unsaved is not None and bool(unsaved.any()):
+            # envs whose previous transition was dropped were given a legal move: their board changed (or the game was over)
+            moved = (env.boards != before) | done | (legal == 0)
+            assert bool(moved[unsaved].all())
+            forced_legal += int(unsaved.sum())
+    assert invalid_rewards > 0 and forced_legal > 0 and stored < 60 * n      # repeats were dropped
+    # no two consecutive stored transitions of an env are the same (state, next_state) pair unless a game ended
+    assert agent.nb_entries == stored
+
+
+@pytest.mark.gpu
+def test_remember_with_more_transitions_than_slots_keeps_the_newest():
+    from g2048 import dqn
+    agent = dqn.BatchedDQNAgent(width=16, hidden=16, memory_size=1000, batch_size=8)
+    n = 2500
+    dev = agent.device
+    st = torch.arange(1, n + 1, dtype=torch.int64, device=dev)
+    agent.remember(st, torch.zeros(n, dtype=torch.uint8, device=dev), st.float(), torch.zeros(n, dtype=torch.bool, device=dev), st + 7)
+    assert agent.nb_entries == 1000
+    order = torch.argsort(agent.mem_state)
+    assert torch.equal(agent.mem_state[order], st[-1000:])                  # the newest 1000, each exactly once
+    assert torch.equal(agent.mem_next[order], st[-1000:] + 7) and torch.equal(agent.mem_reward[order], st[-1000:].float())
+
+
+@pytest.mark.gpu
+def test_evaluate_random_and_dqn_play_modes():
+    """GameDemo.py:272-316 headless: random play on the N = 1 adapter, greedy-legal network play on a batched env."""
+    import g2048
+    from g2048 import dqn
+    env1 = g2048.Game2048_env(flavour="nopenalty", seed=3)
+    res = g2048.evaluate_random(env1, episodes=2, rng=np.random.RandomState(1))
+    assert len(res) == 2 and all(steps > 20 and tile >= 8 for _, tile, steps in res)
+    env = g2048.BatchedGame2048Env(256, "nopenalty", seed=9)
+    agent = dqn.BatchedDQNAgent(width=16, hidden=16, memory_size=1024, batch_size=8)
+    out = g2048.evaluate_dqn(env, agent, episodes=1, max_steps=3000)
+    assert len(out["scores"]) == len(out["max_tiles"]) == 256 and min(out["max_tiles"]) >= 4
+    assert agent.nb_entries == 0                                             # nothing was learned or stored
+
+
 @pytest.mark.gpu
 def test_batched_dqn_agent_trains_on_gpu_envs():
     import g2048
