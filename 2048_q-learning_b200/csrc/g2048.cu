@@ -314,8 +314,7 @@ k_rollout_random(Tables T, u64* boards, u64* aux, int* score, long long n, long 
 //   * warps take their 32 envs at a time from a queue (one atomicAdd per warp and rollout), so a warp that met long
 //     probe sequences plays fewer envs instead of holding the whole grid up.
 struct Deferred {
-    u64* key;                      // [cap] slot * 4 + action; all ones = unused
-    float* target;                 // [cap]
+    ulonglong2* rec;               // [cap] {slot * 4 + action (all ones = unused), float bits of the target}
     unsigned long long* count;     // appended so far (may exceed cap: the excess was applied in place); NULL = no list
     unsigned long long cap;
 };
@@ -394,15 +393,18 @@ __device__ __forceinline__ void flush_late(const TAB& tab, const Deferred& D, co
     }
     if (late.pending) {
         if (j < D.cap) {
-            D.key[j] = (u64)late.slot * 4 + (u64)late.a;
-            D.target[j] = late.target;
+            D.rec[j] = make_ulonglong2((u64)late.slot * 4 + (u64)late.a, (u64)__float_as_uint(late.target));
         } else {
             q_update_atomic<TAB::kSys>(&tab.at(late.slot)->q[late.a], late.seen, lr, late.target);
         }
     }
 }
+// threads per CTA: a local table is bound by requests, not by round trips, and runs best with 768 threads of 80 registers;
+// a table sharded over the GPUs waits for NVLink round trips and wants every thread it can get (1024 x 64)
+template <class TAB> struct QlearnThreads { static constexpr int value = kQlearnThreads; };
+template <> struct QlearnThreads<ShardedTable> { static constexpr int value = kRolloutThreads; };
 template <int FLAVOUR, bool SMEM_LUT, class TAB>
-__global__ void __launch_bounds__(SMEM_LUT ? kQlearnThreads : kSmallRolloutThreads, 1)
+__global__ void __launch_bounds__(SMEM_LUT ? QlearnThreads<TAB>::value : kSmallRolloutThreads, 1)
 k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ TAB table, long long n,
                  long long k_steps, float lr, float gamma, u64 eps_thresh, u64 seed, u64 step_base, u64 id_base,
                  long long* counters, unsigned long long* queue, const __grid_constant__ Deferred D) {
@@ -836,13 +838,13 @@ k_long_run_apply(Slot* tab, const u64* sortkey, const float* target, float lr, l
 constexpr int kDeferBucketBits = 18;
 constexpr u32 kDeferBuckets = 1u << kDeferBucketBits;
 constexpr u32 kInlineBucket = 24;     // buckets of more records than this are applied by a warp
-constexpr u32 kFoldBucket = 256;       // ... and from this size on the warp folds them segment-wise
+constexpr u32 kFoldBucket = 64;        // ... and from this size on the warp folds them segment-wise
 __device__ __forceinline__ u32 defer_bucket(u64 key) { return (u32)((key * 0x9E3779B97F4A7C15ull) >> (64 - kDeferBucketBits)); }
 __global__ void __launch_bounds__(256)
-k_defer_count(const u64* key, const unsigned long long* count, unsigned long long cap, u32* pos, u32* bcount) {
+k_defer_count(const ulonglong2* rec, const unsigned long long* count, unsigned long long cap, u32* pos, u32* bcount) {
     const unsigned long long m = *count < cap ? *count : cap;
     for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < m; j += (unsigned long long)gridDim.x * blockDim.x) {
-        const u64 k = key[j];
+        const u64 k = rec[j].x;
         if (k != ~0ull) pos[j] = atomicAdd(&bcount[defer_bucket(k)], 1u);
     }
 }
@@ -884,17 +886,16 @@ __global__ void __launch_bounds__(256) k_defer_scan_sums(u32* sums) {   // 256 b
     if (threadIdx.x == 255) sums[256] = x + base;
 }
 __global__ void __launch_bounds__(256)
-k_defer_scatter(const u64* key, const float* target, const unsigned long long* count, unsigned long long cap, const u32* pos,
-                const u32* boff, const u32* sums, u64* key_out, float* target_out, u32* index_out) {
+k_defer_scatter(const ulonglong2* rec, const unsigned long long* count, unsigned long long cap, const u32* pos, const u32* boff,
+                const u32* sums, ulonglong2* out) {
     const unsigned long long m = *count < cap ? *count : cap;
     for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < m; j += (unsigned long long)gridDim.x * blockDim.x) {
-        const u64 k = key[j];
-        if (k == ~0ull) continue;
-        const u32 b = defer_bucket(k);
-        const u32 d = sums[b >> 10] + boff[b] + pos[j];
-        key_out[d] = k;
-        target_out[d] = target[j];
-        index_out[d] = (u32)j;                       // its place in the list = the order in which its warp appended it
+        const ulonglong2 r = rec[j];
+        if (r.x == ~0ull) continue;
+        const u32 b = defer_bucket(r.x);
+        // one 16-byte store per record: {address, target bits | its place in the list << 32} (the list index = the order
+        // in which its warp appended it)
+        out[sums[b >> 10] + boff[b] + pos[j]] = make_ulonglong2(r.x, (r.y & 0xFFFFFFFFull) | ((u64)j << 32));
     }
 }
 // q <- q + lr (target - q) record after record; the value is written back with a compare-and-swap from what was read,
@@ -915,8 +916,8 @@ __device__ __forceinline__ u32 load_q_bits(const float* p) {   // coherent at L2
 }
 template <class TAB>
 __global__ void __launch_bounds__(256)
-k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, const u32* index, const u32* boff, const u32* sums,
-              float lr, const u32* work, int long_blocks) {
+k_defer_apply(const __grid_constant__ TAB table, ulonglong2* rec, const u32* boff, const u32* sums, float lr, const u32* work,
+              int long_blocks) {
     __shared__ Slot* shard_base[G2048_MAX_PEERS];
     const auto tab = table.view(shard_base);
     using VIEW = decltype(tab);
@@ -927,7 +928,7 @@ k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, 
         defer_bucket_range(boff, sums, b, begin, end);
         if (end - begin > kInlineBucket) return;
         for (u32 r = begin; r < end; ++r) {
-            const u64 k = key[r];
+            const u64 k = rec[r].x;
             if (k == ~0ull) continue;                  // applied together with an earlier record of the same address
             float* qp = &tab.at(k >> 2)->q[k & 3];
             u32 seen = load_q_bits<VIEW>(qp);
@@ -937,11 +938,15 @@ k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, 
                 float q = __uint_as_float(seen);
                 long long last = -1;
                 for (;;) {
-                    u32 best = ~0u, best_t = 0;
-                    for (u32 t = r; t < end; ++t)
-                        if (key[t] == k && (long long)index[t] > last && index[t] < best) { best = index[t]; best_t = t; }
+                    u32 best = ~0u;
+                    float best_target = 0.f;
+                    for (u32 t = r; t < end; ++t) {
+                        const ulonglong2 x = rec[t];
+                        const u32 ix = (u32)(x.y >> 32);
+                        if (x.x == k && (long long)ix > last && ix < best) { best = ix; best_target = __uint_as_float((u32)x.y); }
+                    }
                     if (best == ~0u) break;
-                    q = td_apply(q, lr, target[best_t]);
+                    q = td_apply(q, lr, best_target);
                     last = (long long)best;
                 }
                 const u32 old = cas32<VIEW::kSys>(reinterpret_cast<u32*>(qp), seen, __float_as_uint(q));
@@ -949,7 +954,7 @@ k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, 
                 seen = old;
             }
             for (u32 t = r + 1; t < end; ++t)
-                if (key[t] == k) key[t] = ~0ull;
+                if (rec[t].x == k) rec[t].x = ~0ull;
         }
         return;
     }
@@ -966,7 +971,7 @@ k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, 
             u64 k = ~0ull;
             while (r < end) {
                 const u32 t = r + lane;
-                const u64 kt = t < end ? key[t] : ~0ull;
+                const u64 kt = t < end ? rec[t].x : ~0ull;
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, kt != ~0ull);
                 if (m) {
                     const int l = __ffs((int)m) - 1;
@@ -987,8 +992,10 @@ k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, 
                 // chain up to float32 rounding of the composition).
                 const float keep = __fsub_rn(1.0f, lr);
                 float A = 1.0f, B = 0.0f;
-                for (u32 t = r + lane; t < end; t += 32)
-                    if (key[t] == k) { B = td_apply(B, lr, target[t]); A = __fmul_rn(A, keep); }
+                for (u32 t = r + lane; t < end; t += 32) {
+                    const ulonglong2 x = rec[t];
+                    if (x.x == k) { B = td_apply(B, lr, __uint_as_float((u32)x.y)); A = __fmul_rn(A, keep); }
+                }
                 for (;;) {
                     float q = __uint_as_float(seen);
 #pragma unroll
@@ -1004,12 +1011,14 @@ k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, 
             for (;;) {
                 float q = __uint_as_float(seen);
                 u32 t = r + lane;
-                bool mine = t < end && key[t] == k;
-                float tt = mine ? target[t] : 0.f;
+                ulonglong2 x = t < end ? rec[t] : make_ulonglong2(~k, 0ull);
+                bool mine = x.x == k;
+                float tt = __uint_as_float((u32)x.y);
                 for (u32 base = r; base < end; base += 32) {
                     const u32 tn = base + 32 + lane;           // the next chunk is in flight while this one is folded
-                    const bool mine_n = tn < end && key[tn] == k;
-                    const float tt_n = mine_n ? target[tn] : 0.f;
+                    x = tn < end ? rec[tn] : make_ulonglong2(~k, 0ull);
+                    const bool mine_n = x.x == k;
+                    const float tt_n = __uint_as_float((u32)x.y);
                     unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
                     if (m == 0xFFFFFFFFu) {
 #pragma unroll
@@ -1031,7 +1040,7 @@ k_defer_apply(const __grid_constant__ TAB table, u64* key, const float* target, 
                 seen = old;
             }
             for (u32 t = r + lane; t < end; t += 32)
-                if (key[t] == k) key[t] = ~0ull;
+                if (rec[t].x == k) rec[t].x = ~0ull;
             __syncwarp();
             r += 1;
         }
@@ -1657,9 +1666,8 @@ namespace {
 // a zeroed list of `cap` deferred updates and the buffers that group them, from the device's ring
 struct DeferBuffers {
     unsigned long long* count;
-    u64 *key, *key_out;
-    float *target, *target_out;
-    u32 *pos, *index_out, *boff, *sums, *work;
+    ulonglong2 *rec, *rec_out;
+    u32 *pos, *boff, *sums, *work;
     int64_t cap;
 };
 int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B) {
@@ -1669,7 +1677,7 @@ int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B)
         set = &D->defer[D->defer_next++ % 4];
     }
     const size_t m = (size_t)cap;
-    const size_t need = 256 + 2 * align256(m * 8) + 4 * align256(m * 4) + 2 * align256(kDeferBuckets * 4) + align256(258 * 4);
+    const size_t need = 256 + 2 * align256(m * 16) + align256(m * 4) + 2 * align256(kDeferBuckets * 4) + align256(258 * 4);
     if (set->bytes < need) {
         CK(cudaDeviceSynchronize());               // growing: nobody may still be using the old buffer
         if (set->buf) CK(cudaFree(set->buf));
@@ -1680,18 +1688,15 @@ int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B)
     }
     char* p = (char*)set->buf;
     B.count = (unsigned long long*)p; p += 256;
-    B.key = (u64*)p; p += align256(m * 8);
-    B.key_out = (u64*)p; p += align256(m * 8);
-    B.target = (float*)p; p += align256(m * 4);
-    B.target_out = (float*)p; p += align256(m * 4);
+    B.rec = (ulonglong2*)p; p += align256(m * 16);
+    B.rec_out = (ulonglong2*)p; p += align256(m * 16);
     B.pos = (u32*)p; p += align256(m * 4);
-    B.index_out = (u32*)p; p += align256(m * 4);
     B.boff = (u32*)p; p += align256(kDeferBuckets * 4);
     B.work = (u32*)p; p += align256(kDeferBuckets * 4);
     B.sums = (u32*)p;
     B.cap = cap;
     CK(cudaMemsetAsync(B.count, 0, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(B.key, 0xFF, m * sizeof(u64), st));   // all ones = no record
+    CK(cudaMemsetAsync(B.rec, 0xFF, m * sizeof(ulonglong2), st));   // all ones = no record
     CK(cudaMemsetAsync(B.boff, 0, kDeferBuckets * sizeof(u32), st));
     CK(cudaMemsetAsync(B.sums, 0, 258 * sizeof(u32), st));
     return 0;
@@ -1707,14 +1712,12 @@ int64_t deferred_capacity(int64_t n, int64_t k_steps) {
 template <class TAB>
 int apply_deferred(DeviceState* D, const TAB& tab, const DeferBuffers& B, float lr, cudaStream_t st) {
     const int g = grid_for(B.cap, 256, D->sm_count);
-    k_defer_count<<<g, 256, 0, st>>>(B.key, B.count, (unsigned long long)B.cap, B.pos, B.boff);
+    k_defer_count<<<g, 256, 0, st>>>(B.rec, B.count, (unsigned long long)B.cap, B.pos, B.boff);
     k_defer_scan<<<kDeferBuckets / 1024, 1024, 0, st>>>(B.boff, B.sums, B.work);
     k_defer_scan_sums<<<1, 256, 0, st>>>(B.sums);
-    k_defer_scatter<<<g, 256, 0, st>>>(B.key, B.target, B.count, (unsigned long long)B.cap, B.pos, B.boff, B.sums, B.key_out,
-                                       B.target_out, B.index_out);
+    k_defer_scatter<<<g, 256, 0, st>>>(B.rec, B.count, (unsigned long long)B.cap, B.pos, B.boff, B.sums, B.rec_out);
     const int long_blocks = D->sm_count * 4;
-    k_defer_apply<TAB><<<long_blocks + kDeferBuckets / 256, 256, 0, st>>>(tab, B.key_out, B.target_out, B.index_out, B.boff,
-                                                                           B.sums, lr, B.work, long_blocks);
+    k_defer_apply<TAB><<<long_blocks + kDeferBuckets / 256, 256, 0, st>>>(tab, B.rec_out, B.boff, B.sums, lr, B.work, long_blocks);
     LAUNCH_CHECK("apply_deferred");
     return 0;
 }
@@ -1725,7 +1728,7 @@ int launch_rollout_qlearn(DeviceState* D, const TAB& tab, uint64_t* boards, uint
                           const DeferBuffers* shared_list) {
     int grid, block, smem_lut;
     size_t smem;
-    rollout_geometry(D, n, grid, block, smem_lut, smem, kQlearnThreads);
+    rollout_geometry(D, n, grid, block, smem_lut, smem, QlearnThreads<TAB>::value);
     // the warps take their envs from a queue: its head is a counter zeroed in stream order before the launch
     unsigned long long* queue;
     {
@@ -1739,12 +1742,12 @@ int launch_rollout_qlearn(DeviceState* D, const TAB& tab, uint64_t* boards, uint
     DeferBuffers db{};
     int64_t cap = 0;
     if (shared_list) {
-        defer = Deferred{shared_list->key, shared_list->target, shared_list->count, (unsigned long long)shared_list->cap};
+        defer = Deferred{shared_list->rec, shared_list->count, (unsigned long long)shared_list->cap};
     } else if (n >= kDeferMinEnvs) {
         cap = deferred_capacity(n, k_steps);
         int rc = deferred_list(D, cap, S(stream), db);
         if (rc) return rc;
-        defer = Deferred{db.key, db.target, db.count, (unsigned long long)cap};
+        defer = Deferred{db.rec, db.count, (unsigned long long)cap};
     }
 #define LAUNCH_RQ(F, SM)                                                                                              \
     k_rollout_qlearn<F, SM, TAB><<<grid, block, smem, S(stream)>>>(D->tables, (u64*)boards, (u64*)aux, score, tab, n,   \
