@@ -477,7 +477,7 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_const
                     P.assumed = __float_as_uint(q);
                     P.ret_q01 = cas32<SYS>(reinterpret_cast<u32*>(&sp->q[a]), P.assumed, __float_as_uint(nq));
                     P.kind = kPendUpd32;
-                } else if (a < 2) {
+                } else if (a < 2 && decltype(tab)::kMerge128) {
                     P.key = s_board;
                     cas_w0<SYS>(sp, 0ull, 0ull, s_board, (u64)__float_as_uint(nq) << (32 * a), P.ret_key, P.ret_q01);
                     P.kind = kPendMerged;

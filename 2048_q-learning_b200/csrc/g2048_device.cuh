@@ -390,6 +390,7 @@ struct LocalTable {
     u64 mask;
     static constexpr bool kSys = false;
     static constexpr bool kSysLoad = false;
+    static constexpr bool kMerge128 = true;    // insert + first update as one 128-bit CAS (k_rollout_qlearn)
     __device__ __forceinline__ Slot* at(u64 h) const { return base + h; }
     __device__ __forceinline__ LocalTable view(Slot**) const { return *this; }
 };
@@ -402,6 +403,7 @@ struct ShardedView {
     u32 shift;
     static constexpr bool kSys = SYS_ATOM;
     static constexpr bool kSysLoad = SYS_LOAD;
+    static constexpr bool kMerge128 = false;   // 128-bit atomics on a peer's memory are slow over NVLink: 64-bit insert, the value follows
     __device__ __forceinline__ Slot* at(u64 h) const { return base[h >> shift] + (h & low); }
 };
 template <bool SYS_LOAD, bool SYS_ATOM>
