@@ -370,6 +370,12 @@ __device__ __forceinline__ void settle_update(const TAB& tab, PendingUpdate& P, 
     }
     P.kind = kPendNone;
 }
+// places a warp reserved in the list and will not use: marked "no record" (all ones), so the list needs no clearing
+__device__ __forceinline__ void release_places(const Deferred& D, unsigned long long cur, unsigned long long end, unsigned live) {
+    const unsigned rank = __popc(live & ((1u << (threadIdx.x & 31)) - 1u)), step = __popc(live);   // the lanes that are here
+    for (unsigned long long j = cur + rank; j < end && j < D.cap; j += step)
+        D.rec[j] = make_ulonglong2(~0ull, 0ull);
+}
 // The late updates of a warp (all its `live` lanes, lane 0 among them, call this together): appended to the list of deferred updates -- the warp
 // reserves 64 places at a time with one atomicAdd and fills them from a cursor it carries in registers; places it does
 // not use stay all ones -- or, without a list or beyond its end, applied in place by a compare-and-swap loop.
@@ -383,6 +389,7 @@ __device__ __forceinline__ void flush_late(const TAB& tab, const Deferred& D, co
     if (D.count) {
         const int cnt = __popc(m);
         if (cur + (unsigned long long)cnt > end) {
+            release_places(D, cur, end, live);             // what is left of the old reservation stays unused
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(D.count, 64ull);
             cur = __shfl_sync(live, base, 0);
@@ -538,6 +545,7 @@ k_rollout_qlearn(Tables T, u64* boards, u64* aux, int* score, const __grid_const
 #endif
     }
 #undef TM
+    if (D.count) release_places(D, dcur, dend, 0xFFFFFFFFu);
     flush_counters(c, counters);
 }
 
@@ -1696,15 +1704,15 @@ int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B)
     B.sums = (u32*)p;
     B.cap = cap;
     CK(cudaMemsetAsync(B.count, 0, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(B.rec, 0xFF, m * sizeof(ulonglong2), st));   // all ones = no record
     CK(cudaMemsetAsync(B.boff, 0, kDeferBuckets * sizeof(u32), st));
     CK(cudaMemsetAsync(B.sums, 0, 258 * sizeof(u32), st));
     return 0;
 }
-// room for one lost race in eight env steps (measured: one in 16-25 once the games have spread out; only the first
-// launch after a common reset, where every env sits on one of 480 boards, overflows into the in-place loop)
+// room for one lost race in four env steps (measured: one in 18 on a local table, one in 9 on a table shared by 8 GPUs,
+// plus a quarter of slack in the warps' reservations; only the first launches after a common reset, where every env sits
+// on one of 480 boards, overflow into the in-place loop)
 int64_t deferred_capacity(int64_t n, int64_t k_steps) {
-    const long double want = (long double)n * (long double)k_steps / 8;
+    const long double want = (long double)n * (long double)k_steps / 4;
     int64_t cap = 1 << 16;
     while (cap < (1 << 23) && (long double)cap < want) cap <<= 1;
     return cap;
