@@ -1097,15 +1097,17 @@ __global__ void __launch_bounds__(256) k_q_size(const Slot* tab, u64 capacity, l
     c = warp_sum(c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long*)count, (unsigned long long)c);
 }
-// occupancy statistics: out[0] = states, out[1] = sum over states of the distance (in slots) from the home slot
-// mix64(key) & mask, out[2] = the largest distance.  A lookup of a stored state costs 1 + distance probes.
+// occupancy statistics: out[0] = states, out[1] = sum over states of the number of probes that precede their slot in
+// their key's probe sequence, out[2] = the largest such number.  A lookup of a stored state costs 1 + that many probes.
 __global__ void __launch_bounds__(256) k_q_probe_stats(const Slot* tab, u64 capacity, long long* out) {
     long long cnt = 0, sum = 0, mx = 0;
     const u64 mask = capacity - 1;
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < capacity; i += (u64)gridDim.x * blockDim.x) {
         u64 k = __ldcg(&tab[i].key);
         if (k) {
-            long long d = (long long)((i - (mix64(k) & mask)) & mask);
+            // probes before this slot in its key's sequence (pair by pair, the home slot's side first: next_probe)
+            const u64 home = mix64(k) & mask;
+            long long d = (long long)(2 * (((i >> 1) - (home >> 1)) & (mask >> 1)) + ((i ^ home) & 1));
             cnt += 1; sum += d; mx = max(mx, d);
         }
     }

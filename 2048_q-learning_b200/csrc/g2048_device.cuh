@@ -454,7 +454,11 @@ __device__ __forceinline__ void cas_w0(Slot* s, u64 cmp_key, u64 cmp_q01, u64 ne
                      "atom.relaxed.gpu.global.cas.b128 d, [%6], c, n;\n\tmov.b128 {%0, %1}, d;\n\t}"
                      : "=l"(old_key), "=l"(old_q01) : "l"(cmp_key), "l"(cmp_q01), "l"(new_key), "l"(new_q01), "l"(s) : "memory");
 }
-// Linear probing by single 32-byte slots.  (A two-slot 64-byte bucket loaded as a pair was measured SLOWER --
+// The probe sequence: the home slot, then its partner in the same 64 bytes (h ^ 1: a lookup's L2 fill brings both, so
+// the second probe is an L2 hit instead of a second miss half of the time), then the next pair, starting on the home
+// slot's side again.  p = index of the probe just made.
+__device__ __forceinline__ u64 next_probe(u64 h, int p, u64 mask) { return (p & 1) ? (((h ^ 1) + 2) & mask) : (h ^ 1); }
+// Probing by single 32-byte slots, pair by pair.  (A two-slot 64-byte bucket loaded as a pair was measured SLOWER --
 // 10.7 vs 14.2 G steps/s: what saturates is the number of L2-miss sector requests, ~36 G/s on B200 whatever the
 // fetch granularity, tools/membench.cu -- so every extra sector costs, even an adjacent one.)
 // defaultdict semantics (main.py:16): reading a state creates its zero row.  Returns the slot index
@@ -462,7 +466,7 @@ __device__ __forceinline__ void cas_w0(Slot* s, u64 cmp_key, u64 cmp_q01, u64 ne
 template <bool INSERT, class TAB>
 __device__ __forceinline__ u32 table_find(const TAB& tab, u64 key, float4& q, u32& inserted) {
     u64 h = mix64(key) & tab.mask;
-    for (int p = 0; p < kMaxProbe; ++p, h = (h + 1) & tab.mask) {
+    for (int p = 0; p < kMaxProbe; h = next_probe(h, p, tab.mask), ++p) {
         u64 k;
         Slot* sp = tab.at(h);
         load_slot<TAB::kSysLoad>(sp, k, q);
@@ -488,7 +492,7 @@ template <class TAB>
 __device__ __forceinline__ u32 table_probe(const TAB& tab, u64 key, float4& q, bool& fresh, u32& dropped) {
     u64 h = mix64(key) & tab.mask, k = 1;
     int p = 0;
-    for (; p < kMaxProbe; ++p, h = (h + 1) & tab.mask) {
+    for (; p < kMaxProbe; h = next_probe(h, p, tab.mask), ++p) {
         load_slot<TAB::kSysLoad>(tab.at(h), k, q);
         if (k == key || k == 0) break;
     }

@@ -302,8 +302,9 @@ G2048_API int g2048_qtable_apply_targets(void* table, uint64_t capacity, const u
                                          size_t scratch_bytes, void* stream);
 /* number of states -> *count (device int64) */
 G2048_API int g2048_qtable_size(const void* table, uint64_t capacity, int64_t* count, void* stream);
-/* stats[3] (device int64): number of states, sum of their distances (in slots) from the home slot of their hash, and
- * the largest distance; a lookup of a stored state costs 1 + distance probes, so mean probe length = 1 + sum / n. */
+/* stats[3] (device int64): number of states, sum over the states of the probes that come BEFORE their slot in their
+ * key's probe sequence (home slot, its partner in the same 64 bytes, then the next pair ...), and the largest such
+ * number; a lookup of a stored state costs 1 + that many probes, so mean probe length = 1 + sum / n. */
 G2048_API int g2048_qtable_probe_stats(const void* table, uint64_t capacity, int64_t* stats, void* stream);
 /* compact (key, row) pairs into keys[max_out], rows[max_out][4]; *count (device int64, zeroed by the caller)
  * receives the number of states (may exceed max_out: the excess is not written) */

@@ -342,7 +342,10 @@ def test_probe_stats_match_a_host_recount(g):
         x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
         x ^= x >> np.uint64(31)
     mask = np.uint64((1 << 18) - 1)
-    d = (pos - (x & mask)) & mask
+    home = x & mask
+    # the probe sequence goes pair by pair (the two slots of one 64-byte fill), the home slot's side first
+    one = np.uint64(1)
+    d = np.uint64(2) * (((pos >> one) - (home >> one)) & (mask >> one)) + ((pos ^ home) & one)
     assert st["states"] == len(k) == len(agent)
     assert st["max_probe_length"] == 1 + int(d.max())
     assert abs(st["mean_probe_length"] - (1 + d.astype(np.float64).mean())) < 1e-9
