@@ -522,7 +522,10 @@ def main():
                                  "charges per request, not per byte (profiles/r02_membench.txt): a table visit of one load + "
                                  "one write-type request runs at 17.5 G/s at most = 8.6 % of the streaming peak at 32 B; "
                                  "traffic = ncu DRAM bytes (64 B fill + 32 B write-back per visit)"},
-            "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary(),
+            "e2e": e2e, "gpu_launches": args.steps * 6, "clocks": clocks.summary(),
+            "gpu_launches_note": "per fused call: k_rollout_qlearn + k_defer_count, k_defer_scan, k_defer_scan_sums, "
+                                 "k_defer_scatter, k_defer_apply (device-resident arm; the e2e arm launches one rollout "
+                                 "kernel per chunk on top)",
             "cpu_baseline": cpu_baseline(os.cpu_count() or 1) if world == 1 else None,
             "extras": extras,
         }

@@ -172,11 +172,19 @@ G2048_API int g2048_rollout_random(uint64_t* boards, uint64_t* aux, int32_t* sco
                                    int64_t* counters, void* stream);
 
 /* The loop of main.py:91-101 for n envs and k_steps steps each, fused: epsilon-greedy choose_action
- * (main.py:34-38) -> env step -> update_q_value (main.py:40-43) on the HBM hash table, asynchronously:
- * each env applies q <- q + lr (target - q) at once with ONE atomic compare-and-swap from the value it read; if
- * another env changed that Q value in between, the update is skipped and counted in counters[G2048_C_LOST]
- * (nothing stale is ever summed, no thread spins).  With one env nothing is lost: N = 1 is exactly the
- * reference's sequential order.  Envs that finish (done) are reset in place (STREAM_AUTORESET). */
+ * (main.py:34-38) -> env step -> update_q_value (main.py:40-43) on the HBM hash table, asynchronously: each env
+ * applies q <- q + lr (target - q) with ONE atomic from the value it read (a state that is not in the table yet is
+ * inserted together with its first update by a 128-bit compare-and-swap).  EVERY update is applied exactly once: one
+ * that loses its race against another env is applied to the winner's value -- in place for launches of fewer than
+ * 16,384 envs, else through a list that the same call groups by address and applies after the rollout, every group as
+ * one sequential chain (still asynchronous on `stream`: when the stream has passed the call, the table is complete).
+ * counters[G2048_C_RETRIED] counts those second applications, counters[G2048_C_LOST] stays 0 unless the table is full.
+ * Nothing stale is ever summed, no thread spins on a contended value.  With one env nothing races: N = 1 is exactly
+ * the reference's sequential order.  Envs that finish (done) are reset in place (STREAM_AUTORESET); every state an
+ * env reads is in the table when the call is done (defaultdict semantics, main.py:16).
+ * The list and its work buffers belong to the device (about 36 bytes per 4 env steps of the launch, allocated on
+ * first use and grown on demand -- the only calls that may synchronise the device); up to four such launches may be in
+ * flight per device at a time. */
 G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* score, void* table, uint64_t capacity,
                                    int64_t n, int64_t k_steps, int flavour, float lr, float gamma, double eps,
                                    uint64_t seed, uint64_t step_base, uint64_t env_id_base, int64_t* counters,
@@ -187,7 +195,7 @@ G2048_API int g2048_rollout_qlearn(uint64_t* boards, uint64_t* aux, int32_t* sco
  * shard j -- this GPU's own memory or a peer's, mapped with g2048_peer_open.  Every GPU runs the call on its own env
  * shard at the same time; lookups are plain loads and updates single atomic compare-and-swaps that travel over NVLink 5 /
  * NVSwitch to the owner's L2 (system scope), so all envs of the box learn the same table (q_table, main.py:16) with
- * no exchange step at all.  n_shards * slots_per_shard <= 2^31.  Each shard is an ordinary slot array: clear, size and
+ * no exchange step at all; lost races are deferred and applied like in g2048_rollout_qlearn (every update is applied).  n_shards * slots_per_shard <= 2^31.  Each shard is an ordinary slot array: clear, size and
  * export it with the g2048_qtable_* calls on its owner. */
 G2048_API int g2048_rollout_qlearn_sharded(uint64_t* boards, uint64_t* aux, int32_t* score, const void* const* shards,
                                            int n_shards, uint64_t slots_per_shard, int64_t n, int64_t k_steps,
