@@ -836,34 +836,45 @@ k_long_run_apply(Slot* tab, const u64* sortkey, const float* target, float lr, l
     }
 }
 
-// ---- the deferred updates of a fused rollout: group by address, apply every group as one sequential chain --------
-// No sort is needed, only "all the records of one Q value in one thread's hands": the records are counted into 2^18
-// hash buckets of their address (one atomicAdd each, which also gives the record its place in the bucket), the bucket
-// sizes are prefix-summed, the records scattered bucket by bucket, and one thread per bucket applies what it holds
-// (a bucket holds a few records of different addresses, or the hundreds that pile up on the action a popular start
-// state takes).  The order inside a group is whatever the atomics produced: the asynchronous mode promises one
-// sequential application of every update; within a group of up to kInlineBucket records it is the order of the list.
-constexpr int kDeferBucketBits = 18;
-constexpr u32 kDeferBuckets = 1u << kDeferBucketBits;
+// ---- grouping update records by address without a sort ------------------------------------------------------------
+// Both the deferred updates of a fused rollout and the records of the exact synchronous step need "all the records of
+// one Q value in one thread's hands", not a total order: the records are counted into 2^bits hash buckets of their
+// address (one atomicAdd each, which also gives the record its place in its bucket), the bucket sizes are prefix-summed
+// and the records scattered bucket by bucket, packed as {address, target bits | order << 32}.  A bucket then holds a few
+// records of different addresses, or the hundreds that pile up on the action a popular start state takes.  Inside a
+// group the records are applied by ascending `order` (the place in the list / the global env index): exactly so in the
+// synchronous step (k_group_apply_exact), and for groups of up to kInlineBucket records in the asynchronous rollout.
+struct Buckets {
+    u32* boff;      // [2^bits] records per bucket, then (k_bucket_scan) offset inside its block of 1024 buckets
+    u32* sums;      // [blocks] offset of every block of 1024 buckets, [blocks] = total, [blocks + 1] = long buckets queued
+    u32* work;      // [2^bits] queue of the buckets with more than kInlineBucket records
+    int bits;       // 10 .. 22
+    __host__ __device__ u32 count() const { return 1u << bits; }
+    __host__ __device__ u32 blocks() const { return 1u << (bits - 10); }
+};
 constexpr u32 kInlineBucket = 24;     // buckets of more records than this are applied by a warp
-constexpr u32 kFoldBucket = 64;        // ... and from this size on the warp folds them segment-wise
-__device__ __forceinline__ u32 defer_bucket(u64 key) { return (u32)((key * 0x9E3779B97F4A7C15ull) >> (64 - kDeferBucketBits)); }
+constexpr u32 kFoldBucket = 64;        // asynchronous rollout: ... and from this size on the warp folds them segment-wise
+__device__ __forceinline__ u32 bucket_of(u64 key, int bits) { return (u32)((key * 0x9E3779B97F4A7C15ull) >> (64 - bits)); }
+__device__ __forceinline__ void bucket_range(const Buckets& B, u32 b, u32& begin, u32& end) {
+    begin = B.sums[b >> 10] + B.boff[b];
+    end = (b + 1 == B.count()) ? B.sums[B.blocks()] : B.sums[(b + 1) >> 10] + B.boff[b + 1];
+}
 __global__ void __launch_bounds__(256)
-k_defer_count(const ulonglong2* rec, const unsigned long long* count, unsigned long long cap, u32* pos, u32* bcount) {
+k_defer_count(const ulonglong2* rec, const unsigned long long* count, unsigned long long cap, u32* pos, Buckets B) {
     const unsigned long long m = *count < cap ? *count : cap;
     for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < m; j += (unsigned long long)gridDim.x * blockDim.x) {
         const u64 k = rec[j].x;
-        if (k != ~0ull) pos[j] = atomicAdd(&bcount[defer_bucket(k)], 1u);
+        if (k != ~0ull) pos[j] = atomicAdd(&B.boff[bucket_of(k, B.bits)], 1u);
     }
 }
-// exclusive prefix sum over the 2^18 bucket sizes: 256 blocks scan 1024 each, block 0's last warp then scans the 256
-// block totals once every block has published its own (a counter in sums[257] says how many have)
-__global__ void __launch_bounds__(1024) k_defer_scan(u32* bcount, u32* sums, u32* work) {
+// exclusive prefix sum over the bucket sizes: every block scans 1024 of them and queues its long buckets, then one block
+// scans the block totals
+__global__ void __launch_bounds__(1024) k_bucket_scan(Buckets B) {
     __shared__ u32 warp_tot[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 idx = blockIdx.x * 1024u + threadIdx.x;
-    const u32 v = bcount[idx];
-    if (v > kInlineBucket) work[atomicAdd(&sums[257], 1u)] = idx;   // long buckets get a warp each (k_defer_apply)
+    const u32 v = B.boff[idx];
+    if (v > kInlineBucket) B.work[atomicAdd(&B.sums[B.blocks() + 1], 1u)] = idx;
     u32 x = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
@@ -874,47 +885,51 @@ __global__ void __launch_bounds__(1024) k_defer_scan(u32* bcount, u32* sums, u32
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
         warp_tot[lane] = z - w;
-        if (lane == 31) sums[blockIdx.x] = z;          // this block's total
+        if (lane == 31) B.sums[blockIdx.x] = z;        // this block's total
     }
     __syncthreads();
-    bcount[idx] = x - v + warp_tot[warp];              // exclusive, within the block
+    B.boff[idx] = x - v + warp_tot[warp];              // exclusive, within the block
 }
-__global__ void __launch_bounds__(256) k_defer_scan_sums(u32* sums) {   // 256 block totals -> exclusive offsets, total in sums[256]
-    __shared__ u32 warp_tot[8];
+__global__ void __launch_bounds__(1024) k_bucket_scan_sums(Buckets B) {   // block totals -> exclusive offsets, grand total behind them
+    __shared__ u32 warp_tot[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 v = sums[threadIdx.x];
-    u32 x = v;
+    const u32 nb = B.blocks(), per = (nb + 1023) / 1024, lo = threadIdx.x * per;
+    u32 mine = 0;
+    for (u32 i = lo; i < lo + per && i < nb; ++i) mine += B.sums[i];
+    u32 x = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
     if (lane == 31) warp_tot[warp] = x;
     __syncthreads();
-    u32 base = 0;
-    for (int w = 0; w < warp; ++w) base += warp_tot[w];
-    sums[threadIdx.x] = x - v + base;
-    if (threadIdx.x == 255) sums[256] = x + base;
+    if (warp == 0) {
+        u32 w = warp_tot[lane], z = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
+        warp_tot[lane] = z - w;
+        if (lane == 31) B.sums[nb] = z;                // grand total
+    }
+    __syncthreads();
+    u32 run = x - mine + warp_tot[warp];
+    for (u32 i = lo; i < lo + per && i < nb; ++i) { const u32 v = B.sums[i]; B.sums[i] = run; run += v; }
 }
 __global__ void __launch_bounds__(256)
-k_defer_scatter(const ulonglong2* rec, const unsigned long long* count, unsigned long long cap, const u32* pos, const u32* boff,
-                const u32* sums, ulonglong2* out) {
+k_defer_scatter(const ulonglong2* rec, const unsigned long long* count, unsigned long long cap, const u32* pos, Buckets B,
+                ulonglong2* out) {
     const unsigned long long m = *count < cap ? *count : cap;
     for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < m; j += (unsigned long long)gridDim.x * blockDim.x) {
         const ulonglong2 r = rec[j];
         if (r.x == ~0ull) continue;
-        const u32 b = defer_bucket(r.x);
+        const u32 b = bucket_of(r.x, B.bits);
         // one 16-byte store per record: {address, target bits | its place in the list << 32} (the list index = the order
         // in which its warp appended it)
-        out[sums[b >> 10] + boff[b] + pos[j]] = make_ulonglong2(r.x, (r.y & 0xFFFFFFFFull) | ((u64)j << 32));
+        out[B.sums[b >> 10] + B.boff[b] + pos[j]] = make_ulonglong2(r.x, (r.y & 0xFFFFFFFFull) | ((u64)j << 32));
     }
 }
 // q <- q + lr (target - q) record after record; the value is written back with a compare-and-swap from what was read,
 // so that a rollout running on another stream cannot be overwritten (it rarely is: start again).  One kernel, two kinds
 // of blocks that run side by side: the first `long_blocks` blocks take the long buckets (more than kInlineBucket records:
-// a popular start state's action collects thousands per launch; queued in work[0 .. sums[257]) by k_defer_scan), one
-// WARP per bucket; the other blocks take one bucket per THREAD and skip the long ones.
-__device__ __forceinline__ void defer_bucket_range(const u32* boff, const u32* sums, u32 b, u32& begin, u32& end) {
-    begin = sums[b >> 10] + boff[b];
-    end = (b + 1 == kDeferBuckets) ? sums[256] : sums[(b + 1) >> 10] + boff[b + 1];
-}
+// a popular start state's action collects thousands per launch; queued by k_bucket_scan), one WARP per bucket; the other
+// blocks take one bucket per THREAD and skip the long ones.
 template <class TAB>
 __device__ __forceinline__ u32 load_q_bits(const float* p) {   // coherent at L2 / at the owner GPU
     u32 v;
@@ -924,16 +939,15 @@ __device__ __forceinline__ u32 load_q_bits(const float* p) {   // coherent at L2
 }
 template <class TAB>
 __global__ void __launch_bounds__(256)
-k_defer_apply(const __grid_constant__ TAB table, ulonglong2* rec, const u32* boff, const u32* sums, float lr, const u32* work,
-              int long_blocks) {
+k_defer_apply(const __grid_constant__ TAB table, ulonglong2* rec, Buckets B, float lr, int long_blocks) {
     __shared__ Slot* shard_base[G2048_MAX_PEERS];
     const auto tab = table.view(shard_base);
     using VIEW = decltype(tab);
     if ((int)blockIdx.x >= long_blocks) {
         const u32 b = (blockIdx.x - long_blocks) * blockDim.x + threadIdx.x;
-        if (b >= kDeferBuckets) return;
+        if (b >= B.count()) return;
         u32 begin, end;
-        defer_bucket_range(boff, sums, b, begin, end);
+        bucket_range(B, b, begin, end);
         if (end - begin > kInlineBucket) return;
         for (u32 r = begin; r < end; ++r) {
             const u64 k = rec[r].x;
@@ -969,10 +983,10 @@ k_defer_apply(const __grid_constant__ TAB table, ulonglong2* rec, const u32* bof
     // for every address of the bucket (in order of first appearance) the lanes fetch the bucket 32 records at a time and
     // fold the targets into the chain in record order: 3 dependent float operations per record, the sequential update
     const int lane = threadIdx.x & 31;
-    const u32 n_warps = (u32)long_blocks * (blockDim.x >> 5), n_work = sums[257];
+    const u32 n_warps = (u32)long_blocks * (blockDim.x >> 5), n_work = B.sums[B.blocks() + 1];
     for (u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_work; w += n_warps) {
         u32 begin, end;
-        defer_bucket_range(boff, sums, work[w], begin, end);
+        bucket_range(B, B.work[w], begin, end);
         u32 r = begin;
         for (;;) {                                     // warp-uniform
             // the next record that has not been applied yet, 32 at a time
@@ -1673,11 +1687,29 @@ int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int6
 
 
 namespace {
+// buckets for grouping about `records` records: four per bucket on average (2^10 .. 2^22 buckets)
+inline int bucket_bits_for(int64_t records) {
+    int bits = 10;
+    while (bits < 22 && (1ll << (bits + 2)) < records) ++bits;
+    return bits;
+}
+inline size_t bucket_bytes(int bits) { return 2 * align256(((size_t)1 << bits) * 4) + align256((((size_t)1 << (bits - 10)) + 2) * 4); }
+// carve boff | work | sums out of `p` and clear what must start at zero
+int make_buckets(char* p, int bits, cudaStream_t st, Buckets& B) {
+    B.bits = bits;
+    B.boff = (u32*)p; p += align256(((size_t)1 << bits) * 4);
+    B.work = (u32*)p; p += align256(((size_t)1 << bits) * 4);
+    B.sums = (u32*)p;
+    CK(cudaMemsetAsync(B.boff, 0, ((size_t)1 << bits) * sizeof(u32), st));
+    CK(cudaMemsetAsync(B.sums, 0, (((size_t)1 << (bits - 10)) + 2) * sizeof(u32), st));
+    return 0;
+}
 // a zeroed list of `cap` deferred updates and the buffers that group them, from the device's ring
 struct DeferBuffers {
     unsigned long long* count;
     ulonglong2 *rec, *rec_out;
-    u32 *pos, *boff, *sums, *work;
+    u32* pos;
+    Buckets buckets;
     int64_t cap;
 };
 int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B) {
@@ -1687,7 +1719,8 @@ int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B)
         set = &D->defer[D->defer_next++ % 4];
     }
     const size_t m = (size_t)cap;
-    const size_t need = 256 + 2 * align256(m * 16) + align256(m * 4) + 2 * align256(kDeferBuckets * 4) + align256(258 * 4);
+    const int bits = bucket_bits_for(cap / 2);      // the list is about half used
+    const size_t need = 256 + 2 * align256(m * 16) + align256(m * 4) + bucket_bytes(bits);
     if (set->bytes < need) {
         CK(cudaDeviceSynchronize());               // growing: nobody may still be using the old buffer
         if (set->buf) CK(cudaFree(set->buf));
@@ -1701,14 +1734,9 @@ int deferred_list(DeviceState* D, int64_t cap, cudaStream_t st, DeferBuffers& B)
     B.rec = (ulonglong2*)p; p += align256(m * 16);
     B.rec_out = (ulonglong2*)p; p += align256(m * 16);
     B.pos = (u32*)p; p += align256(m * 4);
-    B.boff = (u32*)p; p += align256(kDeferBuckets * 4);
-    B.work = (u32*)p; p += align256(kDeferBuckets * 4);
-    B.sums = (u32*)p;
     B.cap = cap;
     CK(cudaMemsetAsync(B.count, 0, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(B.boff, 0, kDeferBuckets * sizeof(u32), st));
-    CK(cudaMemsetAsync(B.sums, 0, 258 * sizeof(u32), st));
-    return 0;
+    return make_buckets(p, bits, st, B.buckets);
 }
 // room for one lost race in four env steps (measured: one in 18 on a local table, one in 9 on a table shared by 8 GPUs,
 // plus a quarter of slack in the warps' reservations; only the first launches after a common reset, where every env sits
@@ -1722,12 +1750,12 @@ int64_t deferred_capacity(int64_t n, int64_t k_steps) {
 template <class TAB>
 int apply_deferred(DeviceState* D, const TAB& tab, const DeferBuffers& B, float lr, cudaStream_t st) {
     const int g = grid_for(B.cap, 256, D->sm_count);
-    k_defer_count<<<g, 256, 0, st>>>(B.rec, B.count, (unsigned long long)B.cap, B.pos, B.boff);
-    k_defer_scan<<<kDeferBuckets / 1024, 1024, 0, st>>>(B.boff, B.sums, B.work);
-    k_defer_scan_sums<<<1, 256, 0, st>>>(B.sums);
-    k_defer_scatter<<<g, 256, 0, st>>>(B.rec, B.count, (unsigned long long)B.cap, B.pos, B.boff, B.sums, B.rec_out);
+    k_defer_count<<<g, 256, 0, st>>>(B.rec, B.count, (unsigned long long)B.cap, B.pos, B.buckets);
+    k_bucket_scan<<<B.buckets.blocks(), 1024, 0, st>>>(B.buckets);
+    k_bucket_scan_sums<<<1, 1024, 0, st>>>(B.buckets);
+    k_defer_scatter<<<g, 256, 0, st>>>(B.rec, B.count, (unsigned long long)B.cap, B.pos, B.buckets, B.rec_out);
     const int long_blocks = D->sm_count * 4;
-    k_defer_apply<TAB><<<long_blocks + kDeferBuckets / 256, 256, 0, st>>>(tab, B.rec_out, B.boff, B.sums, lr, B.work, long_blocks);
+    k_defer_apply<TAB><<<long_blocks + B.buckets.count() / 256, 256, 0, st>>>(tab, B.rec_out, B.buckets, lr, long_blocks);
     LAUNCH_CHECK("apply_deferred");
     return 0;
 }
