@@ -337,6 +337,25 @@ class OwnerComputesQLearning:
             self._carry_slot = torch.zeros(env.n, dtype=torch.int32, device=self.device) if self.window > 1 else None
             self._carry_row = torch.zeros((env.n, 4), dtype=torch.float32, device=self.device) if self.window > 1 else None
         self.epoch, self.t, self.k = 0, 0, 0      # barrier epoch, window number, step inside the window
+        # everything a step passes by pointer, built once per buffer slot (the step is short: per-step Python work --
+        # ctypes arrays, pointer arithmetic -- would be a third of it)
+        ct = ctypes
+        self._args = []
+        for slot in (0, 1):
+            self._args.append({
+                "lists": (ct.c_void_p * self.world)(*[self._list(self.rank, slot, j) for j in range(self.world)]),
+                "counts": self._counts(self.rank, slot),
+                "src": (ct.c_void_p * self.world)(*[self._counts(r, slot) + 8 * self.rank for r in range(self.world)]),
+                "mine": (ct.c_void_p * self.world)(*[self._list(r, slot, self.rank) for r in range(self.world)]),
+            })
+        self._host = (ct.c_uint64 * self.world)()
+        self._counts_i64 = (ct.c_int64 * self.world)()
+        self._ptrs = (env.boards.data_ptr(), env.aux.data_ptr(), env.score.data_ptr(), env.counters.data_ptr(),
+                      None if self._carry_slot is None else self._carry_slot.data_ptr(),
+                      None if self._carry_row is None else self._carry_row.data_ptr(), self.timed_out.data_ptr())
+        with torch.cuda.device(self.device):      # scratch for twice the even share of a window's records (grown if ever needed)
+            need = int(self.lib.g2048_qlearn_scratch_bytes(2 * self.cap * self.window))
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
 
     # layout helpers: counts[slot][j] and list[slot][j] inside rank r's buffer
     def _counts(self, r, slot):
@@ -345,30 +364,34 @@ class OwnerComputesQLearning:
     def _list(self, r, slot, j):
         return self.base[r] + self.HEAD + (slot * self.world + j) * self.list_bytes
 
-    def _barrier(self):
+    def _barrier(self, st=None):
         self.epoch += 1
-        self._check(self.lib.g2048_peer_barrier(self._flags, self.rank, self.world, self.epoch, 0,
-                                                self.timed_out.data_ptr(), torch.cuda.current_stream().cuda_stream),
-                    "g2048_peer_barrier")
+        rc = self.lib.g2048_peer_barrier(self._flags, self.rank, self.world, self.epoch, 0, self._ptrs[6],
+                                         st if st is not None else torch.cuda.current_stream().cuda_stream)
+        if rc:
+            self._check(rc, "g2048_peer_barrier")
 
     def step(self):
         """One env step of every env of this rank; returns the number of records this rank applied to its shard (0
         inside a window)."""
-        ct, env, sh, slot = self._ct, self.env, self.shared, self.t & 1
+        env, sh, slot = self.env, self.shared, self.t & 1
+        if env.boards.data_ptr() != self._ptrs[0]:           # the env's buffers were replaced: take the new addresses
+            self._ptrs = (env.boards.data_ptr(), env.aux.data_ptr(), env.score.data_ptr(), env.counters.data_ptr()) + self._ptrs[4:]
+        args, p = self._args[slot], self._ptrs
         st = torch.cuda.current_stream().cuda_stream
         total = 0
         self._check_timeout()
         with torch.cuda.device(self.device):
             if self.k == 0:
-                self._check(self.lib.g2048_peer_memset(self._counts(self.rank, slot), 0, 128, st), "g2048_peer_memset")
-            lists = (ct.c_void_p * self.world)(*[self._list(self.rank, slot, j) for j in range(self.world)])
-            self._check(self.lib.g2048_qlearn_emit_owned(
-                env.boards.data_ptr(), env.aux.data_ptr(), env.score.data_ptr(), sh._arr, sh.n_shards, sh.slots_per_shard,
-                env.n, env.flavour, self.gamma, float(self.eps), env.seed, env.step_idx, env.env_id_base,
-                self.k * self.n_total + self.lo, self.idx_bits, env.counters.data_ptr(), lists,
-                self._counts(self.rank, slot), None if self._carry_slot is None else self._carry_slot.data_ptr(),
-                None if self._carry_row is None else self._carry_row.data_ptr(), int(self.k > 0), st),
-                "g2048_qlearn_emit_owned")
+                rc = self.lib.g2048_peer_memset(args["counts"], 0, 128, st)
+                if rc:
+                    self._check(rc, "g2048_peer_memset")
+            rc = self.lib.g2048_qlearn_emit_owned(
+                p[0], p[1], p[2], sh._arr, sh.n_shards, sh.slots_per_shard, env.n, env.flavour, self.gamma, float(self.eps),
+                env.seed, env.step_idx, env.env_id_base, self.k * self.n_total + self.lo, self.idx_bits, p[3],
+                args["lists"], args["counts"], p[4], p[5], int(self.k > 0), st)
+            if rc:
+                self._check(rc, "g2048_qlearn_emit_owned")
             env.step_idx += 1
             self.k += 1
             if self.k == self.window:
@@ -388,22 +411,25 @@ class OwnerComputesQLearning:
         return total
 
     def _exchange_and_apply(self, slot, st):
-        ct, sh = self._ct, self.shared
-        self._barrier()                                     # every rank's records and counts are written
-        src = (ct.c_void_p * self.world)(*[self._counts(r, slot) + 8 * self.rank for r in range(self.world)])
-        host = (ct.c_uint64 * self.world)()
-        self._check(self.lib.g2048_peer_read_u64(src, self.world, host, st), "g2048_peer_read_u64")
+        sh, args, host, counts = self.shared, self._args[slot], self._host, self._counts_i64
+        self._barrier(st)                                   # every rank's records and counts are written
+        rc = self.lib.g2048_peer_read_u64(args["src"], self.world, host, st)
+        if rc:
+            self._check(rc, "g2048_peer_read_u64")
         self._check_timeout()                               # (the read synchronised the stream: the barrier is over)
-        counts = (ct.c_int64 * self.world)(*[int(x) for x in host])
-        total = sum(int(x) for x in host)
-        need = int(self.lib.g2048_qlearn_scratch_bytes(max(total, 1)))
-        if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
-        mine = (ct.c_void_p * self.world)(*[self._list(r, slot, self.rank) for r in range(self.world)])
-        self._check(self.lib.g2048_qtable_apply_owned(sh.ptrs[self.rank], sh.slots_per_shard, mine, counts, self.world,
-                                                      self.idx_bits, self.lr, self._scratch.data_ptr(),
-                                                      self._scratch.numel(), st), "g2048_qtable_apply_owned")
-        self._barrier()                                     # all shards updated before anyone reads them again
+        total = 0
+        for r in range(self.world):
+            counts[r] = host[r]
+            total += host[r]
+        if total > 2 * self.cap * self.window:              # a very uneven split: more scratch
+            need = int(self.lib.g2048_qlearn_scratch_bytes(total))
+            if self._scratch.numel() < need:
+                self._scratch = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
+        rc = self.lib.g2048_qtable_apply_owned(sh.ptrs[self.rank], sh.slots_per_shard, args["mine"], counts, self.world,
+                                               self.idx_bits, self.lr, self._scratch.data_ptr(), self._scratch.numel(), st)
+        if rc:
+            self._check(rc, "g2048_qtable_apply_owned")
+        self._barrier(st)                                   # all shards updated before anyone reads them again
         return total
 
     def _check_timeout(self):
