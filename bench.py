@@ -517,7 +517,7 @@ def main():
                          "request_bound": {"table_visits_per_sec": 17.5e9, "env_steps_per_sec": 17.5e9 / table_stats["valid_fraction"],
                                            "frac_of_bound": value / world * table_stats["valid_fraction"] / 17.5e9,
                                            "source": "tools/membench5.cu: random 32 B load that misses L2 + ONE write-type request"},
-                         "note": "achieved = 32 algorithmic B/env-step / duration of the whole call (k_rollout_qlearn = 91 % of "
+                         "note": "achieved = 32 algorithmic B/env-step / duration of the whole call (k_rollout_qlearn = 89 % of "
                                  "it, the deferred-update kernels the rest; CUDA events around the call).  The memory system "
                                  "charges per request, not per byte (profiles/r02_membench.txt): a table visit of one load + "
                                  "one write-type request runs at 17.5 G/s at most = 8.6 % of the streaming peak at 32 B; "
