@@ -102,6 +102,11 @@ _SIG = {
     "g2048_peer_close": (i32, [vp]),
     "g2048_peer_free": (i32, [vp]),
     "g2048_peer_barrier": (i32, [vp, i32, i32, u64, u64, vp, vp]),
+    "g2048_routed_buffer_bytes": (sz, [i32, i64]),
+    "g2048_routed_create": (vp, [i32, i32, i64, i64, vp, vp, u64]),
+    "g2048_routed_destroy": (None, [vp]),
+    "g2048_routed_prime": (i32, [vp, vp, i64, vp]),
+    "g2048_routed_step": (i32, [vp, vp, vp, vp, i64, i32, f32, f32, f64, u64, u64, u64, vp, vp, vp]),
     "g2048_qtable_bytes": (sz, [u64]),
     "g2048_qtable_clear": (i32, [vp, u64, vp]),
     "g2048_qtable_lookup": (i32, [vp, u64, vp, i64, vp, vp, i32, vp]),

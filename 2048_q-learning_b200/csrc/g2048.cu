@@ -765,6 +765,219 @@ __global__ void k_peer_barrier(PeerFlags F, int rank, int world, u64 epoch, u64 
     }
 }
 
+// ---- exact synchronous step on a SHARDED table, ROUTED: every table access is local to the owner ---------------
+// k_qlearn_emit_owned looks s and s' up wherever they live: ~2.4 small NVLink requests per env, and the rate of small
+// remote requests (6.7 G/s per GPU) is what bounds that step.  Here nothing but coalesced lists crosses NVLink:
+//   k_routed_request  every env takes (slot, row) of its state from the answers of the last step, chooses, steps, and
+//                     appends the key of s' (and of the fresh board after a game over) to its list for the GPU that OWNS
+//                     the key's home slot                                                        [local writes]
+//   k_routed_lookup   the owner pulls the lists written for it (coalesced peer reads), finds-or-inserts every key in
+//                     its OWN shard and pushes {slot, max Q} to the same place of the requester's answer buffer
+//   k_routed_records  the requester builds r + gamma max Q(s') and appends the record to its list for the owner of s
+//   (k_gather_owned + sort + k_segment_apply: the owner applies its records, as in the owner-computes step)
+//   k_routed_rows     the owner pushes the rows as they are AFTER the apply for every request: what the next step's
+//                     choose_action reads
+// with a flag barrier after each of the four.  A request handle = owner << 28 | place in the list for that owner.
+struct RoutedLocal {                 // the requester's side: everything lives in this GPU's memory
+    u64* req_out[G2048_MAX_PEERS];            // keys for owner d
+    ulonglong2* rec_out[G2048_MAX_PEERS];     // records for owner d
+    const uint2* reply1[G2048_MAX_PEERS];     // {slot, max Q bits} from owner d, same places as req_out[d]
+    const float4* reply2[G2048_MAX_PEERS];    // rows after the apply from owner d
+    unsigned long long* req_count;            // [world]
+    unsigned long long* rec_count;            // [world]
+    u64* sk;                                  // per env: sort key of its record (all ones: the state has no slot)
+    u32* req1;                                // per env: handle of the request for s'
+    u32* cur;                                 // per env: handle of the request that answers for the state it sits in
+    float* reward;                            // per env
+    u32* meta;                                // per env: owner of s | done << 8
+    int world, idx_bits;
+    u32 owner_shift;                          // owner(key) = (mix64(key) >> owner_shift) & (world - 1)
+};
+struct RoutedServe {                 // the owner's side
+    const u64* req[G2048_MAX_PEERS];                        // rank r's keys for this GPU          (peer memory, read)
+    const unsigned long long* req_count[G2048_MAX_PEERS];   // how many                            (peer memory, read)
+    uint2* reply1[G2048_MAX_PEERS];                          // this GPU's part of r's answer buffer (peer memory, written)
+    float4* reply2[G2048_MAX_PEERS];
+    u32* saved_slot[G2048_MAX_PEERS];                        // local: slot of every request, kept for k_routed_rows
+    unsigned long long* count_cache;                        // local [world]: the counts k_routed_lookup read
+    int world;
+};
+constexpr u32 kHandleBits = 28;
+// the lanes of a warp that append to the same list take consecutive places with one atomicAdd (all 32 lanes call this;
+// list < 0: nothing to append); returns the place
+__device__ __forceinline__ u32 warp_append(int list, unsigned long long* counts) {
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, list);
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader && list >= 0) base = atomicAdd(&counts[list], (unsigned long long)__popc(peers));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return (u32)base + (u32)__popc(peers & ((1u << lane) - 1u));
+}
+template <int FLAVOUR, bool PRIME>
+__global__ void __launch_bounds__(256)
+k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ RoutedLocal R, long long n,
+                 u64 eps_thresh, u64 seed, u64 t, u64 id_base, u64 rec_base, long long* counters) {
+    __shared__ u64* req_out[G2048_MAX_PEERS];
+    __shared__ const uint2* reply1[G2048_MAX_PEERS];
+    __shared__ const float4* reply2[G2048_MAX_PEERS];
+    if (threadIdx.x < G2048_MAX_PEERS) {
+        req_out[threadIdx.x] = R.req_out[threadIdx.x];
+        reply1[threadIdx.x] = R.reply1[threadIdx.x];
+        reply2[threadIdx.x] = R.reply2[threadIdx.x];
+    }
+    __syncthreads();
+    Lut L = global_lut(T);
+    Counters c;
+    const int lane = threadIdx.x & 31;
+    const u32 owner_mask = (u32)R.world - 1u;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {   // warp-uniform
+        const long long i = i0 + lane;
+        int owner1 = -1, owner2 = -1;
+        u64 key1 = 0, key2 = 0;
+        if (i < n) {
+            if (PRIME) {
+                key1 = boards[i];
+            } else {
+                Env e;
+                env_load(e, boards[i], (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) ? aux[i] : G2048_AUX_INIT, score ? score[i] : 0);
+                const u64 id = id_base + (u64)i;
+                const u32 cur = R.cur[i], os = cur >> kHandleBits, pos = cur & ((1u << kHandleBits) - 1u);
+                const u32 slot = reply1[os][pos].x;
+                const float4 row = reply2[os][pos];
+                Draw4 x = philox(seed, id, t, G2048_STREAM_STEP);
+                const int a = choose_action(row, x, eps_thresh);
+                StepOut o;
+                philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
+                c.add(o);
+                key1 = e.board;                       // s' (== s after an invalid move: the owner answers for s again)
+                R.sk[i] = slot == kNoSlot ? ~0ull : (((((u64)slot << 2) | (u64)a) << R.idx_bits) | (rec_base + (u64)i));
+                R.reward[i] = (float)o.reward;
+                R.meta[i] = os | (o.done ? 256u : 0u);
+                if (o.done) {
+                    philox_autoreset(e, seed, id, t);
+                    key2 = e.board;
+                    owner2 = (int)((u32)(mix64(key2) >> R.owner_shift) & owner_mask);
+                }
+                boards[i] = e.board;
+                if (FLAVOUR == G2048_FLAVOUR_PENALTY && aux) aux[i] = env_to_aux(e);
+                if (score) score[i] = e.score;
+            }
+            owner1 = (int)((u32)(mix64(key1) >> R.owner_shift) & owner_mask);
+        }
+        const u32 p1 = warp_append(owner1, R.req_count);
+        if (owner1 >= 0) req_out[owner1][p1] = key1;
+        u32 h1 = ((u32)owner1 << kHandleBits) | p1, h2 = h1;
+        if (!PRIME && __any_sync(0xFFFFFFFFu, owner2 >= 0)) {
+            const u32 p2 = warp_append(owner2, R.req_count);
+            if (owner2 >= 0) {
+                req_out[owner2][p2] = key2;
+                h2 = ((u32)owner2 << kHandleBits) | p2;
+            }
+        }
+        if (i < n) {
+            R.req1[i] = h1;
+            R.cur[i] = h2;
+        }
+    }
+    flush_counters(c, counters);
+}
+// prefix ends of the `world` request lists in shared memory; returns the total
+__device__ __forceinline__ long long routed_ends(const unsigned long long* cnt, int world, long long* end) {
+    if (threadIdx.x == 0) {
+        long long s = 0;
+        for (int j = 0; j < world; ++j) { s += (long long)cnt[j]; end[j] = s; }
+    }
+    __syncthreads();
+    return end[world - 1];
+}
+__global__ void __launch_bounds__(256)
+k_routed_lookup(Slot* shard, u64 mask, const __grid_constant__ RoutedServe V, long long* counters, const int* abort_flag) {
+    __shared__ unsigned long long cnt[G2048_MAX_PEERS];
+    __shared__ long long end[G2048_MAX_PEERS];
+    if (abort_flag && *(const volatile int*)abort_flag != 0) return;   // a peer never reached the barrier: its list is not valid
+    if ((int)threadIdx.x < V.world) {
+        unsigned long long v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(V.req_count[threadIdx.x]) : "memory");
+        cnt[threadIdx.x] = v;
+        if (blockIdx.x == 0) V.count_cache[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const long long m = routed_ends(cnt, V.world, end);
+    Counters c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (i >= end[j]) ++j;
+        const long long local = i - (j ? end[j - 1] : 0);
+        u64 key;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(key) : "l"(V.req[j] + local) : "memory");
+        float4 row;
+        const u32 slot = table_find<true>(shard, mask, key, row, c.inserts);
+        c.dropped += (slot == kNoSlot);
+        V.saved_slot[j][local] = slot;
+        V.reply1[j][local] = make_uint2(slot, __float_as_uint(max4(row)));
+    }
+    flush_counters(c, counters);
+}
+__global__ void __launch_bounds__(256)
+k_routed_rows(const Slot* shard, const __grid_constant__ RoutedServe V, const int* abort_flag) {
+    __shared__ unsigned long long cnt[G2048_MAX_PEERS];
+    __shared__ long long end[G2048_MAX_PEERS];
+    if (abort_flag && *(const volatile int*)abort_flag != 0) return;
+    if ((int)threadIdx.x < V.world) cnt[threadIdx.x] = V.count_cache[threadIdx.x];
+    __syncthreads();
+    const long long m = routed_ends(cnt, V.world, end);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (i >= end[j]) ++j;
+        const long long local = i - (j ? end[j - 1] : 0);
+        const u32 slot = V.saved_slot[j][local];
+        float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (slot != kNoSlot) {
+            u64 k;
+            load_slot<false>(shard + slot, k, row);
+        }
+        V.reply2[j][local] = row;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_routed_records(const __grid_constant__ RoutedLocal R, long long n, float gamma) {
+    __shared__ ulonglong2* rec_out[G2048_MAX_PEERS];
+    __shared__ const uint2* reply1[G2048_MAX_PEERS];
+    if (threadIdx.x < G2048_MAX_PEERS) {
+        rec_out[threadIdx.x] = R.rec_out[threadIdx.x];
+        reply1[threadIdx.x] = R.reply1[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {   // warp-uniform
+        const long long i = i0 + lane;
+        int owner = -1;
+        u64 sk = ~0ull;
+        float target = 0.f;
+        if (i < n) {
+            sk = R.sk[i];
+            const u32 h = R.req1[i], meta = R.meta[i];
+            const uint2 ans = reply1[h >> kHandleBits][h & ((1u << kHandleBits) - 1u)];
+            target = td_target(gamma, R.reward[i], __uint_as_float(ans.y), (meta & 256u) != 0);
+            if (sk != ~0ull) owner = (int)(meta & 255u);
+        }
+        const u32 p = warp_append(owner, R.rec_count);
+        if (owner >= 0) rec_out[owner][p] = make_ulonglong2(sk, (u64)__float_as_uint(target));
+    }
+}
+// `world` 8-byte values at local or peer addresses -> pinned host memory (one launch instead of `world` small copies)
+struct PeerWords { const u64* ptr[G2048_MAX_PEERS]; };
+__global__ void k_peer_words_to_host(PeerWords W, int world, u64* host_out) {
+    if ((int)threadIdx.x < world) {
+        u64 v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(W.ptr[threadIdx.x]) : "memory");
+        host_out[threadIdx.x] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_apply_atomic(Slot* tab, const u64* sortkey, const float* target, float lr, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1999,6 +2212,228 @@ G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, ui
     int* abort_flag = (dev >= 0 && dev < kMaxDevices && g_dev[dev].ready) ? g_dev[dev].abort_flag : nullptr;
     k_peer_barrier<<<1, 32, 0, S(stream)>>>(F, rank, world, epoch, timeout_ns ? timeout_ns : 5000000000ull, timed_out, abort_flag);
     LAUNCH_CHECK("k_peer_barrier");
+    return 0;
+}
+
+// ---- exact synchronous step on a sharded table, routed (see k_routed_request)
+// Layout of the buffer every rank shares with its peers (CUDA IPC), C = cap (the largest env count of any rank):
+//   [0, 128) barrier flags | [256, 384) request counts per owner | [512, 640) record counts per owner | from 1024:
+//   req_out[world][2C] u64 | rec_out[world][C] 16 B | reply1[world][2C] 8 B | reply2[world][2C] 16 B
+namespace {
+constexpr size_t kRoutedHead = 1024, kRoutedReqCount = 256, kRoutedRecCount = 512;
+struct RoutedLayout {
+    size_t req, rec, reply1, reply2, req_stride, rec_stride, r1_stride, r2_stride, total;
+};
+RoutedLayout routed_layout(int world, int64_t cap) {
+    RoutedLayout l{};
+    const size_t c = (size_t)(cap > 0 ? cap : 1);
+    l.req_stride = align256(2 * c * 8);
+    l.rec_stride = align256(c * 16);
+    l.r1_stride = align256(2 * c * 8);
+    l.r2_stride = align256(2 * c * 16);
+    l.req = kRoutedHead;
+    l.rec = l.req + (size_t)world * l.req_stride;
+    l.reply1 = l.rec + (size_t)world * l.rec_stride;
+    l.reply2 = l.reply1 + (size_t)world * l.r1_stride;
+    l.total = l.reply2 + (size_t)world * l.r2_stride;
+    return l;
+}
+}  // namespace
+struct g2048_routed {
+    int device = 0, rank = 0, world = 1, idx_bits = 1;
+    int64_t cap = 0, n_total = 0;
+    Slot* shard = nullptr;
+    uint64_t slots = 0;
+    RoutedLocal L{};
+    RoutedServe V{};
+    PeerFlags F{};
+    PeerWords rec_counts{};          // rank r's count of records for this GPU
+    RecordLists recs{};              // rank r's records for this GPU (ptr only; ends are filled per step)
+    char* local = nullptr;           // per-env state of the requester side + saved slots of the owner side
+    void* sort_buf = nullptr;
+    size_t sort_bytes = 0;
+    u64* host_counts = nullptr;      // pinned: [world] record counts, [world] = the barrier's time-out flag (int)
+    int* timed_out = nullptr;
+    u64 epoch = 0;
+    bool primed = false;
+};
+namespace {
+int routed_barrier(g2048_routed* r, DeviceState* D, cudaStream_t st) {
+    r->epoch += 1;
+    k_peer_barrier<<<1, 32, 0, st>>>(r->F, r->rank, r->world, r->epoch, 5000000000ull, r->timed_out, D->abort_flag);
+    LAUNCH_CHECK("k_peer_barrier");
+    return 0;
+}
+int routed_check(g2048_routed* r) {
+    if (*(volatile int*)r->timed_out) return fail(G2048_ERR_PEER, "g2048_routed: a peer did not reach the barrier (the ranks are no longer in step)");
+    return 0;
+}
+}  // namespace
+
+G2048_API size_t g2048_routed_buffer_bytes(int world, int64_t cap) {
+    if (world < 1 || world > G2048_MAX_PEERS || cap < 1) return 0;
+    return routed_layout(world, cap).total;
+}
+G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, int64_t n_total, void* const* peer_buffers,
+                                            void* shard, uint64_t slots_per_shard) {
+    DeviceState* D = nullptr;
+    if (current_device_state(&D)) return nullptr;
+    if (world < 1 || world > G2048_MAX_PEERS || (world & (world - 1)) || rank < 0 || rank >= world || cap < 1 ||
+        2 * cap >= (1ll << kHandleBits) || n_total < 1 || !peer_buffers || !shard || !pow2(slots_per_shard)) {
+        fail(G2048_ERR_ARG, "g2048_routed_create: bad arguments");
+        return nullptr;
+    }
+    for (int j = 0; j < world; ++j)
+        if (!peer_buffers[j] || ((uintptr_t)peer_buffers[j] & 255)) { fail(G2048_ERR_ARG, "g2048_routed_create: bad peer buffer"); return nullptr; }
+    g2048_routed* r = new g2048_routed();
+    cudaGetDevice(&r->device);
+    r->rank = rank; r->world = world; r->cap = cap; r->n_total = n_total;
+    r->shard = (Slot*)shard; r->slots = slots_per_shard;
+    r->idx_bits = 1;
+    while (((uint64_t)(n_total - 1) >> r->idx_bits) != 0) ++r->idx_bits;
+    int slot_bits = 0;
+    while ((1ull << slot_bits) < slots_per_shard) ++slot_bits;
+    if (slot_bits + 2 + r->idx_bits > 63) { fail(G2048_ERR_ARG, "g2048_routed_create: slot and env index do not fit one sort key"); delete r; return nullptr; }
+    const RoutedLayout lay = routed_layout(world, cap);
+    char* mine = (char*)peer_buffers[rank];
+    // requester side
+    const size_t c = (size_t)cap;
+    const size_t local_bytes = align256(c * 8) + 4 * align256(c * 4) + (size_t)world * align256(2 * c * 4) + 256;
+    if (cudaMalloc(&r->local, local_bytes) != cudaSuccess || cudaMemset(r->local, 0, local_bytes) != cudaSuccess ||
+        cudaHostAlloc(&r->host_counts, (G2048_MAX_PEERS + 1) * sizeof(u64), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        fail((int)cudaGetLastError(), "g2048_routed_create: allocation");
+        if (r->local) cudaFree(r->local);
+        delete r;
+        return nullptr;
+    }
+    memset(r->host_counts, 0, (G2048_MAX_PEERS + 1) * sizeof(u64));
+    r->timed_out = (int*)(r->host_counts + G2048_MAX_PEERS);
+    char* p = r->local;
+    r->L.sk = (u64*)p; p += align256(c * 8);
+    r->L.req1 = (u32*)p; p += align256(c * 4);
+    r->L.cur = (u32*)p; p += align256(c * 4);
+    r->L.reward = (float*)p; p += align256(c * 4);
+    r->L.meta = (u32*)p; p += align256(c * 4);
+    for (int j = 0; j < world; ++j) { r->V.saved_slot[j] = (u32*)p; p += align256(2 * c * 4); }
+    r->V.count_cache = (unsigned long long*)p;
+    r->L.world = world; r->L.idx_bits = r->idx_bits; r->L.owner_shift = (u32)slot_bits;
+    r->L.req_count = (unsigned long long*)(mine + kRoutedReqCount);
+    r->L.rec_count = (unsigned long long*)(mine + kRoutedRecCount);
+    r->V.world = world;
+    for (int j = 0; j < world; ++j) {
+        char* peer = (char*)peer_buffers[j];
+        r->L.req_out[j] = (u64*)(mine + lay.req + (size_t)j * lay.req_stride);
+        r->L.rec_out[j] = (ulonglong2*)(mine + lay.rec + (size_t)j * lay.rec_stride);
+        r->L.reply1[j] = (const uint2*)(mine + lay.reply1 + (size_t)j * lay.r1_stride);
+        r->L.reply2[j] = (const float4*)(mine + lay.reply2 + (size_t)j * lay.r2_stride);
+        r->V.req[j] = (const u64*)(peer + lay.req + (size_t)rank * lay.req_stride);
+        r->V.req_count[j] = (const unsigned long long*)(peer + kRoutedReqCount) + rank;
+        r->V.reply1[j] = (uint2*)(peer + lay.reply1 + (size_t)rank * lay.r1_stride);
+        r->V.reply2[j] = (float4*)(peer + lay.reply2 + (size_t)rank * lay.r2_stride);
+        r->F.ptr[j] = (u64*)peer;
+        r->rec_counts.ptr[j] = (const u64*)(peer + kRoutedRecCount) + rank;
+        r->recs.ptr[j] = (const ulonglong2*)(peer + lay.rec + (size_t)rank * lay.rec_stride);
+    }
+    r->recs.n_lists = world;
+    return r;
+}
+G2048_API void g2048_routed_destroy(g2048_routed* r) {
+    if (!r) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(r->device);
+    if (r->local) cudaFree(r->local);
+    if (r->sort_buf) cudaFree(r->sort_buf);
+    if (r->host_counts) cudaFreeHost(r->host_counts);
+    cudaSetDevice(prev);
+    delete r;
+}
+G2048_API int g2048_routed_prime(g2048_routed* r, const uint64_t* boards, int64_t n, void* stream) {
+    DEVSTATE();
+    if (!r || n < 0 || n > r->cap || (n && !boards)) return fail(G2048_ERR_ARG, "g2048_routed_prime: bad arguments");
+    cudaStream_t st = S(stream);
+    int rc;
+    CK(cudaMemsetAsync(r->L.req_count, 0, 128, st));
+    CK(cudaMemsetAsync(r->L.rec_count, 0, 128, st));
+    if ((rc = routed_barrier(r, D, st))) return rc;            // nobody still reads the counts of an earlier use
+    if (n) {
+        k_routed_request<0, true><<<grid_for(n, 256, D->sm_count), 256, 0, st>>>(D->tables, (u64*)boards, nullptr, nullptr, r->L, n, 0, 0,
+                                                                                  0, 0, 0, nullptr);
+        LAUNCH_CHECK("k_routed_request");
+    }
+    if ((rc = routed_barrier(r, D, st))) return rc;
+    const int g = grid_for(2 * r->cap, 256, D->sm_count);
+    k_routed_lookup<<<g, 256, 0, st>>>(r->shard, r->slots - 1, r->V, nullptr, D->abort_flag);
+    LAUNCH_CHECK("k_routed_lookup");
+    if ((rc = routed_barrier(r, D, st))) return rc;
+    CK(cudaMemsetAsync(r->L.req_count, 0, 128, st));
+    k_routed_rows<<<g, 256, 0, st>>>(r->shard, r->V, D->abort_flag);
+    LAUNCH_CHECK("k_routed_rows");
+    if ((rc = routed_barrier(r, D, st))) return rc;
+    CK(cudaStreamSynchronize(st));
+    r->primed = true;
+    return routed_check(r);
+}
+G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n, int flavour,
+                                float lr, float gamma, double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base,
+                                int64_t* counters, int64_t* applied, void* stream) {
+    DEVSTATE();
+    if (!r || n < 0 || n > r->cap || (n && !boards) || (flavour != 0 && flavour != 1))
+        return fail(G2048_ERR_ARG, "g2048_routed_step: bad arguments");
+    if (!r->primed) return fail(G2048_ERR_ARG, "g2048_routed_step: call g2048_routed_prime first");
+    if (((env_id_base + (uint64_t)(n ? n - 1 : 0)) >> r->idx_bits) != 0)
+        return fail(G2048_ERR_ARG, "g2048_routed_step: env_id_base + n exceeds the total the exchange was created for");
+    cudaStream_t st = S(stream);
+    int rc;
+    if ((rc = routed_check(r))) return rc;
+    const int ge = grid_for(n, 256, D->sm_count), gs = grid_for(2 * r->cap, 256, D->sm_count);
+    CK(cudaMemsetAsync(r->L.rec_count, 0, 128, st));             // (the owners read it before the last barrier of the step before)
+    if (n) {
+#define REQ(F) k_routed_request<F, false><<<ge, 256, 0, st>>>(D->tables, (u64*)boards, (u64*)aux, score, r->L, n, eps_threshold(eps), \
+                                                               seed, step_idx, env_id_base, env_id_base, (long long*)counters)
+        if (flavour == 0) REQ(0); else REQ(1);
+#undef REQ
+        LAUNCH_CHECK("k_routed_request");
+    }
+    if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's requests are written
+    k_routed_lookup<<<gs, 256, 0, st>>>(r->shard, r->slots - 1, r->V, (long long*)counters, D->abort_flag);
+    LAUNCH_CHECK("k_routed_lookup");
+    if ((rc = routed_barrier(r, D, st))) return rc;            // the answers are there; every owner has read my requests
+    CK(cudaMemsetAsync(r->L.req_count, 0, 128, st));
+    if (n) {
+        k_routed_records<<<ge, 256, 0, st>>>(r->L, n, gamma);
+        LAUNCH_CHECK("k_routed_records");
+    }
+    if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's records are written
+    k_peer_words_to_host<<<1, 32, 0, st>>>(r->rec_counts, r->world, r->host_counts);
+    LAUNCH_CHECK("k_peer_words_to_host");
+    CK(cudaStreamSynchronize(st));
+    if ((rc = routed_check(r))) return rc;
+    long long total = 0;
+    for (int j = 0; j < r->world; ++j) {
+        total += (long long)r->host_counts[j];
+        r->recs.end[j] = total;
+    }
+    if (total > 0) {
+        const size_t need = scratch_bytes(total);
+        if (r->sort_bytes < need) {
+            if (r->sort_buf) CK(cudaFree(r->sort_buf));
+            r->sort_buf = nullptr;
+            r->sort_bytes = 0;
+            const size_t want = scratch_bytes(total + total / 4 + 1024);
+            CK(cudaMalloc(&r->sort_buf, want));
+            r->sort_bytes = want;
+        }
+        Scratch sc{};
+        if ((rc = carve(r->sort_buf, r->sort_bytes, total, sc))) return rc;
+        k_gather_owned<<<grid_for(total, 256, D->sm_count), 256, 0, st>>>(r->recs, total, sc.key_in, sc.val_in, D->abort_flag);
+        LAUNCH_CHECK("k_gather_owned");
+        if ((rc = apply_records(D, r->shard, r->slots, sc, total, lr, G2048_MODE_DETERMINISTIC, st, r->idx_bits))) return rc;
+    }
+    k_routed_rows<<<gs, 256, 0, st>>>(r->shard, r->V, D->abort_flag);
+    LAUNCH_CHECK("k_routed_rows");
+    if ((rc = routed_barrier(r, D, st))) return rc;            // the rows for the next step are there
+    if (applied) *applied = total;
     return 0;
 }
 

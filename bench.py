@@ -610,11 +610,15 @@ def shared_learning_measurement(torch, dist, g2048, dev, rank, world, n_total, m
     slots_total = 1 << 30
     out = []
 
-    def run_owner(window, warm, steps):
+    def run_owner(window, warm, steps, routed=False):
         env = g2048.BatchedGame2048Env(n, "penalty", device=dev.index, seed=SEED, env_id_base=rank * n)
         env.reset()
         shared = gdist.SharedQTable(L, dev, slots_total // world)
-        oc = gdist.OwnerComputesQLearning(env, shared, n_total, LR, GAMMA, EPS, window=window)
+        if routed:
+            oc = gdist.RoutedQLearning(env, shared, n_total, LR, GAMMA, EPS)
+            oc.flush = lambda: 0
+        else:
+            oc = gdist.OwnerComputesQLearning(env, shared, n_total, LR, GAMMA, EPS, window=window)
         for _ in range(warm):
             oc.step()
         barrier()
@@ -677,11 +681,16 @@ def shared_learning_measurement(torch, dist, g2048, dev, rank, world, n_total, m
         barrier()
         return d
 
-    for window, warm, steps in ((1, 4, 12), (16, 16, 32)):
-        dt, digest, cnt = run_owner(window, warm, steps)
-        ref = one_gpu_reference(window, warm + steps)
+    refs = {}                 # both every-step modes are compared with the same single-GPU run
+    for window, warm, steps, routed in ((1, 4, 12, True), (1, 4, 12, False), (16, 16, 32, False)):
+        dt, digest, cnt = run_owner(window, warm, steps, routed)
+        if (window, warm + steps) not in refs:
+            refs[(window, warm + steps)] = one_gpu_reference(window, warm + steps)
+        ref = refs[(window, warm + steps)]
         if rank == 0:
-            out.append({"mode": f"owner computes, exact, exchange every {window} step" + ("s" if window > 1 else ""),
+            name = ("routed, exact, exchange every step (lookups and records travel to the owner as bulk lists; no remote table access)"
+                    if routed else f"owner computes, exact, exchange every {window} step" + ("s" if window > 1 else ""))
+            out.append({"mode": name,
                         "env_steps_per_sec": n_total * steps / dt, "ms_per_step": dt / steps * 1e3, "envs_total": n_total,
                         "envs_per_gpu": n, "steps_timed": steps, "table_digest": digest, "digest_1gpu": ref,
                         "digest_equal_to_1gpu": digest == ref, "lost": int(cnt[8]), "dropped": int(cnt[7])})

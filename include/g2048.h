@@ -42,6 +42,7 @@
 #define G2048_ERR_ARG (-1)      /* bad argument (null pointer, bad flavour/mode, capacity not 2^k ...) */
 #define G2048_ERR_NOINIT (-2)   /* g2048_init(device) was not called for the current device */
 #define G2048_ERR_NOMEM (-3)    /* scratch buffer too small / allocation failed */
+#define G2048_ERR_PEER (-4)     /* a peer GPU did not reach a barrier of the exchange in time: the ranks are out of step */
 
 /* env flavours */
 #define G2048_FLAVOUR_PENALTY 0    /* ENV-P: shaped float64 reward, stall penalty, lagged done */
@@ -287,6 +288,39 @@ G2048_API int g2048_peer_free(void* dev_ptr);
  * valid), and the caller must stop (dist.py raises at the step). */
 G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, uint64_t epoch, uint64_t timeout_ns,
                                  int* timed_out, void* stream);
+
+/* The same exact step, ROUTED (round 2): no GPU ever touches another GPU's shard.  The owner of a state is the GPU that
+ * holds its home slot, owner(key) = top bits of the global home slot, exactly as in the sharded table above; a probe
+ * sequence stays inside the shard.  Per step (update_q_value of every env on ONE table, main.py:40-43; choose_action on
+ * the table as it stands at step start, main.py:34-38):
+ *   1. every env takes (slot, row) of its state from the owner's last answer, chooses, steps, and appends the key of s'
+ *      (after a game over also the fresh board) to its list for the owner of that key          -- barrier --
+ *   2. every owner pulls the lists written for it (coalesced NVLink reads), finds-or-inserts the keys in its own shard
+ *      and pushes {slot, max Q} into the requester's answer buffer (coalesced NVLink writes)   -- barrier --
+ *   3. every env forms r + gamma max Q(s') and appends its record to the list for the owner of s   -- barrier --
+ *   4. every owner sorts and applies the records for its shard (ascending global env index per (s, a), as
+ *      g2048_qtable_apply_owned) and pushes the rows as they are now for every request of 2.   -- barrier --
+ * Same table as the single-GPU deterministic g2048_qlearn_step, bit for bit (states with a non-zero value; the fresh
+ * board after a game over is inserted one step earlier here).  Only bulk lists cross NVLink: 48 bytes per env step.
+ *
+ * g2048_routed_buffer_bytes(world, cap): size of the zero-filled buffer every rank must allocate with
+ * g2048_peer_alloc and share with all peers (cap = the largest env count of any rank).  g2048_routed_create: rank's
+ * view; peer_buffers[j] (HOST array) = rank j's buffer as mapped in this process, `shard` = this rank's
+ * slots_per_shard * 32 bytes of table, n_total = envs of all ranks (global env ids must stay below it).
+ * g2048_routed_prime: looks the envs' current boards up (call once after reset, on every rank, before the first step;
+ * again whenever the boards were changed from outside).  g2048_routed_step: one env step of this rank's n envs; every
+ * rank must call it the same number of times; *applied (host, may be NULL) = records applied to this rank's shard.
+ * The step synchronises the stream once (the sort needs the record count).  A peer that does not reach a barrier
+ * within 5 s makes the call (or the next one) return G2048_ERR_PEER; nothing of that step is applied on this GPU. */
+typedef struct g2048_routed g2048_routed;
+G2048_API size_t g2048_routed_buffer_bytes(int world, int64_t cap);
+G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, int64_t n_total, void* const* peer_buffers,
+                                            void* shard, uint64_t slots_per_shard);
+G2048_API void g2048_routed_destroy(g2048_routed* r);
+G2048_API int g2048_routed_prime(g2048_routed* r, const uint64_t* boards, int64_t n, void* stream);
+G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux, int32_t* score, int64_t n, int flavour,
+                                float lr, float gamma, double eps, uint64_t seed, uint64_t step_idx, uint64_t env_id_base,
+                                int64_t* counters, int64_t* applied, void* stream);
 
 /* ------------------------------------------------------------------ Q-table (device pointers) */
 /* QLearningAgent.q_table (main.py:16): `table` is capacity * 32 bytes of device memory, 32-byte aligned,

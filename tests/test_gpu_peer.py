@@ -19,9 +19,9 @@ def np_boards(t):
     return t.detach().cpu().numpy().view(np.uint64)
 
 
-def single_process_result(g, n, steps, flavour="penalty"):
+def single_process_result(g, n, steps, flavour="penalty", cap=CAP):
     env = g.BatchedGame2048Env(n, flavour, seed=SEED)
-    agent = g.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 0.4, capacity=CAP, seed=SEED)
+    agent = g.BatchedQLearningAgent(1000, 4, 0.1, 0.99, 0.4, capacity=cap, seed=SEED)
     env.reset()
     for _ in range(steps):
         agent.step_sync(env, mode="deterministic")
@@ -397,3 +397,60 @@ def test_two_processes_owner_computes_with_a_4_step_window(tmp_path):
     rows = np.concatenate([d[0]["rows"], d[1]["rows"]])
     order = np.argsort(keys)
     assert np.array_equal(keys[order], keys1) and np.array_equal(rows[order], rows1)
+
+
+# ---------------------------------------------------------------- exact synchronous step, routed (every table access local)
+def _routed_worker(rank, world, port, out, flavour):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import g2048
+    from g2048 import dist as gdist
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = gdist.shard_range(N_TOTAL, rank, world)
+    env = g2048.BatchedGame2048Env(hi - lo, flavour, seed=SEED, env_id_base=lo)
+    env.reset()
+    shared = gdist.SharedQTable(g2048.lib(), torch.device("cuda", 0), CAP_ROUTED // world)
+    rq = gdist.RoutedQLearning(env, shared, N_TOTAL, 0.1, 0.99, 0.4)
+    handled = [rq.step() for _ in range(STEPS_ROUTED)]
+    torch.cuda.synchronize()
+    dist.barrier()
+    keys, rows = shared.export_local()
+    nz = np.abs(rows).sum(1) > 0
+    np.savez(os.path.join(out, f"routed{rank}.npz"), boards=np_boards(env.boards), keys=keys[nz], rows=rows[nz], lo=lo, hi=hi,
+             handled=np.array(handled), counters=env.counters.cpu().numpy(), all_keys=keys)
+    rq.close()
+    shared.close()
+    dist.destroy_process_group()
+
+
+STEPS_ROUTED = 160         # long enough for games to end: the request for the fresh board after a game over is exercised
+CAP_ROUTED = 1 << 21       # (about 450,000 states)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("flavour", ["penalty", "nopenalty"])
+def test_two_processes_routed_step_equals_the_single_table_deterministic_step(tmp_path, flavour):
+    """g2048_routed_*: keys travel to the owner of their home slot, {slot, max Q} and rows come back, records go to the
+    owner of s; no process touches the other's shard.  Boards and every non-zero row equal the single-process
+    deterministic step on one table, bit for bit; every state a shard holds is owned by it."""
+    import torch.multiprocessing as mp
+    import g2048
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_routed_worker, args=(2, port, str(tmp_path), flavour), nprocs=2, join=True)
+    boards1, keys1, rows1 = single_process_result(g2048, N_TOTAL, STEPS_ROUTED, flavour, CAP_ROUTED)
+    d = [np.load(tmp_path / f"routed{r}.npz") for r in range(2)]
+    for x in d:
+        assert np.array_equal(x["boards"], boards1[int(x["lo"]):int(x["hi"])])
+    assert np.array_equal(d[0]["handled"] + d[1]["handled"], np.array([N_TOTAL] * STEPS_ROUTED))
+    assert min(d[0]["handled"].min(), d[1]["handled"].min()) > 0.3 * N_TOTAL        # both owners had work
+    keys = np.concatenate([d[0]["keys"], d[1]["keys"]])
+    rows = np.concatenate([d[0]["rows"], d[1]["rows"]])
+    order = np.argsort(keys)
+    assert np.array_equal(keys[order], keys1) and np.array_equal(rows[order], rows1)
+    assert len(np.intersect1d(d[0]["all_keys"], d[1]["all_keys"])) == 0              # no state lives in both shards
+    episodes = int(d[0]["counters"][2] + d[1]["counters"][2])
+    assert episodes > 0
