@@ -770,27 +770,35 @@ __global__ void k_peer_barrier(PeerFlags F, int rank, int world, u64 epoch, u64 
 // remote requests (6.7 G/s per GPU) is what bounds that step.  Here nothing but coalesced lists crosses NVLink:
 //   k_routed_request  every env takes (slot, row) of its state from the answers of the last step, chooses, steps, and
 //                     appends the key of s' (and of the fresh board after a game over) to its list for the GPU that OWNS
-//                     the key's home slot                                                        [local writes]
+//                     the key's home slot; counts its record per (warp, owner)                 [local writes]
+//   k_routed_scan     the counts become places: every rank's records for one owner in ascending env order
+//   k_routed_offsets  (after the barrier) where this rank's records start in every owner's sort input = the records of
+//                     the lower ranks; the total for this GPU goes to the host (the only synchronisation of the step)
 //   k_routed_lookup   the owner pulls the lists written for it (coalesced peer reads), finds-or-inserts every key in
 //                     its OWN shard and pushes {slot, max Q} to the same place of the requester's answer buffer
-//   k_routed_records  the requester builds r + gamma max Q(s') and appends the record to its list for the owner of s
-//   (k_gather_owned + sort + k_segment_apply: the owner applies its records, as in the owner-computes step)
+//   k_routed_records  the requester builds r + gamma max Q(s') and pushes {slot * 4 + action, target} straight into the
+//                     sort input of the owner of s, at its place: the input is then in ascending GLOBAL env order
+//   (stable radix sort on the slot bits + k_segment_apply: the single-GPU deterministic apply, on the owner's share)
 //   k_routed_rows     the owner pushes the rows as they are AFTER the apply for every request: what the next step's
 //                     choose_action reads
-// with a flag barrier after each of the four.  A request handle = owner << 28 | place in the list for that owner.
-struct RoutedLocal {                 // the requester's side: everything lives in this GPU's memory
-    u64* req_out[G2048_MAX_PEERS];            // keys for owner d
-    ulonglong2* rec_out[G2048_MAX_PEERS];     // records for owner d
-    const uint2* reply1[G2048_MAX_PEERS];     // {slot, max Q bits} from owner d, same places as req_out[d]
-    const float4* reply2[G2048_MAX_PEERS];    // rows after the apply from owner d
+// with a flag barrier after request, lookup, records and rows.  A request handle = owner << 28 | place in the list.
+struct RoutedLocal {                 // the requester's side
+    u64* req_out[G2048_MAX_PEERS];            // keys for owner d                                   (local)
+    u64* push_key[G2048_MAX_PEERS];           // owner d's sort input: slot * 4 + action            (peer memory, written)
+    float* push_val[G2048_MAX_PEERS];         //                       TD target                    (peer memory, written)
+    const uint2* reply1[G2048_MAX_PEERS];     // {slot, max Q bits} from owner d, same places as req_out[d]   (local)
+    const float4* reply2[G2048_MAX_PEERS];    // rows after the apply from owner d                  (local)
     unsigned long long* req_count;            // [world]
-    unsigned long long* rec_count;            // [world]
-    u64* sk;                                  // per env: sort key of its record (all ones: the state has no slot)
+    unsigned long long* rec_count;            // [world] records for owner d (k_routed_scan)
+    const u32* off;                           // [world] my first place in owner d's sort input (k_routed_offsets)
+    u64* sk;                                  // per env: slot * 4 + action of its record (all ones: the state has no slot)
     u32* req1;                                // per env: handle of the request for s'
     u32* cur;                                 // per env: handle of the request that answers for the state it sits in
     float* reward;                            // per env
     u32* meta;                                // per env: owner of s | done << 8
-    int world, idx_bits;
+    u32* chunk;                               // [world][warps]: records of a warp's 32 envs per owner, then their first place
+    long long n_warps;                        // row length of `chunk`
+    int world;
     u32 owner_shift;                          // owner(key) = (mix64(key) >> owner_shift) & (world - 1)
 };
 struct RoutedServe {                 // the owner's side
@@ -817,7 +825,7 @@ __device__ __forceinline__ u32 warp_append(int list, unsigned long long* counts)
 template <int FLAVOUR, bool PRIME>
 __global__ void __launch_bounds__(256)
 k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ RoutedLocal R, long long n,
-                 u64 eps_thresh, u64 seed, u64 t, u64 id_base, u64 rec_base, long long* counters) {
+                 u64 eps_thresh, u64 seed, u64 t, u64 id_base, long long* counters) {
     __shared__ u64* req_out[G2048_MAX_PEERS];
     __shared__ const uint2* reply1[G2048_MAX_PEERS];
     __shared__ const float4* reply2[G2048_MAX_PEERS];
@@ -834,7 +842,7 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {   // warp-uniform
         const long long i = i0 + lane;
-        int owner1 = -1, owner2 = -1;
+        int owner1 = -1, owner2 = -1, owner_s = -1;
         u64 key1 = 0, key2 = 0;
         if (i < n) {
             if (PRIME) {
@@ -852,7 +860,8 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
                 philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
                 c.add(o);
                 key1 = e.board;                       // s' (== s after an invalid move: the owner answers for s again)
-                R.sk[i] = slot == kNoSlot ? ~0ull : (((((u64)slot << 2) | (u64)a) << R.idx_bits) | (rec_base + (u64)i));
+                R.sk[i] = slot == kNoSlot ? ~0ull : (((u64)slot << 2) | (u64)a);
+                if (slot != kNoSlot) owner_s = (int)os;
                 R.reward[i] = (float)o.reward;
                 R.meta[i] = os | (o.done ? 256u : 0u);
                 if (o.done) {
@@ -869,11 +878,21 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
         const u32 p1 = warp_append(owner1, R.req_count);
         if (owner1 >= 0) req_out[owner1][p1] = key1;
         u32 h1 = ((u32)owner1 << kHandleBits) | p1, h2 = h1;
-        if (!PRIME && __any_sync(0xFFFFFFFFu, owner2 >= 0)) {
-            const u32 p2 = warp_append(owner2, R.req_count);
-            if (owner2 >= 0) {
-                req_out[owner2][p2] = key2;
-                h2 = ((u32)owner2 << kHandleBits) | p2;
+        if (!PRIME) {
+            // how many records this warp's 32 envs will send to every owner: k_routed_scan turns the counts into places,
+            // so that k_routed_records writes every owner's input in ascending env order without an atomic
+            u32 mine = 0;
+            for (int j = 0; j < R.world; ++j) {
+                const u32 cnt = (u32)__popc(__ballot_sync(0xFFFFFFFFu, owner_s == j));
+                if (lane == j) mine = cnt;
+            }
+            if (lane < R.world) R.chunk[(long long)lane * R.n_warps + (i0 >> 5)] = mine;
+            if (__any_sync(0xFFFFFFFFu, owner2 >= 0)) {          // a game ended in this warp (rare): the fresh board
+                const u32 p2 = warp_append(owner2, R.req_count);
+                if (owner2 >= 0) {
+                    req_out[owner2][p2] = key2;
+                    h2 = ((u32)owner2 << kHandleBits) | p2;
+                }
             }
         }
         if (i < n) {
@@ -882,6 +901,55 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
         }
     }
     flush_counters(c, counters);
+}
+// chunk[j][w] = records warp w sends to owner j  ->  exclusive prefix over the warps, the total to count[j].
+// One block per owner; every thread scans a contiguous run of warps.
+__global__ void __launch_bounds__(1024) k_routed_scan(u32* chunk, long long n_warps, long long row, unsigned long long* count) {
+    __shared__ u32 warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32* col = chunk + (long long)blockIdx.x * row;
+    const long long per = (n_warps + 1023) / 1024, lo = threadIdx.x * per, hi = (lo + per < n_warps) ? lo + per : n_warps;
+    u32 mine = 0;
+    for (long long c = lo; c < hi; ++c) mine += col[c];
+    u32 x = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const u32 w = warp_tot[lane];
+        u32 z = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
+        warp_tot[lane] = z - w;
+        if (lane == 31) count[blockIdx.x] = z;
+    }
+    __syncthreads();
+    u32 run = x - mine + warp_tot[warp];
+    for (long long c = lo; c < hi; ++c) { const u32 v = col[c]; col[c] = run; run += v; }
+}
+// after the barrier: every rank's record counts (peer memory) -> where my records start in every owner's sort input
+// (= the records of the lower ranks for that owner), and how many records this GPU will receive (to the host)
+struct PeerWords { const u64* ptr[G2048_MAX_PEERS]; };
+__global__ void __launch_bounds__(256) k_routed_offsets(PeerWords counts, int world, int me, u32* off, u64* host_total) {
+    __shared__ u64 m[G2048_MAX_PEERS][G2048_MAX_PEERS];
+    const int r = threadIdx.x / G2048_MAX_PEERS, j = threadIdx.x % G2048_MAX_PEERS;
+    if (r < world && j < world) {
+        u64 v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(counts.ptr[r] + j) : "memory");
+        m[r][j] = v;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        u64 s = 0;
+        for (int q = 0; q < me; ++q) s += m[q][threadIdx.x];
+        off[threadIdx.x] = (u32)s;
+    }
+    if (threadIdx.x == 0) {
+        u64 s = 0;
+        for (int q = 0; q < world; ++q) s += m[q][me];
+        *host_total = s;
+    }
 }
 // prefix ends of the `world` request lists in shared memory; returns the total
 __device__ __forceinline__ long long routed_ends(const unsigned long long* cnt, int world, long long* end) {
@@ -943,11 +1011,15 @@ k_routed_rows(const Slot* shard, const __grid_constant__ RoutedServe V, const in
 }
 __global__ void __launch_bounds__(256)
 k_routed_records(const __grid_constant__ RoutedLocal R, long long n, float gamma) {
-    __shared__ ulonglong2* rec_out[G2048_MAX_PEERS];
+    __shared__ u64* push_key[G2048_MAX_PEERS];
+    __shared__ float* push_val[G2048_MAX_PEERS];
     __shared__ const uint2* reply1[G2048_MAX_PEERS];
+    __shared__ u32 off[G2048_MAX_PEERS];
     if (threadIdx.x < G2048_MAX_PEERS) {
-        rec_out[threadIdx.x] = R.rec_out[threadIdx.x];
+        push_key[threadIdx.x] = R.push_key[threadIdx.x];
+        push_val[threadIdx.x] = R.push_val[threadIdx.x];
         reply1[threadIdx.x] = R.reply1[threadIdx.x];
+        off[threadIdx.x] = (int)threadIdx.x < R.world ? R.off[threadIdx.x] : 0u;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -964,17 +1036,14 @@ k_routed_records(const __grid_constant__ RoutedLocal R, long long n, float gamma
             target = td_target(gamma, R.reward[i], __uint_as_float(ans.y), (meta & 256u) != 0);
             if (sk != ~0ull) owner = (int)(meta & 255u);
         }
-        const u32 p = warp_append(owner, R.rec_count);
-        if (owner >= 0) rec_out[owner][p] = make_ulonglong2(sk, (u64)__float_as_uint(target));
-    }
-}
-// `world` 8-byte values at local or peer addresses -> pinned host memory (one launch instead of `world` small copies)
-struct PeerWords { const u64* ptr[G2048_MAX_PEERS]; };
-__global__ void k_peer_words_to_host(PeerWords W, int world, u64* host_out) {
-    if ((int)threadIdx.x < world) {
-        u64 v;
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(W.ptr[threadIdx.x]) : "memory");
-        host_out[threadIdx.x] = v;
+        // place = my first place in the owner's input + the warp's first place among my records for it (k_routed_scan)
+        //         + the rank among the warp's lanes for that owner: ascending env order
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, owner);
+        if (owner >= 0) {
+            const u32 p = off[owner] + R.chunk[(long long)owner * R.n_warps + (i0 >> 5)] + (u32)__popc(peers & ((1u << lane) - 1u));
+            push_key[owner][p] = sk;
+            push_val[owner][p] = target;
+        }
     }
 }
 
@@ -994,7 +1063,9 @@ k_apply_atomic(Slot* tab, const u64* sortkey, const float* target, float lr, lon
 // reset of 8 M envs).  worklist[0] = number of queued runs (zeroed by the caller), worklist[1 + w] = index of the head.
 constexpr int kInlineRun = 8;
 __global__ void __launch_bounds__(256)
-k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, u64* worklist, int kshift) {
+k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, u64* worklist, int kshift,
+                const int* abort_flag = nullptr) {
+    if (abort_flag && *(const volatile int*)abort_flag != 0) return;   // a peer never reached the barrier: its records are not valid
     // kshift: low bits of the sort key that only order the records of a run (0 here; the global env index in the
     // owner-computes form); the all-ones key ("no slot") is checked before shifting
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1019,7 +1090,8 @@ k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, lo
 // float operations per record, the order of the records untouched, so the result is bit-identical to the serial walk.
 __global__ void __launch_bounds__(256)
 k_long_run_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, const u64* worklist,
-                 int kshift) {
+                 int kshift, const int* abort_flag = nullptr) {
+    if (abort_flag && *(const volatile int*)abort_flag != 0) return;
     const int lane = threadIdx.x & 31;
     const u64 n_warps = (u64)gridDim.x * (blockDim.x >> 5);
     const u64 count = worklist[0];
@@ -1767,7 +1839,7 @@ struct Scratch;
 size_t scratch_bytes(int64_t n);
 int carve(void* scratch, size_t bytes, int64_t n, Scratch& s);
 int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, float lr, int mode, cudaStream_t st,
-                  int kshift = 0);
+                  int kshift = 0, const int* abort_flag = nullptr);
 
 struct DeferBuffers;
 template <class TAB>
@@ -1870,7 +1942,7 @@ int carve(void* scratch, size_t bytes, int64_t n, Scratch& s) {
 }
 // apply the records in s.key_in / s.val_in
 int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int64_t n, float lr, int mode, cudaStream_t st,
-                  int kshift) {
+                  int kshift, const int* abort_flag) {
     int g = grid_for(n, 256, D->sm_count);
     if (mode == G2048_MODE_ATOMIC) {
         k_apply_atomic<<<g, 256, 0, st>>>(tab, s.key_in, s.val_in, lr, n);
@@ -1888,10 +1960,10 @@ int apply_records(DeviceState* D, Slot* tab, uint64_t capacity, Scratch& s, int6
                                        s.val_out, (int64_t)n, 0, end_bit, st));
     u64* worklist = s.key_in;   // the sort's input is dead now: reuse it for the queue of long runs (< n / 8 entries)
     CK(cudaMemsetAsync(worklist, 0, sizeof(u64), st));
-    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist, kshift);
+    k_segment_apply<<<g, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist, kshift, abort_flag);
     LAUNCH_CHECK("k_segment_apply");
     if (n > kInlineRun) {
-        k_long_run_apply<<<D->sm_count * 4, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist, kshift);
+        k_long_run_apply<<<D->sm_count * 4, 256, 0, st>>>(tab, s.key_out, s.val_out, lr, n, worklist, kshift, abort_flag);
         LAUNCH_CHECK("k_long_run_apply");
     }
     return 0;
@@ -2218,44 +2290,52 @@ G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, ui
 // ---- exact synchronous step on a sharded table, routed (see k_routed_request)
 // Layout of the buffer every rank shares with its peers (CUDA IPC), C = cap (the largest env count of any rank):
 //   [0, 128) barrier flags | [256, 384) request counts per owner | [512, 640) record counts per owner | from 1024:
-//   req_out[world][2C] u64 | rec_out[world][C] 16 B | reply1[world][2C] 8 B | reply2[world][2C] 16 B
+//   req_out[world][2C] u64 | reply1[world][2C] 8 B | reply2[world][2C] 16 B | sort input: keys[world * C] u64, targets[world * C] f32
 namespace {
 constexpr size_t kRoutedHead = 1024, kRoutedReqCount = 256, kRoutedRecCount = 512;
 struct RoutedLayout {
-    size_t req, rec, reply1, reply2, req_stride, rec_stride, r1_stride, r2_stride, total;
+    size_t req, reply1, reply2, key_in, val_in, req_stride, r1_stride, r2_stride, total;
 };
 RoutedLayout routed_layout(int world, int64_t cap) {
     RoutedLayout l{};
     const size_t c = (size_t)(cap > 0 ? cap : 1);
     l.req_stride = align256(2 * c * 8);
-    l.rec_stride = align256(c * 16);
     l.r1_stride = align256(2 * c * 8);
     l.r2_stride = align256(2 * c * 16);
     l.req = kRoutedHead;
-    l.rec = l.req + (size_t)world * l.req_stride;
-    l.reply1 = l.rec + (size_t)world * l.rec_stride;
+    l.reply1 = l.req + (size_t)world * l.req_stride;
     l.reply2 = l.reply1 + (size_t)world * l.r1_stride;
-    l.total = l.reply2 + (size_t)world * l.r2_stride;
+    l.key_in = l.reply2 + (size_t)world * l.r2_stride;
+    l.val_in = l.key_in + align256((size_t)world * c * 8);
+    l.total = l.val_in + align256((size_t)world * c * 4);
     return l;
 }
 }  // namespace
 struct g2048_routed {
-    int device = 0, rank = 0, world = 1, idx_bits = 1;
+    int device = 0, rank = 0, world = 1;
     int64_t cap = 0, n_total = 0;
     Slot* shard = nullptr;
     uint64_t slots = 0;
     RoutedLocal L{};
     RoutedServe V{};
     PeerFlags F{};
-    PeerWords rec_counts{};          // rank r's count of records for this GPU
-    RecordLists recs{};              // rank r's records for this GPU (ptr only; ends are filled per step)
+    PeerWords rec_counts{};          // rank r's record counts (all owners)
+    u64* key_in = nullptr;           // this GPU's sort input, in the shared buffer: the peers push their records into it
+    float* val_in = nullptr;
+    u32* off = nullptr;              // local [world]
     char* local = nullptr;           // per-env state of the requester side + saved slots of the owner side
-    void* sort_buf = nullptr;
+    void* sort_buf = nullptr;        // sort output + CUB's temporary storage
     size_t sort_bytes = 0;
-    u64* host_counts = nullptr;      // pinned: [world] record counts, [world] = the barrier's time-out flag (int)
+    u64* host_total = nullptr;       // pinned: [0] records for this GPU in the current step, [1] = the barrier's time-out flag (int)
     int* timed_out = nullptr;
     u64 epoch = 0;
     bool primed = false;
+    // G2048_ROUTED_PROFILE=1: device time of every phase of the step (CUDA events), printed by g2048_routed_destroy
+    bool profile = false;
+    static constexpr int kPhases = 10;
+    cudaEvent_t ev[kPhases + 1] = {};
+    double phase_ms[kPhases] = {};
+    long long profiled_steps = 0;
 };
 namespace {
 int routed_barrier(g2048_routed* r, DeviceState* D, cudaStream_t st) {
@@ -2279,7 +2359,8 @@ G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, in
     DeviceState* D = nullptr;
     if (current_device_state(&D)) return nullptr;
     if (world < 1 || world > G2048_MAX_PEERS || (world & (world - 1)) || rank < 0 || rank >= world || cap < 1 ||
-        2 * cap >= (1ll << kHandleBits) || n_total < 1 || !peer_buffers || !shard || !pow2(slots_per_shard)) {
+        2 * cap >= (1ll << kHandleBits) || (int64_t)world * cap >= (1ll << 32) || n_total < 1 || !peer_buffers || !shard ||
+        !pow2(slots_per_shard)) {
         fail(G2048_ERR_ARG, "g2048_routed_create: bad arguments");
         return nullptr;
     }
@@ -2289,52 +2370,59 @@ G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, in
     cudaGetDevice(&r->device);
     r->rank = rank; r->world = world; r->cap = cap; r->n_total = n_total;
     r->shard = (Slot*)shard; r->slots = slots_per_shard;
-    r->idx_bits = 1;
-    while (((uint64_t)(n_total - 1) >> r->idx_bits) != 0) ++r->idx_bits;
     int slot_bits = 0;
     while ((1ull << slot_bits) < slots_per_shard) ++slot_bits;
-    if (slot_bits + 2 + r->idx_bits > 63) { fail(G2048_ERR_ARG, "g2048_routed_create: slot and env index do not fit one sort key"); delete r; return nullptr; }
     const RoutedLayout lay = routed_layout(world, cap);
     char* mine = (char*)peer_buffers[rank];
-    // requester side
     const size_t c = (size_t)cap;
-    const size_t local_bytes = align256(c * 8) + 4 * align256(c * 4) + (size_t)world * align256(2 * c * 4) + 256;
+    const size_t n_warps = (c + 31) / 32;
+    const size_t local_bytes = align256(c * 8) + 4 * align256(c * 4) + align256(n_warps * world * 4) +
+                               (size_t)world * align256(2 * c * 4) + 512;
     if (cudaMalloc(&r->local, local_bytes) != cudaSuccess || cudaMemset(r->local, 0, local_bytes) != cudaSuccess ||
-        cudaHostAlloc(&r->host_counts, (G2048_MAX_PEERS + 1) * sizeof(u64), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        cudaHostAlloc(&r->host_total, 2 * sizeof(u64), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         fail((int)cudaGetLastError(), "g2048_routed_create: allocation");
         if (r->local) cudaFree(r->local);
         delete r;
         return nullptr;
     }
-    memset(r->host_counts, 0, (G2048_MAX_PEERS + 1) * sizeof(u64));
-    r->timed_out = (int*)(r->host_counts + G2048_MAX_PEERS);
+    r->host_total[0] = r->host_total[1] = 0;
+    r->timed_out = (int*)(r->host_total + 1);
     char* p = r->local;
     r->L.sk = (u64*)p; p += align256(c * 8);
     r->L.req1 = (u32*)p; p += align256(c * 4);
     r->L.cur = (u32*)p; p += align256(c * 4);
     r->L.reward = (float*)p; p += align256(c * 4);
     r->L.meta = (u32*)p; p += align256(c * 4);
+    r->L.chunk = (u32*)p; p += align256(n_warps * world * 4);
+    r->L.n_warps = (long long)n_warps;
     for (int j = 0; j < world; ++j) { r->V.saved_slot[j] = (u32*)p; p += align256(2 * c * 4); }
-    r->V.count_cache = (unsigned long long*)p;
-    r->L.world = world; r->L.idx_bits = r->idx_bits; r->L.owner_shift = (u32)slot_bits;
+    r->V.count_cache = (unsigned long long*)p; p += 256;
+    r->off = (u32*)p;
+    r->L.off = r->off;
+    r->L.world = world; r->L.owner_shift = (u32)slot_bits;
     r->L.req_count = (unsigned long long*)(mine + kRoutedReqCount);
     r->L.rec_count = (unsigned long long*)(mine + kRoutedRecCount);
+    r->key_in = (u64*)(mine + lay.key_in);
+    r->val_in = (float*)(mine + lay.val_in);
     r->V.world = world;
     for (int j = 0; j < world; ++j) {
         char* peer = (char*)peer_buffers[j];
         r->L.req_out[j] = (u64*)(mine + lay.req + (size_t)j * lay.req_stride);
-        r->L.rec_out[j] = (ulonglong2*)(mine + lay.rec + (size_t)j * lay.rec_stride);
         r->L.reply1[j] = (const uint2*)(mine + lay.reply1 + (size_t)j * lay.r1_stride);
         r->L.reply2[j] = (const float4*)(mine + lay.reply2 + (size_t)j * lay.r2_stride);
+        r->L.push_key[j] = (u64*)(peer + lay.key_in);
+        r->L.push_val[j] = (float*)(peer + lay.val_in);
         r->V.req[j] = (const u64*)(peer + lay.req + (size_t)rank * lay.req_stride);
         r->V.req_count[j] = (const unsigned long long*)(peer + kRoutedReqCount) + rank;
         r->V.reply1[j] = (uint2*)(peer + lay.reply1 + (size_t)rank * lay.r1_stride);
         r->V.reply2[j] = (float4*)(peer + lay.reply2 + (size_t)rank * lay.r2_stride);
         r->F.ptr[j] = (u64*)peer;
-        r->rec_counts.ptr[j] = (const u64*)(peer + kRoutedRecCount) + rank;
-        r->recs.ptr[j] = (const ulonglong2*)(peer + lay.rec + (size_t)rank * lay.rec_stride);
+        r->rec_counts.ptr[j] = (const u64*)(peer + kRoutedRecCount);
     }
-    r->recs.n_lists = world;
+    const char* prof = getenv("G2048_ROUTED_PROFILE");
+    r->profile = prof && prof[0] == '1';
+    if (r->profile)
+        for (auto& e : r->ev) cudaEventCreate(&e);
     return r;
 }
 G2048_API void g2048_routed_destroy(g2048_routed* r) {
@@ -2342,9 +2430,17 @@ G2048_API void g2048_routed_destroy(g2048_routed* r) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(r->device);
+    if (r->profile && r->profiled_steps) {
+        static const char* names[g2048_routed::kPhases] = {"request + scan", "barrier 1 + offsets", "host (sync, launch)", "lookup", "barrier 2",
+                                                           "records", "barrier 3", "sort + apply", "rows", "barrier 4"};
+        fprintf(stderr, "g2048_routed rank %d: %lld steps, ms per step:", r->rank, r->profiled_steps);
+        for (int i = 0; i < g2048_routed::kPhases; ++i) fprintf(stderr, " %s %.3f |", names[i], r->phase_ms[i] / (double)r->profiled_steps);
+        fprintf(stderr, "\n");
+        for (auto& e : r->ev) cudaEventDestroy(e);
+    }
     if (r->local) cudaFree(r->local);
     if (r->sort_buf) cudaFree(r->sort_buf);
-    if (r->host_counts) cudaFreeHost(r->host_counts);
+    if (r->host_total) cudaFreeHost(r->host_total);
     cudaSetDevice(prev);
     delete r;
 }
@@ -2358,7 +2454,7 @@ G2048_API int g2048_routed_prime(g2048_routed* r, const uint64_t* boards, int64_
     if ((rc = routed_barrier(r, D, st))) return rc;            // nobody still reads the counts of an earlier use
     if (n) {
         k_routed_request<0, true><<<grid_for(n, 256, D->sm_count), 256, 0, st>>>(D->tables, (u64*)boards, nullptr, nullptr, r->L, n, 0, 0,
-                                                                                  0, 0, 0, nullptr);
+                                                                                  0, 0, nullptr);
         LAUNCH_CHECK("k_routed_request");
     }
     if ((rc = routed_barrier(r, D, st))) return rc;
@@ -2381,59 +2477,85 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
     if (!r || n < 0 || n > r->cap || (n && !boards) || (flavour != 0 && flavour != 1))
         return fail(G2048_ERR_ARG, "g2048_routed_step: bad arguments");
     if (!r->primed) return fail(G2048_ERR_ARG, "g2048_routed_step: call g2048_routed_prime first");
-    if (((env_id_base + (uint64_t)(n ? n - 1 : 0)) >> r->idx_bits) != 0)
+    if (env_id_base + (uint64_t)n > (uint64_t)r->n_total)
         return fail(G2048_ERR_ARG, "g2048_routed_step: env_id_base + n exceeds the total the exchange was created for");
     cudaStream_t st = S(stream);
     int rc;
     if ((rc = routed_check(r))) return rc;
     const int ge = grid_for(n, 256, D->sm_count), gs = grid_for(2 * r->cap, 256, D->sm_count);
-    CK(cudaMemsetAsync(r->L.rec_count, 0, 128, st));             // (the owners read it before the last barrier of the step before)
+#define MARK(i) do { if (r->profile) cudaEventRecord(r->ev[i], st); } while (0)
+    MARK(0);
     if (n) {
 #define REQ(F) k_routed_request<F, false><<<ge, 256, 0, st>>>(D->tables, (u64*)boards, (u64*)aux, score, r->L, n, eps_threshold(eps), \
-                                                               seed, step_idx, env_id_base, env_id_base, (long long*)counters)
+                                                               seed, step_idx, env_id_base, (long long*)counters)
         if (flavour == 0) REQ(0); else REQ(1);
 #undef REQ
         LAUNCH_CHECK("k_routed_request");
     }
-    if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's requests are written
-    k_routed_lookup<<<gs, 256, 0, st>>>(r->shard, r->slots - 1, r->V, (long long*)counters, D->abort_flag);
-    LAUNCH_CHECK("k_routed_lookup");
-    if ((rc = routed_barrier(r, D, st))) return rc;            // the answers are there; every owner has read my requests
-    CK(cudaMemsetAsync(r->L.req_count, 0, 128, st));
-    if (n) {
-        k_routed_records<<<ge, 256, 0, st>>>(r->L, n, gamma);
-        LAUNCH_CHECK("k_routed_records");
-    }
-    if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's records are written
-    k_peer_words_to_host<<<1, 32, 0, st>>>(r->rec_counts, r->world, r->host_counts);
-    LAUNCH_CHECK("k_peer_words_to_host");
+    // (the peers read the record counts of the step before ahead of its last barrier)
+    k_routed_scan<<<r->world, 1024, 0, st>>>(r->L.chunk, (n + 31) / 32, r->L.n_warps, r->L.rec_count);
+    LAUNCH_CHECK("k_routed_scan");
+    MARK(1);
+    if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's requests and record counts are written
+    k_routed_offsets<<<1, 256, 0, st>>>(r->rec_counts, r->world, r->rank, r->off, r->host_total);
+    LAUNCH_CHECK("k_routed_offsets");
+    MARK(2);
+    // the one synchronisation of the step: the sort needs the record count on the host.  It comes this early so that
+    // everything below is enqueued while the lookup kernel runs -- the device never waits for a launch.
     CK(cudaStreamSynchronize(st));
     if ((rc = routed_check(r))) return rc;
-    long long total = 0;
-    for (int j = 0; j < r->world; ++j) {
-        total += (long long)r->host_counts[j];
-        r->recs.end[j] = total;
-    }
+    const long long total = (long long)r->host_total[0];
+    if (total > (long long)r->world * r->cap) return fail(G2048_ERR_ARG, "g2048_routed_step: more records than envs");
+    Scratch sc{};
     if (total > 0) {
-        const size_t need = scratch_bytes(total);
+        const size_t m = (size_t)total, temp = cub_temp_bytes(total);
+        const size_t need = align256(m * 8) + align256(m * 4) + align256(temp) + 256;
         if (r->sort_bytes < need) {
             if (r->sort_buf) CK(cudaFree(r->sort_buf));
             r->sort_buf = nullptr;
             r->sort_bytes = 0;
-            const size_t want = scratch_bytes(total + total / 4 + 1024);
+            const size_t want = need + need / 4;
             CK(cudaMalloc(&r->sort_buf, want));
             r->sort_bytes = want;
         }
-        Scratch sc{};
-        if ((rc = carve(r->sort_buf, r->sort_bytes, total, sc))) return rc;
-        k_gather_owned<<<grid_for(total, 256, D->sm_count), 256, 0, st>>>(r->recs, total, sc.key_in, sc.val_in, D->abort_flag);
-        LAUNCH_CHECK("k_gather_owned");
-        if ((rc = apply_records(D, r->shard, r->slots, sc, total, lr, G2048_MODE_DETERMINISTIC, st, r->idx_bits))) return rc;
+        char* p = (char*)r->sort_buf;
+        sc.key_in = r->key_in; sc.val_in = r->val_in;
+        sc.key_out = (u64*)p; p += align256(m * 8);
+        sc.val_out = (float*)p; p += align256(m * 4);
+        sc.cub_temp = p; sc.cub_bytes = temp;
     }
+    MARK(3);
+    k_routed_lookup<<<gs, 256, 0, st>>>(r->shard, r->slots - 1, r->V, (long long*)counters, D->abort_flag);
+    LAUNCH_CHECK("k_routed_lookup");
+    MARK(4);
+    if ((rc = routed_barrier(r, D, st))) return rc;            // the answers are there; every owner has read my requests
+    CK(cudaMemsetAsync(r->L.req_count, 0, 128, st));
+    MARK(5);
+    if (n) {
+        k_routed_records<<<ge, 256, 0, st>>>(r->L, n, gamma);
+        LAUNCH_CHECK("k_routed_records");
+    }
+    MARK(6);
+    if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's records are in their owner's sort input
+    MARK(7);
+    if (total > 0 && (rc = apply_records(D, r->shard, r->slots, sc, total, lr, G2048_MODE_DETERMINISTIC, st, 0, D->abort_flag))) return rc;
+    MARK(8);
     k_routed_rows<<<gs, 256, 0, st>>>(r->shard, r->V, D->abort_flag);
     LAUNCH_CHECK("k_routed_rows");
+    MARK(9);
     if ((rc = routed_barrier(r, D, st))) return rc;            // the rows for the next step are there
+    MARK(10);
+#undef MARK
     if (applied) *applied = total;
+    if (r->profile && total > 0) {
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < g2048_routed::kPhases; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r->ev[i], r->ev[i + 1]);
+            r->phase_ms[i] += ms;
+        }
+        r->profiled_steps += 1;
+    }
     return 0;
 }
 

@@ -306,7 +306,8 @@ G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, ui
  * g2048_routed_buffer_bytes(world, cap): size of the zero-filled buffer every rank must allocate with
  * g2048_peer_alloc and share with all peers (cap = the largest env count of any rank).  g2048_routed_create: rank's
  * view; peer_buffers[j] (HOST array) = rank j's buffer as mapped in this process, `shard` = this rank's
- * slots_per_shard * 32 bytes of table, n_total = envs of all ranks (global env ids must stay below it).
+ * slots_per_shard * 32 bytes of table, n_total = envs of all ranks (global env ids must stay below it; rank j's env
+ * ids must all be smaller than rank j + 1's -- the owners apply the lists in rank order, which is then env order).
  * g2048_routed_prime: looks the envs' current boards up (call once after reset, on every rank, before the first step;
  * again whenever the boards were changed from outside).  g2048_routed_step: one env step of this rank's n envs; every
  * rank must call it the same number of times; *applied (host, may be NULL) = records applied to this rank's shard.
