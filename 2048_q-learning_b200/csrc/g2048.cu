@@ -797,7 +797,9 @@ struct RoutedLocal {                 // the requester's side
     float* reward;                            // per env
     u32* meta;                                // per env: owner of s | done << 8
     u32* chunk;                               // [world][warps]: records of a warp's 32 envs per owner, then their first place
+    u32* tile;                                // [world][tiles]: the same summed over tiles of 1024 warps (zeroed per step)
     long long n_warps;                        // row length of `chunk`
+    int tiles;                                // row length of `tile`
     int world;
     u32 owner_shift;                          // owner(key) = (mix64(key) >> owner_shift) & (world - 1)
 };
@@ -886,7 +888,10 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
                 const u32 cnt = (u32)__popc(__ballot_sync(0xFFFFFFFFu, owner_s == j));
                 if (lane == j) mine = cnt;
             }
-            if (lane < R.world) R.chunk[(long long)lane * R.n_warps + (i0 >> 5)] = mine;
+            if (lane < R.world) {
+                R.chunk[(long long)lane * R.n_warps + (i0 >> 5)] = mine;
+                if (mine) atomicAdd(&R.tile[lane * R.tiles + (int)(i0 >> 15)], mine);
+            }
             if (__any_sync(0xFFFFFFFFu, owner2 >= 0)) {          // a game ended in this warp (rare): the fresh board
                 const u32 p2 = warp_append(owner2, R.req_count);
                 if (owner2 >= 0) {
@@ -903,17 +908,36 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
     flush_counters(c, counters);
 }
 // chunk[j][w] = records warp w sends to owner j  ->  exclusive prefix over the warps, the total to count[j].
-// One block per owner; every thread scans a contiguous run of warps.
-__global__ void __launch_bounds__(1024) k_routed_scan(u32* chunk, long long n_warps, long long row, unsigned long long* count) {
+// Block (t, j) scans tile t (1024 warps) of owner j's row; the tile's first place = the sum of the tiles before it, which
+// k_routed_request accumulated in tile[j][t] (one atomicAdd per warp and owner, spread over world * tiles addresses).
+__global__ void __launch_bounds__(1024) k_routed_scan(u32* chunk, const u32* tile, long long n_warps, long long row, int tiles,
+                                                      unsigned long long* count) {
     __shared__ u32 warp_tot[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32* col = chunk + (long long)blockIdx.x * row;
-    const long long per = (n_warps + 1023) / 1024, lo = threadIdx.x * per, hi = (lo + per < n_warps) ? lo + per : n_warps;
-    u32 mine = 0;
-    for (long long c = lo; c < hi; ++c) mine += col[c];
+    __shared__ u32 base_sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = blockIdx.x, j = blockIdx.y;
+    const u32* ts = tile + (long long)j * tiles;
+    // sum of the tiles before this one (tiles <= 1024 * k: every thread takes a strided share)
+    u32 before = 0;
+    for (int q = threadIdx.x; q < t; q += 1024) before += ts[q];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
+    if (lane == 0) warp_tot[warp] = before;
+    __syncthreads();
+    if (warp == 0) {
+        u32 z = warp_tot[lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) z += __shfl_xor_sync(0xFFFFFFFFu, z, d);
+        if (lane == 0) base_sh = z;
+    }
+    __syncthreads();
+    const u32 base = base_sh;
+    const long long c = (long long)t * 1024 + threadIdx.x;
+    u32* col = chunk + (long long)j * row;
+    const u32 mine = c < n_warps ? col[c] : 0u;
     u32 x = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    __syncthreads();
     if (lane == 31) warp_tot[warp] = x;
     __syncthreads();
     if (warp == 0) {
@@ -922,11 +946,10 @@ __global__ void __launch_bounds__(1024) k_routed_scan(u32* chunk, long long n_wa
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
         warp_tot[lane] = z - w;
-        if (lane == 31) count[blockIdx.x] = z;
+        if (lane == 31 && t == tiles - 1) count[j] = (unsigned long long)(base + z);
     }
     __syncthreads();
-    u32 run = x - mine + warp_tot[warp];
-    for (long long c = lo; c < hi; ++c) { const u32 v = col[c]; col[c] = run; run += v; }
+    if (c < n_warps) col[c] = base + x - mine + warp_tot[warp];
 }
 // after the barrier: every rank's record counts (peer memory) -> where my records start in every owner's sort input
 // (= the records of the lower ranks for that owner), and how many records this GPU will receive (to the host)
@@ -2376,7 +2399,8 @@ G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, in
     char* mine = (char*)peer_buffers[rank];
     const size_t c = (size_t)cap;
     const size_t n_warps = (c + 31) / 32;
-    const size_t local_bytes = align256(c * 8) + 4 * align256(c * 4) + align256(n_warps * world * 4) +
+    const size_t tiles = (n_warps + 1023) / 1024;
+    const size_t local_bytes = align256(c * 8) + 4 * align256(c * 4) + align256(n_warps * world * 4) + align256(tiles * world * 4) +
                                (size_t)world * align256(2 * c * 4) + 512;
     if (cudaMalloc(&r->local, local_bytes) != cudaSuccess || cudaMemset(r->local, 0, local_bytes) != cudaSuccess ||
         cudaHostAlloc(&r->host_total, 2 * sizeof(u64), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
@@ -2395,6 +2419,8 @@ G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, in
     r->L.meta = (u32*)p; p += align256(c * 4);
     r->L.chunk = (u32*)p; p += align256(n_warps * world * 4);
     r->L.n_warps = (long long)n_warps;
+    r->L.tile = (u32*)p; p += align256(tiles * world * 4);
+    r->L.tiles = (int)tiles;
     for (int j = 0; j < world; ++j) { r->V.saved_slot[j] = (u32*)p; p += align256(2 * c * 4); }
     r->V.count_cache = (unsigned long long*)p; p += 256;
     r->off = (u32*)p;
@@ -2485,6 +2511,7 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
     const int ge = grid_for(n, 256, D->sm_count), gs = grid_for(2 * r->cap, 256, D->sm_count);
 #define MARK(i) do { if (r->profile) cudaEventRecord(r->ev[i], st); } while (0)
     MARK(0);
+    CK(cudaMemsetAsync(r->L.tile, 0, (size_t)r->L.tiles * r->world * sizeof(u32), st));
     if (n) {
 #define REQ(F) k_routed_request<F, false><<<ge, 256, 0, st>>>(D->tables, (u64*)boards, (u64*)aux, score, r->L, n, eps_threshold(eps), \
                                                                seed, step_idx, env_id_base, (long long*)counters)
@@ -2493,7 +2520,8 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
         LAUNCH_CHECK("k_routed_request");
     }
     // (the peers read the record counts of the step before ahead of its last barrier)
-    k_routed_scan<<<r->world, 1024, 0, st>>>(r->L.chunk, (n + 31) / 32, r->L.n_warps, r->L.rec_count);
+    k_routed_scan<<<dim3((unsigned)r->L.tiles, (unsigned)r->world), 1024, 0, st>>>(r->L.chunk, r->L.tile, (n + 31) / 32, r->L.n_warps,
+                                                                                    r->L.tiles, r->L.rec_count);
     LAUNCH_CHECK("k_routed_scan");
     MARK(1);
     if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's requests and record counts are written

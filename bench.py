@@ -682,7 +682,8 @@ def shared_learning_measurement(torch, dist, g2048, dev, rank, world, n_total, m
         return d
 
     refs = {}                 # both every-step modes are compared with the same single-GPU run
-    for window, warm, steps, routed in ((1, 4, 12, True), (1, 4, 12, False), (16, 16, 32, False)):
+    # 160 warm-up env steps like the main arm and the asynchronous mode below: the games have left the 480 start boards
+    for window, warm, steps, routed in ((1, 160, 12, True), (1, 160, 12, False), (16, 160, 32, False)):
         dt, digest, cnt = run_owner(window, warm, steps, routed)
         if (window, warm + steps) not in refs:
             refs[(window, warm + steps)] = one_gpu_reference(window, warm + steps)
