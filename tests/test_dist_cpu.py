@@ -139,3 +139,98 @@ def test_dqn_gradient_allreduce_keeps_two_replicas_identical(tmp_path):
     assert not torch.equal(a["local"][0], b["local"][0])          # the ranks really saw different data
     for p, q in zip(a["params"], b["params"]):
         assert torch.equal(p, q)
+
+
+# ---------------------------------------------------------------- the routed exact step (dist.RoutedQLearning) as a protocol
+def _mix64(x):
+    x = x.astype(np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+def _owner(keys, world, slot_bits=16):
+    """owner(key) of g2048_routed_*: the top bits of the global home slot (csrc/g2048.cu, RoutedLocal.owner_shift)."""
+    return ((_mix64(keys) >> np.uint64(slot_bits)) & np.uint64(world - 1)).astype(np.int64)
+
+
+def _exchange(per_dest):
+    """per_dest[d] = what this rank sends to rank d; returns [what rank r sent to this rank for all r]."""
+    box = [None] * dist.get_world_size()
+    dist.all_gather_object(box, per_dest)
+    return [box[r][dist.get_rank()] for r in range(dist.get_world_size())]
+
+
+def _routed_worker(rank, world, port, out, flavour):
+    """The message flow of k_routed_request / _lookup / _records / apply / _rows with the oracle's pieces on gloo: a rank
+    only ever reads and writes the states it owns; keys travel to the owner, rows and max Q come back, records go to the
+    owner of s and are applied there in ascending global env order."""
+    sys.path.insert(0, ROOT)
+    import oracle
+    from g2048 import dist as gdist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = gdist.shard_range(N_TOTAL, rank, world)
+    n, lr, gamma, eps = hi - lo, np.float32(0.1), np.float32(0.99), 0.4
+    boards = np.zeros(n, np.uint64)
+    oracle.env_reset(boards, None, None, None, seed=SEED, episode_idx=0, env_id_base=lo)
+    aux, score = np.full(n, oracle.AUX_INIT, np.uint64), np.zeros(n, np.int32)
+    shard = oracle.QTable(1 << 16, f32=True)
+    thresh = oracle.eps_threshold(eps)
+
+    def ask(keys):                       # keys -> rows, each answered by the owner of the key from ITS shard
+        own = _owner(keys, world)
+        got = _exchange([keys[own == d] for d in range(world)])
+        answers = _exchange([np.array([shard.get(k)[0] for k in q], np.float64).reshape(-1, 4).astype(np.float32) for q in got])
+        rows = np.zeros((len(keys), 4), np.float32)
+        for d in range(world):
+            rows[own == d] = answers[d]
+        return rows
+
+    for t in range(STEPS_ROUTED):
+        rows = ask(boards)                                             # the rows as they are after the last apply
+        draws = np.array([oracle.philox(SEED, lo + i, t, 0) for i in range(n)], np.uint32)
+        actions = np.where(draws[:, 2] < thresh, draws[:, 3] >> 30, rows.argmax(1)).astype(np.uint8)
+        s = boards.copy()
+        reward, flags, _, _ = oracle.env_step(boards, aux, score, actions, None, flavour, SEED, t, lo)
+        done = ((flags >> 2) & 1).astype(bool)
+        assert not done.any()                                          # (no game ends this early: no reset in the emulation)
+        best = ask(boards).max(1)                                      # max Q(s') BEFORE this step's apply
+        target = reward.astype(np.float32) + np.where(done, np.float32(0), gamma * best).astype(np.float32)
+        own = _owner(s, world)
+        got = _exchange([(s[own == d], actions[own == d], target[own == d]) for d in range(world)])
+        keys = np.concatenate([g[0] for g in got])                     # rank order = ascending global env order
+        assert np.all(_owner(keys, world) == rank)
+        shard.apply_targets_f32(keys, np.concatenate([g[1] for g in got]), np.concatenate([g[2] for g in got]), float(lr))
+    keys, rows = shard.export()
+    nz = np.abs(rows).sum(1) > 0
+    np.savez(os.path.join(out, f"routed{rank}.npz"), boards=boards, keys=keys[nz], rows=rows[nz], lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+STEPS_ROUTED = 10
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("flavour", [0, 1])
+def test_routed_protocol_on_two_ranks_equals_the_single_table_step(tmp_path, flavour):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_routed_worker, args=(2, port, str(tmp_path), flavour), nprocs=2, join=True)
+    sys.path.insert(0, ROOT)
+    import oracle
+    single = OracleEngine(0, N_TOTAL)
+    for t in range(STEPS_ROUTED):
+        oracle.qlearn_step_sync(single.boards, single.aux, single.score, single.tab, 0.1, 0.99, 0.4, flavour, SEED, t, 0)
+    keys, rows = single.tab.export()
+    nz = np.abs(rows).sum(1) > 0
+    d = [np.load(tmp_path / f"routed{r}.npz") for r in range(2)]
+    for x in d:
+        assert np.array_equal(x["boards"], single.boards[int(x["lo"]):int(x["hi"])])
+    assert len(np.intersect1d(d[0]["keys"], d[1]["keys"])) == 0 and min(len(d[0]["keys"]), len(d[1]["keys"])) > 100
+    k = np.concatenate([d[0]["keys"], d[1]["keys"]])
+    r = np.concatenate([d[0]["rows"], d[1]["rows"]])
+    order = np.argsort(k)
+    assert np.array_equal(k[order], keys[nz]) and np.array_equal(r[order], rows[nz])

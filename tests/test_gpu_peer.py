@@ -400,7 +400,7 @@ def test_two_processes_owner_computes_with_a_4_step_window(tmp_path):
 
 
 # ---------------------------------------------------------------- exact synchronous step, routed (every table access local)
-def _routed_worker(rank, world, port, out, flavour):
+def _routed_worker(rank, world, port, out, flavour, n_total=N_TOTAL, steps=None):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -408,12 +408,12 @@ def _routed_worker(rank, world, port, out, flavour):
     from g2048 import dist as gdist
     torch.cuda.set_device(0)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    lo, hi = gdist.shard_range(N_TOTAL, rank, world)
+    lo, hi = gdist.shard_range(n_total, rank, world)
     env = g2048.BatchedGame2048Env(hi - lo, flavour, seed=SEED, env_id_base=lo)
     env.reset()
     shared = gdist.SharedQTable(g2048.lib(), torch.device("cuda", 0), CAP_ROUTED // world)
-    rq = gdist.RoutedQLearning(env, shared, N_TOTAL, 0.1, 0.99, 0.4)
-    handled = [rq.step() for _ in range(STEPS_ROUTED)]
+    rq = gdist.RoutedQLearning(env, shared, n_total, 0.1, 0.99, 0.4)
+    handled = [rq.step() for _ in range(steps or STEPS_ROUTED)]
     torch.cuda.synchronize()
     dist.barrier()
     keys, rows = shared.export_local()
@@ -454,3 +454,24 @@ def test_two_processes_routed_step_equals_the_single_table_deterministic_step(tm
     assert len(np.intersect1d(d[0]["all_keys"], d[1]["all_keys"])) == 0              # no state lives in both shards
     episodes = int(d[0]["counters"][2] + d[1]["counters"][2])
     assert episodes > 0
+
+
+@pytest.mark.timeout(600)
+def test_routed_step_with_many_envs_per_rank(tmp_path):
+    """40,000 envs per rank: the places of the records come from more than one tile of k_routed_scan."""
+    import torch.multiprocessing as mp
+    import g2048
+    n_total, steps = 80001, 5
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_routed_worker, args=(2, port, str(tmp_path), "penalty", n_total, steps), nprocs=2, join=True)
+    boards1, keys1, rows1 = single_process_result(g2048, n_total, steps, "penalty", CAP_ROUTED)
+    d = [np.load(tmp_path / f"routed{r}.npz") for r in range(2)]
+    for x in d:
+        assert np.array_equal(x["boards"], boards1[int(x["lo"]):int(x["hi"])])
+    assert np.array_equal(d[0]["handled"] + d[1]["handled"], np.array([n_total] * steps))
+    keys = np.concatenate([d[0]["keys"], d[1]["keys"]])
+    rows = np.concatenate([d[0]["rows"], d[1]["rows"]])
+    order = np.argsort(keys)
+    assert np.array_equal(keys[order], keys1) and np.array_equal(rows[order], rows1)
