@@ -784,22 +784,20 @@ __global__ void k_peer_barrier(PeerFlags F, int rank, int world, u64 epoch, u64 
 // with a flag barrier after request, lookup, records and rows.  A request handle = owner << 28 | place in the list.
 struct RoutedLocal {                 // the requester's side
     u64* req_out[G2048_MAX_PEERS];            // keys for owner d                                   (local)
-    u64* push_key[G2048_MAX_PEERS];           // owner d's sort input: slot * 4 + action            (peer memory, written)
-    float* push_val[G2048_MAX_PEERS];         //                       TD target                    (peer memory, written)
+    u64* push_rec[G2048_MAX_PEERS];           // owner d's sort input: (slot * 4 + action) << 32 | TD target bits  (peer memory, written)
     const uint2* reply1[G2048_MAX_PEERS];     // {slot, max Q bits} from owner d, same places as req_out[d]   (local)
     const float4* reply2[G2048_MAX_PEERS];    // rows after the apply from owner d                  (local)
     unsigned long long* req_count;            // [world]
     unsigned long long* rec_count;            // [world] records for owner d (k_routed_scan)
     const u32* off;                           // [world] my first place in owner d's sort input (k_routed_offsets)
-    u64* sk;                                  // per env: slot * 4 + action of its record (all ones: the state has no slot)
+    u32* sk;                                  // per env: slot * 4 + action of its record
     u32* req1;                                // per env: handle of the request for s'
     u32* cur;                                 // per env: handle of the request that answers for the state it sits in
     float* reward;                            // per env
-    u32* meta;                                // per env: owner of s | done << 8
-    u32* chunk;                               // [world][warps]: records of a warp's 32 envs per owner, then their first place
-    u32* tile;                                // [world][tiles]: the same summed over tiles of 1024 warps (zeroed per step)
-    long long n_warps;                        // row length of `chunk`
-    int tiles;                                // row length of `tile`
+    u32* meta;                                // per env: owner of s (255: the state has no slot, no record) | done << 8
+    u32* chunk;                               // [world][warps]: records of a warp's 32 envs per owner (k_routed_request)
+    u32* place;                               // [world][warps]: their first place among this rank's records for that owner (k_routed_scan)
+    long long n_warps;                        // row length of `chunk` and `place`
     int world;
     u32 owner_shift;                          // owner(key) = (mix64(key) >> owner_shift) & (world - 1)
 };
@@ -813,6 +811,7 @@ struct RoutedServe {                 // the owner's side
     int world;
 };
 constexpr u32 kHandleBits = 28;
+constexpr int kInlineRun = 8;      // sorted runs of more records than this are applied by a warp (k_long_run_apply)
 // the lanes of a warp that append to the same list take consecutive places with one atomicAdd (all 32 lanes call this;
 // list < 0: nothing to append); returns the place
 __device__ __forceinline__ u32 warp_append(int list, unsigned long long* counts) {
@@ -862,10 +861,10 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
                 philox_step<FLAVOUR>(e, a, x, seed, id, t, L, T, o);
                 c.add(o);
                 key1 = e.board;                       // s' (== s after an invalid move: the owner answers for s again)
-                R.sk[i] = slot == kNoSlot ? ~0ull : (((u64)slot << 2) | (u64)a);
+                R.sk[i] = (slot << 2) | (u32)a;
                 if (slot != kNoSlot) owner_s = (int)os;
                 R.reward[i] = (float)o.reward;
-                R.meta[i] = os | (o.done ? 256u : 0u);
+                R.meta[i] = (slot != kNoSlot ? os : 255u) | (o.done ? 256u : 0u);
                 if (o.done) {
                     philox_autoreset(e, seed, id, t);
                     key2 = e.board;
@@ -888,10 +887,7 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
                 const u32 cnt = (u32)__popc(__ballot_sync(0xFFFFFFFFu, owner_s == j));
                 if (lane == j) mine = cnt;
             }
-            if (lane < R.world) {
-                R.chunk[(long long)lane * R.n_warps + (i0 >> 5)] = mine;
-                if (mine) atomicAdd(&R.tile[lane * R.tiles + (int)(i0 >> 15)], mine);
-            }
+            if (lane < R.world) R.chunk[(long long)lane * R.n_warps + (i0 >> 5)] = mine;
             if (__any_sync(0xFFFFFFFFu, owner2 >= 0)) {          // a game ended in this warp (rare): the fresh board
                 const u32 p2 = warp_append(owner2, R.req_count);
                 if (owner2 >= 0) {
@@ -907,18 +903,17 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
     }
     flush_counters(c, counters);
 }
-// chunk[j][w] = records warp w sends to owner j  ->  exclusive prefix over the warps, the total to count[j].
-// Block (t, j) scans tile t (1024 warps) of owner j's row; the tile's first place = the sum of the tiles before it, which
-// k_routed_request accumulated in tile[j][t] (one atomicAdd per warp and owner, spread over world * tiles addresses).
-__global__ void __launch_bounds__(1024) k_routed_scan(u32* chunk, const u32* tile, long long n_warps, long long row, int tiles,
+// chunk[j][w] = records warp w sends to owner j  ->  place[j][w] = exclusive prefix over the warps, the total to count[j].
+// Block (t, j) scans tile t (1024 warps) of owner j's row; the tile's first place = the sum of everything before it,
+// which the block adds up itself (the rows are a few hundred KB and sit in L2; no atomics, nothing to clear).
+__global__ void __launch_bounds__(1024) k_routed_scan(const u32* chunk, u32* place, long long n_warps, long long row, int tiles,
                                                       unsigned long long* count) {
     __shared__ u32 warp_tot[32];
     __shared__ u32 base_sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = blockIdx.x, j = blockIdx.y;
-    const u32* ts = tile + (long long)j * tiles;
-    // sum of the tiles before this one (tiles <= 1024 * k: every thread takes a strided share)
+    const u32* col = chunk + (long long)j * row;
     u32 before = 0;
-    for (int q = threadIdx.x; q < t; q += 1024) before += ts[q];
+    for (long long c = threadIdx.x; c < (long long)t * 1024 && c < n_warps; c += 1024) before += col[c];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
     if (lane == 0) warp_tot[warp] = before;
@@ -932,7 +927,6 @@ __global__ void __launch_bounds__(1024) k_routed_scan(u32* chunk, const u32* til
     __syncthreads();
     const u32 base = base_sh;
     const long long c = (long long)t * 1024 + threadIdx.x;
-    u32* col = chunk + (long long)j * row;
     const u32 mine = c < n_warps ? col[c] : 0u;
     u32 x = mine;
 #pragma unroll
@@ -949,7 +943,7 @@ __global__ void __launch_bounds__(1024) k_routed_scan(u32* chunk, const u32* til
         if (lane == 31 && t == tiles - 1) count[j] = (unsigned long long)(base + z);
     }
     __syncthreads();
-    if (c < n_warps) col[c] = base + x - mine + warp_tot[warp];
+    if (c < n_warps) place[(long long)j * row + c] = base + x - mine + warp_tot[warp];
 }
 // after the barrier: every rank's record counts (peer memory) -> where my records start in every owner's sort input
 // (= the records of the lower ranks for that owner), and how many records this GPU will receive (to the host)
@@ -1034,13 +1028,11 @@ k_routed_rows(const Slot* shard, const __grid_constant__ RoutedServe V, const in
 }
 __global__ void __launch_bounds__(256)
 k_routed_records(const __grid_constant__ RoutedLocal R, long long n, float gamma) {
-    __shared__ u64* push_key[G2048_MAX_PEERS];
-    __shared__ float* push_val[G2048_MAX_PEERS];
+    __shared__ u64* push_rec[G2048_MAX_PEERS];
     __shared__ const uint2* reply1[G2048_MAX_PEERS];
     __shared__ u32 off[G2048_MAX_PEERS];
     if (threadIdx.x < G2048_MAX_PEERS) {
-        push_key[threadIdx.x] = R.push_key[threadIdx.x];
-        push_val[threadIdx.x] = R.push_val[threadIdx.x];
+        push_rec[threadIdx.x] = R.push_rec[threadIdx.x];
         reply1[threadIdx.x] = R.reply1[threadIdx.x];
         off[threadIdx.x] = (int)threadIdx.x < R.world ? R.off[threadIdx.x] : 0u;
     }
@@ -1050,23 +1042,69 @@ k_routed_records(const __grid_constant__ RoutedLocal R, long long n, float gamma
     for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {   // warp-uniform
         const long long i = i0 + lane;
         int owner = -1;
-        u64 sk = ~0ull;
-        float target = 0.f;
+        u64 rec = 0;
         if (i < n) {
-            sk = R.sk[i];
             const u32 h = R.req1[i], meta = R.meta[i];
             const uint2 ans = reply1[h >> kHandleBits][h & ((1u << kHandleBits) - 1u)];
-            target = td_target(gamma, R.reward[i], __uint_as_float(ans.y), (meta & 256u) != 0);
-            if (sk != ~0ull) owner = (int)(meta & 255u);
+            const float target = td_target(gamma, R.reward[i], __uint_as_float(ans.y), (meta & 256u) != 0);
+            if ((meta & 255u) != 255u) owner = (int)(meta & 255u);
+            rec = ((u64)R.sk[i] << 32) | (u64)__float_as_uint(target);
         }
         // place = my first place in the owner's input + the warp's first place among my records for it (k_routed_scan)
-        //         + the rank among the warp's lanes for that owner: ascending env order
+        //         + the rank among the warp's lanes for that owner: ascending env order.  One 8-byte store per record.
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, owner);
-        if (owner >= 0) {
-            const u32 p = off[owner] + R.chunk[(long long)owner * R.n_warps + (i0 >> 5)] + (u32)__popc(peers & ((1u << lane) - 1u));
-            push_key[owner][p] = sk;
-            push_val[owner][p] = target;
+        if (owner >= 0)
+            push_rec[owner][off[owner] + R.place[(long long)owner * R.n_warps + (i0 >> 5)] + (u32)__popc(peers & ((1u << lane) - 1u))] = rec;
+    }
+}
+// k_segment_apply / k_long_run_apply on packed records (key << 32 | target bits), sorted by key, equal keys in env order
+__global__ void __launch_bounds__(256)
+k_segment_apply_packed(Slot* tab, const u64* rec, float lr, long long n, u64* worklist, const int* abort_flag) {
+    if (abort_flag && *(const volatile int*)abort_flag != 0) return;   // a peer never reached the barrier: the records are not valid
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const u32 k = (u32)(rec[i] >> 32);
+        if (i > 0 && (u32)(rec[i - 1] >> 32) == k) continue;
+        long long j = i + 1;
+        while (j - i <= kInlineRun && j < n && (u32)(rec[j] >> 32) == k) ++j;
+        if (j - i > kInlineRun) {
+            const u64 w = atomicAdd((unsigned long long*)&worklist[0], 1ull);
+            worklist[1 + w] = (u64)i;
+            continue;
         }
+        float* qp = &tab[k >> 2].q[k & 3];
+        float q = *qp;
+        for (long long t = i; t < j; ++t) q = td_apply(q, lr, __uint_as_float((u32)rec[t]));
+        *qp = q;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_long_run_apply_packed(Slot* tab, const u64* rec, float lr, long long n, const u64* worklist, const int* abort_flag) {
+    if (abort_flag && *(const volatile int*)abort_flag != 0) return;
+    const int lane = threadIdx.x & 31;
+    const u64 n_warps = (u64)gridDim.x * (blockDim.x >> 5);
+    const u64 count = worklist[0];
+    for (u64 w = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += n_warps) {
+        long long j = (long long)worklist[1 + w];
+        const u32 k = (u32)(rec[j] >> 32);
+        float* qp = &tab[k >> 2].q[k & 3];
+        float q = *qp;
+        u64 r = (j + lane < n) ? rec[j + lane] : ((u64)~k << 32);
+        for (;;) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, (u32)(r >> 32) == k);
+            const int cnt = (m == 0xFFFFFFFFu) ? 32 : __ffs(~m) - 1;   // records of this run in the chunk (a prefix)
+            u64 rn = (u64)~k << 32;
+            if (cnt == 32 && j + 32 + lane < n) rn = rec[j + 32 + lane];
+            const float tt = __uint_as_float((u32)r);
+            if (cnt == 32) {
+#pragma unroll
+                for (int l = 0; l < 32; ++l) q = td_apply(q, lr, __shfl_sync(0xFFFFFFFFu, tt, l));
+            } else {
+                for (int l = 0; l < cnt; ++l) q = td_apply(q, lr, __shfl_sync(0xFFFFFFFFu, tt, l));
+                break;
+            }
+            j += 32; r = rn;
+        }
+        if (lane == 0) *qp = q;
     }
 }
 
@@ -1084,7 +1122,6 @@ k_apply_atomic(Slot* tab, const u64* sortkey, const float* target, float lr, lon
 // it itself; longer runs (early-game states shared by thousands of envs) are queued for k_long_run_apply, because
 // one thread walking a long run pays a full load latency per record (measured: 16 ms for the first step after a
 // reset of 8 M envs).  worklist[0] = number of queued runs (zeroed by the caller), worklist[1 + w] = index of the head.
-constexpr int kInlineRun = 8;
 __global__ void __launch_bounds__(256)
 k_segment_apply(Slot* tab, const u64* sortkey, const float* target, float lr, long long n, u64* worklist, int kshift,
                 const int* abort_flag = nullptr) {
@@ -2313,11 +2350,11 @@ G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, ui
 // ---- exact synchronous step on a sharded table, routed (see k_routed_request)
 // Layout of the buffer every rank shares with its peers (CUDA IPC), C = cap (the largest env count of any rank):
 //   [0, 128) barrier flags | [256, 384) request counts per owner | [512, 640) record counts per owner | from 1024:
-//   req_out[world][2C] u64 | reply1[world][2C] 8 B | reply2[world][2C] 16 B | sort input: keys[world * C] u64, targets[world * C] f32
+//   req_out[world][2C] u64 | reply1[world][2C] 8 B | reply2[world][2C] 16 B | sort input: records[world * C] u64
 namespace {
 constexpr size_t kRoutedHead = 1024, kRoutedReqCount = 256, kRoutedRecCount = 512;
 struct RoutedLayout {
-    size_t req, reply1, reply2, key_in, val_in, req_stride, r1_stride, r2_stride, total;
+    size_t req, reply1, reply2, key_in, req_stride, r1_stride, r2_stride, total;
 };
 RoutedLayout routed_layout(int world, int64_t cap) {
     RoutedLayout l{};
@@ -2329,8 +2366,7 @@ RoutedLayout routed_layout(int world, int64_t cap) {
     l.reply1 = l.req + (size_t)world * l.req_stride;
     l.reply2 = l.reply1 + (size_t)world * l.r1_stride;
     l.key_in = l.reply2 + (size_t)world * l.r2_stride;
-    l.val_in = l.key_in + align256((size_t)world * c * 8);
-    l.total = l.val_in + align256((size_t)world * c * 4);
+    l.total = l.key_in + align256((size_t)world * c * 8);
     return l;
 }
 }  // namespace
@@ -2344,7 +2380,6 @@ struct g2048_routed {
     PeerFlags F{};
     PeerWords rec_counts{};          // rank r's record counts (all owners)
     u64* key_in = nullptr;           // this GPU's sort input, in the shared buffer: the peers push their records into it
-    float* val_in = nullptr;
     u32* off = nullptr;              // local [world]
     char* local = nullptr;           // per-env state of the requester side + saved slots of the owner side
     void* sort_buf = nullptr;        // sort output + CUB's temporary storage
@@ -2383,7 +2418,7 @@ G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, in
     if (current_device_state(&D)) return nullptr;
     if (world < 1 || world > G2048_MAX_PEERS || (world & (world - 1)) || rank < 0 || rank >= world || cap < 1 ||
         2 * cap >= (1ll << kHandleBits) || (int64_t)world * cap >= (1ll << 32) || n_total < 1 || !peer_buffers || !shard ||
-        !pow2(slots_per_shard)) {
+        !pow2(slots_per_shard) || slots_per_shard > (1ull << 30)) {   // slot * 4 + action must fit 32 bits of a record
         fail(G2048_ERR_ARG, "g2048_routed_create: bad arguments");
         return nullptr;
     }
@@ -2399,9 +2434,7 @@ G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, in
     char* mine = (char*)peer_buffers[rank];
     const size_t c = (size_t)cap;
     const size_t n_warps = (c + 31) / 32;
-    const size_t tiles = (n_warps + 1023) / 1024;
-    const size_t local_bytes = align256(c * 8) + 4 * align256(c * 4) + align256(n_warps * world * 4) + align256(tiles * world * 4) +
-                               (size_t)world * align256(2 * c * 4) + 512;
+    const size_t local_bytes = 5 * align256(c * 4) + 2 * align256(n_warps * world * 4) + (size_t)world * align256(2 * c * 4) + 512;
     if (cudaMalloc(&r->local, local_bytes) != cudaSuccess || cudaMemset(r->local, 0, local_bytes) != cudaSuccess ||
         cudaHostAlloc(&r->host_total, 2 * sizeof(u64), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         fail((int)cudaGetLastError(), "g2048_routed_create: allocation");
@@ -2412,15 +2445,14 @@ G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, in
     r->host_total[0] = r->host_total[1] = 0;
     r->timed_out = (int*)(r->host_total + 1);
     char* p = r->local;
-    r->L.sk = (u64*)p; p += align256(c * 8);
+    r->L.sk = (u32*)p; p += align256(c * 4);
     r->L.req1 = (u32*)p; p += align256(c * 4);
     r->L.cur = (u32*)p; p += align256(c * 4);
     r->L.reward = (float*)p; p += align256(c * 4);
     r->L.meta = (u32*)p; p += align256(c * 4);
     r->L.chunk = (u32*)p; p += align256(n_warps * world * 4);
+    r->L.place = (u32*)p; p += align256(n_warps * world * 4);
     r->L.n_warps = (long long)n_warps;
-    r->L.tile = (u32*)p; p += align256(tiles * world * 4);
-    r->L.tiles = (int)tiles;
     for (int j = 0; j < world; ++j) { r->V.saved_slot[j] = (u32*)p; p += align256(2 * c * 4); }
     r->V.count_cache = (unsigned long long*)p; p += 256;
     r->off = (u32*)p;
@@ -2429,15 +2461,13 @@ G2048_API g2048_routed* g2048_routed_create(int rank, int world, int64_t cap, in
     r->L.req_count = (unsigned long long*)(mine + kRoutedReqCount);
     r->L.rec_count = (unsigned long long*)(mine + kRoutedRecCount);
     r->key_in = (u64*)(mine + lay.key_in);
-    r->val_in = (float*)(mine + lay.val_in);
     r->V.world = world;
     for (int j = 0; j < world; ++j) {
         char* peer = (char*)peer_buffers[j];
         r->L.req_out[j] = (u64*)(mine + lay.req + (size_t)j * lay.req_stride);
         r->L.reply1[j] = (const uint2*)(mine + lay.reply1 + (size_t)j * lay.r1_stride);
         r->L.reply2[j] = (const float4*)(mine + lay.reply2 + (size_t)j * lay.r2_stride);
-        r->L.push_key[j] = (u64*)(peer + lay.key_in);
-        r->L.push_val[j] = (float*)(peer + lay.val_in);
+        r->L.push_rec[j] = (u64*)(peer + lay.key_in);
         r->V.req[j] = (const u64*)(peer + lay.req + (size_t)rank * lay.req_stride);
         r->V.req_count[j] = (const unsigned long long*)(peer + kRoutedReqCount) + rank;
         r->V.reply1[j] = (uint2*)(peer + lay.reply1 + (size_t)rank * lay.r1_stride);
@@ -2511,7 +2541,6 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
     const int ge = grid_for(n, 256, D->sm_count), gs = grid_for(2 * r->cap, 256, D->sm_count);
 #define MARK(i) do { if (r->profile) cudaEventRecord(r->ev[i], st); } while (0)
     MARK(0);
-    CK(cudaMemsetAsync(r->L.tile, 0, (size_t)r->L.tiles * r->world * sizeof(u32), st));
     if (n) {
 #define REQ(F) k_routed_request<F, false><<<ge, 256, 0, st>>>(D->tables, (u64*)boards, (u64*)aux, score, r->L, n, eps_threshold(eps), \
                                                                seed, step_idx, env_id_base, (long long*)counters)
@@ -2520,8 +2549,9 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
         LAUNCH_CHECK("k_routed_request");
     }
     // (the peers read the record counts of the step before ahead of its last barrier)
-    k_routed_scan<<<dim3((unsigned)r->L.tiles, (unsigned)r->world), 1024, 0, st>>>(r->L.chunk, r->L.tile, (n + 31) / 32, r->L.n_warps,
-                                                                                    r->L.tiles, r->L.rec_count);
+    const long long warps = (n + 31) / 32;
+    const int tiles = (int)((warps + 1023) / 1024) > 0 ? (int)((warps + 1023) / 1024) : 1;
+    k_routed_scan<<<dim3((unsigned)tiles, (unsigned)r->world), 1024, 0, st>>>(r->L.chunk, r->L.place, warps, r->L.n_warps, tiles, r->L.rec_count);
     LAUNCH_CHECK("k_routed_scan");
     MARK(1);
     if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's requests and record counts are written
@@ -2534,10 +2564,17 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
     if ((rc = routed_check(r))) return rc;
     const long long total = (long long)r->host_total[0];
     if (total > (long long)r->world * r->cap) return fail(G2048_ERR_ARG, "g2048_routed_step: more records than envs");
-    Scratch sc{};
+    // the records are sorted as 64-bit KEYS on the bits of (slot * 4 + action) only: the target rides in the low half, and
+    // the sort is stable, so equal (slot, action) keep their ascending env order
+    int slot_bits = 0;
+    while ((1ull << slot_bits) < r->slots) ++slot_bits;
+    u64 *rec_out = nullptr, *worklist = nullptr;
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
     if (total > 0) {
-        const size_t m = (size_t)total, temp = cub_temp_bytes(total);
-        const size_t need = align256(m * 8) + align256(m * 4) + align256(temp) + 256;
+        const size_t m = (size_t)total;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const u64*)nullptr, (u64*)nullptr, (int64_t)total, 32, 34 + slot_bits, st));
+        const size_t need = align256(m * 8) + align256((m / kInlineRun + 2) * 8) + align256(temp_bytes) + 256;
         if (r->sort_bytes < need) {
             if (r->sort_buf) CK(cudaFree(r->sort_buf));
             r->sort_buf = nullptr;
@@ -2547,10 +2584,9 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
             r->sort_bytes = want;
         }
         char* p = (char*)r->sort_buf;
-        sc.key_in = r->key_in; sc.val_in = r->val_in;
-        sc.key_out = (u64*)p; p += align256(m * 8);
-        sc.val_out = (float*)p; p += align256(m * 4);
-        sc.cub_temp = p; sc.cub_bytes = temp;
+        rec_out = (u64*)p; p += align256(m * 8);
+        worklist = (u64*)p; p += align256((m / kInlineRun + 2) * 8);
+        temp = p;
     }
     MARK(3);
     k_routed_lookup<<<gs, 256, 0, st>>>(r->shard, r->slots - 1, r->V, (long long*)counters, D->abort_flag);
@@ -2566,7 +2602,13 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
     MARK(6);
     if ((rc = routed_barrier(r, D, st))) return rc;            // every rank's records are in their owner's sort input
     MARK(7);
-    if (total > 0 && (rc = apply_records(D, r->shard, r->slots, sc, total, lr, G2048_MODE_DETERMINISTIC, st, 0, D->abort_flag))) return rc;
+    if (total > 0) {
+        CK(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, (const u64*)r->key_in, rec_out, (int64_t)total, 32, 34 + slot_bits, st));
+        CK(cudaMemsetAsync(worklist, 0, sizeof(u64), st));
+        k_segment_apply_packed<<<grid_for(total, 256, D->sm_count), 256, 0, st>>>(r->shard, rec_out, lr, total, worklist, D->abort_flag);
+        k_long_run_apply_packed<<<D->sm_count * 4, 256, 0, st>>>(r->shard, rec_out, lr, total, worklist, D->abort_flag);
+        LAUNCH_CHECK("k_segment_apply_packed");
+    }
     MARK(8);
     k_routed_rows<<<gs, 256, 0, st>>>(r->shard, r->V, D->abort_flag);
     LAUNCH_CHECK("k_routed_rows");
