@@ -297,16 +297,18 @@ G2048_API int g2048_peer_barrier(uint64_t* const* flags, int rank, int world, ui
  *      (after a game over also the fresh board) to its list for the owner of that key          -- barrier --
  *   2. every owner pulls the lists written for it (coalesced NVLink reads), finds-or-inserts the keys in its own shard
  *      and pushes {slot, max Q} into the requester's answer buffer (coalesced NVLink writes)   -- barrier --
- *   3. every env forms r + gamma max Q(s') and appends its record to the list for the owner of s   -- barrier --
- *   4. every owner sorts and applies the records for its shard (ascending global env index per (s, a), as
- *      g2048_qtable_apply_owned) and pushes the rows as they are now for every request of 2.   -- barrier --
+ *   3. every env forms r + gamma max Q(s') and pushes its record (one 8-byte word) into the sort input of the owner
+ *      of s, at a place that makes the input ascending in the global env index                  -- barrier --
+ *   4. every owner sorts (stable, on the slot and action bits) and applies the records for its shard, each (s, a) in
+ *      ascending global env index, and pushes the rows as they are now for every request of 2.   -- barrier --
  * Same table as the single-GPU deterministic g2048_qlearn_step, bit for bit (states with a non-zero value; the fresh
- * board after a game over is inserted one step earlier here).  Only bulk lists cross NVLink: 48 bytes per env step.
+ * board after a game over is inserted one step earlier here).  Only bulk lists cross NVLink: 40 bytes per env step (key, {slot, max Q},
+ * 8-byte record, row).
  *
  * g2048_routed_buffer_bytes(world, cap): size of the zero-filled buffer every rank must allocate with
  * g2048_peer_alloc and share with all peers (cap = the largest env count of any rank).  g2048_routed_create: rank's
  * view; peer_buffers[j] (HOST array) = rank j's buffer as mapped in this process, `shard` = this rank's
- * slots_per_shard * 32 bytes of table, n_total = envs of all ranks (global env ids must stay below it; rank j's env
+ * slots_per_shard * 32 bytes of table (slots_per_shard <= 2^30), n_total = envs of all ranks (global env ids must stay below it; rank j's env
  * ids must all be smaller than rank j + 1's -- the owners apply the lists in rank order, which is then env order).
  * g2048_routed_prime: looks the envs' current boards up (call once after reset, on every rank, before the first step;
  * again whenever the boards were changed from outside).  g2048_routed_step: one env step of this rank's n envs; every
