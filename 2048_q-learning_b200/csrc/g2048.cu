@@ -823,10 +823,13 @@ __device__ __forceinline__ u32 warp_append(int list, unsigned long long* counts)
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     return (u32)base + (u32)__popc(peers & ((1u << lane) - 1u));
 }
-template <int FLAVOUR, bool PRIME>
-__global__ void __launch_bounds__(256)
+// SMEM_LUT (big batches): one block of 1024 threads per SM with the row LUT staged in shared memory, as k_env_step
+// (with the LUT in global memory the kernel needs 76 registers and runs latency-bound at 768 threads per SM)
+template <int FLAVOUR, bool PRIME, bool SMEM_LUT>
+__global__ void __launch_bounds__(SMEM_LUT ? kRolloutThreads : 256, SMEM_LUT ? 1 : 3)
 k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_constant__ RoutedLocal R, long long n,
                  u64 eps_thresh, u64 seed, u64 t, u64 id_base, long long* counters) {
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ u64* req_out[G2048_MAX_PEERS];
     __shared__ const uint2* reply1[G2048_MAX_PEERS];
     __shared__ const float4* reply2[G2048_MAX_PEERS];
@@ -836,7 +839,7 @@ k_routed_request(Tables T, u64* boards, u64* aux, int* score, const __grid_const
         reply2[threadIdx.x] = R.reply2[threadIdx.x];
     }
     __syncthreads();
-    Lut L = global_lut(T);
+    Lut L = SMEM_LUT ? stage_lut(T, smem) : global_lut(T);
     Counters c;
     const int lane = threadIdx.x & 31;
     const u32 owner_mask = (u32)R.world - 1u;
@@ -1719,6 +1722,8 @@ G2048_API int g2048_init(int device) {
     CK(cudaFuncSetAttribute(k_env_step<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_env_step<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_env_step<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_routed_request<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
+    CK(cudaFuncSetAttribute(k_routed_request<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_rollout_qlearn<0, true, LocalTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_rollout_qlearn<1, true, LocalTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
     CK(cudaFuncSetAttribute(k_rollout_qlearn<0, true, ShardedTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes));
@@ -2509,7 +2514,7 @@ G2048_API int g2048_routed_prime(g2048_routed* r, const uint64_t* boards, int64_
     CK(cudaMemsetAsync(r->L.rec_count, 0, 128, st));
     if ((rc = routed_barrier(r, D, st))) return rc;            // nobody still reads the counts of an earlier use
     if (n) {
-        k_routed_request<0, true><<<grid_for(n, 256, D->sm_count), 256, 0, st>>>(D->tables, (u64*)boards, nullptr, nullptr, r->L, n, 0, 0,
+        k_routed_request<0, true, false><<<grid_for(n, 256, D->sm_count), 256, 0, st>>>(D->tables, (u64*)boards, nullptr, nullptr, r->L, n, 0, 0,
                                                                                   0, 0, nullptr);
         LAUNCH_CHECK("k_routed_request");
     }
@@ -2542,9 +2547,11 @@ G2048_API int g2048_routed_step(g2048_routed* r, uint64_t* boards, uint64_t* aux
 #define MARK(i) do { if (r->profile) cudaEventRecord(r->ev[i], st); } while (0)
     MARK(0);
     if (n) {
-#define REQ(F) k_routed_request<F, false><<<ge, 256, 0, st>>>(D->tables, (u64*)boards, (u64*)aux, score, r->L, n, eps_threshold(eps), \
-                                                               seed, step_idx, env_id_base, (long long*)counters)
-        if (flavour == 0) REQ(0); else REQ(1);
+        const bool big = n >= kEnvStepSmemLutMinEnvs;   // enough work to amortise the 213 KB staging copy per SM
+#define REQ(F, SM) k_routed_request<F, false, SM><<<big ? D->sm_count : ge, big ? kRolloutThreads : 256, big ? kLutBytes : 0, st>>>( \
+        D->tables, (u64*)boards, (u64*)aux, score, r->L, n, eps_threshold(eps), seed, step_idx, env_id_base, (long long*)counters)
+        if (flavour == 0) { if (big) REQ(0, true); else REQ(0, false); }
+        else { if (big) REQ(1, true); else REQ(1, false); }
 #undef REQ
         LAUNCH_CHECK("k_routed_request");
     }

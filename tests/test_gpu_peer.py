@@ -400,7 +400,7 @@ def test_two_processes_owner_computes_with_a_4_step_window(tmp_path):
 
 
 # ---------------------------------------------------------------- exact synchronous step, routed (every table access local)
-def _routed_worker(rank, world, port, out, flavour, n_total=N_TOTAL, steps=None):
+def _routed_worker(rank, world, port, out, flavour, n_total=N_TOTAL, steps=None, cap=None):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -411,7 +411,7 @@ def _routed_worker(rank, world, port, out, flavour, n_total=N_TOTAL, steps=None)
     lo, hi = gdist.shard_range(n_total, rank, world)
     env = g2048.BatchedGame2048Env(hi - lo, flavour, seed=SEED, env_id_base=lo)
     env.reset()
-    shared = gdist.SharedQTable(g2048.lib(), torch.device("cuda", 0), CAP_ROUTED // world)
+    shared = gdist.SharedQTable(g2048.lib(), torch.device("cuda", 0), (cap or CAP_ROUTED) // world)
     rq = gdist.RoutedQLearning(env, shared, n_total, 0.1, 0.99, 0.4)
     handled = [rq.step() for _ in range(steps or STEPS_ROUTED)]
     torch.cuda.synchronize()
@@ -457,16 +457,18 @@ def test_two_processes_routed_step_equals_the_single_table_deterministic_step(tm
 
 
 @pytest.mark.timeout(600)
-def test_routed_step_with_many_envs_per_rank(tmp_path):
-    """40,000 envs per rank: the places of the records come from more than one tile of k_routed_scan."""
+@pytest.mark.parametrize("n_total,steps,cap,flavour", [(80001, 5, CAP_ROUTED, "penalty"), ((1 << 20) + 77, 3, 1 << 23, "penalty"),
+                                                       ((1 << 20) + 77, 3, 1 << 23, "nopenalty")])
+def test_routed_step_with_many_envs_per_rank(tmp_path, n_total, steps, cap, flavour):
+    """40,000 envs per rank: the places of the records come from more than one tile of k_routed_scan.  524,000 envs per
+    rank: k_routed_request runs with the row LUT staged in shared memory (the path BASELINE-size runs take)."""
     import torch.multiprocessing as mp
     import g2048
-    n_total, steps = 80001, 5
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_routed_worker, args=(2, port, str(tmp_path), "penalty", n_total, steps), nprocs=2, join=True)
-    boards1, keys1, rows1 = single_process_result(g2048, n_total, steps, "penalty", CAP_ROUTED)
+    mp.spawn(_routed_worker, args=(2, port, str(tmp_path), flavour, n_total, steps, cap), nprocs=2, join=True)
+    boards1, keys1, rows1 = single_process_result(g2048, n_total, steps, flavour, cap)
     d = [np.load(tmp_path / f"routed{r}.npz") for r in range(2)]
     for x in d:
         assert np.array_equal(x["boards"], boards1[int(x["lo"]):int(x["hi"])])
