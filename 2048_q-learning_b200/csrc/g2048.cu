@@ -916,7 +916,9 @@ __global__ void __launch_bounds__(1024) k_routed_scan(const u32* chunk, u32* pla
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = blockIdx.x, j = blockIdx.y;
     const u32* col = chunk + (long long)j * row;
     u32 before = 0;
-    for (long long c = threadIdx.x; c < (long long)t * 1024 && c < n_warps; c += 1024) before += col[c];
+    const long long stop = (long long)t * 1024 < n_warps ? (long long)t * 1024 : n_warps;
+#pragma unroll 8
+    for (long long c = threadIdx.x; c < stop; c += 1024) before += col[c];   // (independent loads: eight in flight per thread)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
     if (lane == 0) warp_tot[warp] = before;
