@@ -1,21 +1,25 @@
-"""Env shards over the GPUs of one box + the Q-target exchange (one process per GPU, torch.distributed).
+"""Env shards over the GPUs of one box + the ways the GPUs learn together (one process per GPU, torch.distributed).
 
 Envs are independent (the reference has exactly one, main.py:66), so rank r owns the contiguous global env
 ids [lo, hi) and its Philox draws are keyed by the GLOBAL env id: results do not depend on the sharding.
-The Q-table is replicated; the only exchange step is the list of (state key, action, target) records of one
-synchronous step (16 B per transition, fixed size per rank): `all_gather` in rank order = ascending global
-env id, then every replica applies the whole list with the same deterministic kernel (sort by
-(state, action), then each run applied in order), so all replicas stay identical and equal to the 1-GPU result.
-Two transports on GPUs:
-  "peer"  records are written into CUDA-IPC shared device memory; after a flag barrier in that memory every rank's
-          apply kernel reads each record straight from its owner over NVLink 5 / NVSwitch (gather fused into the
-          lookup kernel, no collective call, no gathered copy) -- `PeerRecordBuffers`;
-  "nccl"  one `all_gather_into_tensor` of the packed 16-byte records, then the same apply kernel on the result.
-The same class runs on gloo for the CPU tests with an oracle-backed engine (plain emit()/apply() protocol).
 
-The fused asynchronous rollout (agent.rollout) has no exchange step: across GPUs it runs as independent
-replicas (DESIGN.md "Multi-GPU": a replicated table cannot scale an exact per-step exchange, every replica
-must apply every rank's updates).
+  ShardedQLearning        replicated tables, exact: the (state key, action, target) records of one synchronous step
+                          (16 B per transition) are exchanged -- transport "peer": every rank's apply kernel reads
+                          each record straight from its owner over NVLink 5 / NVSwitch (CUDA-IPC buffers, flag
+                          barrier, no collective call); "nccl": one all_gather_into_tensor; "auto": generic engines
+                          (the oracle on gloo in the CPU tests) -- and every replica applies the whole list with the
+                          same deterministic kernel.  Cannot scale (every replica applies every record); kept for comparison.
+  SharedQTable            ONE table for the box, shard j in the HBM of rank j; the fused asynchronous rollout reaches
+                          remote slots itself (NVLink loads and atomics inside the kernel).
+  OwnerComputesQLearning  exact synchronous steps on that table: lookups are remote, each record goes to the owner of
+                          its slot, every GPU sorts and applies only its share (optionally every K steps).
+  RoutedQLearning         the same exact step with every table access LOCAL: keys travel to the owner as bulk lists,
+                          {slot, max Q} and rows come back, records are pushed into the owner's sort input in env
+                          order (g2048_routed_*) -- the fastest exact mode.
+  GradientAllReduce       data-parallel DQN: one flat gradient buffer, one NCCL all-reduce per training step.
+
+The fused asynchronous rollout on a LOCAL table (agent.rollout) has no exchange step: across GPUs it runs as independent
+replicas.
 """
 from __future__ import annotations
 

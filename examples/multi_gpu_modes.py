@@ -77,6 +77,20 @@ def main():
         print(f"[rank {rank}] owner: table digest {float(t):.6f} (the same number as 'exact')")
         oc.close()
         shared.close()
+        # the same exact step routed: no GPU touches another GPU's shard, only bulk lists cross NVLink
+        env = fresh()
+        shared = gdist.SharedQTable(g2048.lib(), dev, (1 << 24) // world)
+        rq = gdist.RoutedQLearning(env, shared, n_total, 0.1, 0.99, 0.1)
+        for _ in range(16):
+            rq.step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        _, rows = shared.export_local()
+        t = torch.tensor([float(rows.astype("float64").sum())], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        print(f"[rank {rank}] routed: table digest {float(t):.6f} (the same number again)")
+        rq.close()
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
 

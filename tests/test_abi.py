@@ -119,3 +119,15 @@ def test_ctypes_signatures_agree_with_the_header():
         for i, (p, a) in enumerate(zip(plist, argtypes)):
             assert kind(p + " x" if " " not in p else p) == ctype_kind[a], (name, i, p, a)
         assert kind(ret + " x") == ctype_kind[restype], (name, ret, restype)
+
+
+def test_routed_buffer_size_is_a_pure_host_function():
+    """g2048_routed_buffer_bytes needs no device: 0 for bad arguments, 256-byte granular, grows with world and cap, and
+    holds what the header says (requests 2 x 8 B, answers 2 x (8 + 16) B per env and peer, records 8 B per env and peer)."""
+    L = _lib.lib()
+    f = L.g2048_routed_buffer_bytes
+    assert f(0, 100) == 0 and f(17, 100) == 0 and f(2, 0) == 0
+    a, b, c = f(2, 1 << 20), f(8, 1 << 20), f(8, 1 << 21)
+    assert a % 256 == 0 and a < b < c
+    per_env_and_peer = 2 * 8 + 2 * 8 + 2 * 16 + 8
+    assert abs(b - 1024 - 8 * (1 << 20) * per_env_and_peer) < 8 * 5 * 256
