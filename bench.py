@@ -10,9 +10,10 @@ HBM.  One bench "step" = one fused call g2048_rollout_qlearn advancing every env
 steps (each env step = choose_action + env.step + update_q_value, i.e. one Q-update; every update is applied,
 `lost_update_fraction` is 0).  Multi-GPU `value` = weak scaling: every rank runs its own env shard (global env
 ids) against its own table replica, no data-path collective; with N > 1 the same line carries `shared_learning`:
-BASELINE configs[3] (2^23 envs in total learning ONE table across the GPUs: exact owner-computes exchange every step
-and every 16 steps, and the asynchronous table sharded over NVLink), each with its table digest compared with the
-1-GPU run (DESIGN.md "Multi-GPU").
+BASELINE configs[3] (2^23 envs in total learning ONE table across the GPUs: the exact routed step -- lookups and
+records travel to the owner of a state as bulk lists --, the exact owner-computes exchange every step and every 16
+steps, and the asynchronous table sharded over NVLink), the exact modes with their table digest compared with the
+1-GPU run (DESIGN.md "Multi-GPU"), all timed after 160 warm-up env steps.
 
 Prints ONE JSON line (rank 0).  `value`: device-resident throughput (CUDA events, max over ranks);
 `e2e`: the same metric through the host-buffer C-ABI call g2048_ctx_rollout_qlearn with pinned HOST buffers,
