@@ -453,8 +453,11 @@ def main():
         L.g2048_ctx_destroy(ctx)                   # the 64 GiB replica table makes room for the shared tables
         ctx = None
         torch.cuda.empty_cache()
-        shared_learning = shared_learning_measurement(torch, dist, g2048, dev, rank, world, args.shared_envs,
-                                                      max_over_ranks, barrier)
+        try:
+            shared_learning = shared_learning_measurement(torch, dist, g2048, dev, rank, world, args.shared_envs,
+                                                          max_over_ranks, barrier)
+        except Exception as e:   # (a peer barrier that timed out raises on every rank) the main line is still reported
+            shared_learning = [{"error": f"{type(e).__name__}: {e}"}]
     extras = {}
     if args.exchange:
         sync = sync_exchange_measurement(torch, dist, g2048, dev, rank, world, args.exchange_envs or min(n, 1 << 20),
